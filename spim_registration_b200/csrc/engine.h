@@ -1,0 +1,330 @@
+// Host-side driver of the FFT-convolution engine: FFT size selection, stage planning, twiddle
+// tables, and the five-sweep convolution built from the kernel bodies in kernels.h.
+#pragma once
+#include "kernels.h"
+#include "runtime.h"
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
+
+namespace spim {
+
+enum KernelId { K_XFWD = 0, K_YFWD, K_ZMID, K_YINV, K_XINV, K_ZFWD, K_MISC, K_COUNT };
+
+// ------------------------------------------------------------------------------------------
+// stage planning
+// ------------------------------------------------------------------------------------------
+inline bool is_smooth(int n, int maxp) {
+    if (n < 1) return false;
+    for (int p : {2, 3, 5, 7, 11, 13}) {
+        if (p > maxp) break;
+        while (n % p == 0) n /= p;
+    }
+    return n == 1;
+}
+
+// factor n into <= MAX_STAGES radices from {2..16}: fewest stages, then smallest radix sum
+inline bool plan_radices(int n, std::vector<int>& best) {
+    static const int allowed[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    std::vector<int> cur;
+    int best_sum = 1 << 30;
+    best.clear();
+    struct Rec {
+        static void go(int rem, int start, std::vector<int>& cur, std::vector<int>& best, int& best_sum) {
+            if (rem == 1) {
+                int sum = 0;
+                for (int r : cur) sum += r;
+                if (best.empty() || cur.size() < best.size() || (cur.size() == best.size() && sum < best_sum)) {
+                    best = cur;
+                    best_sum = sum;
+                }
+                return;
+            }
+            if ((int)cur.size() >= MAX_STAGES) return;
+            if (!best.empty() && cur.size() + 1 > best.size()) return;
+            for (int i = start; i < 15; ++i) {
+                int r = allowed[i];
+                if (rem % r) continue;
+                cur.push_back(r);
+                go(rem / r, i, cur, best, best_sum);
+                cur.pop_back();
+            }
+        }
+    };
+    if (n == 1) return false;
+    Rec::go(n, 0, cur, best, best_sum);
+    return !best.empty();
+}
+
+// smallest supported FFT length >= min_n (even if need_even).  7-smooth sizes are preferred; an
+// 11/13-smooth size is taken only when it is >3% shorter.
+inline int choose_fft_size(int min_n, bool need_even) {
+    if (min_n < 2) min_n = 2;
+    if (need_even && min_n < 4) min_n = 4;
+    int best7 = -1, best13 = -1;
+    for (int n = min_n; n < 4 * min_n + 64; ++n) {
+        if (need_even && (n & 1)) continue;
+        const int m = need_even ? n / 2 : n;
+        std::vector<int> r;
+        if (best13 < 0 && is_smooth(n, 13) && plan_radices(m, r)) best13 = n;
+        if (is_smooth(n, 7) && plan_radices(m, r)) { best7 = n; break; }
+    }
+    if (best7 < 0) return best13;
+    if (best13 > 0 && best13 < 0.97 * best7) return best13;
+    return best7;
+}
+
+struct FftPlanHost {
+    FftPlanDev dev;
+    float2* d_tw = nullptr;
+    std::vector<int> radices;
+    std::vector<unsigned short> pos;   // pos[k]: row that holds frequency k after the DIF stages
+
+    void create(int n) {
+        if (!plan_radices(n, radices)) throw rt::Error("unsupported FFT length " + std::to_string(n));
+        memset(&dev, 0, sizeof(dev));
+        dev.n = n;
+        dev.nstages = (int)radices.size();
+        int prod = 1;
+        for (int s = 0; s < dev.nstages; ++s) {
+            dev.radix[s] = radices[s];
+            prod *= radices[s];
+            dev.M[s] = n / prod;
+            dev.magicM[s] = dev.M[s] > 1 ? (uint32_t)((0x100000000ull / (uint64_t)dev.M[s]) + 1ull) : 0u;
+        }
+        std::vector<float2> tw(n);
+        for (int t = 0; t < n; ++t) {
+            const double a = -2.0 * 3.14159265358979323846 * (double)t / (double)n;
+            tw[t] = make_float2((float)cos(a), (float)sin(a));
+        }
+        d_tw = (float2*)rt::dmalloc(sizeof(float2) * n);
+        rt::h2d(d_tw, tw.data(), sizeof(float2) * n, 0);
+        rt::stream_sync(0);
+        dev.tw = d_tw;
+        pos.resize(n);
+        for (int k = 0; k < n; ++k) {
+            int rem = k, p = 0;
+            for (int s = 0; s < dev.nstages; ++s) {
+                const int d = rem % dev.radix[s];
+                rem /= dev.radix[s];
+                p += d * dev.M[s];
+            }
+            pos[k] = (unsigned short)p;
+        }
+    }
+    void destroy() { rt::dfree(d_tw); d_tw = nullptr; }
+};
+
+inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
+
+// ------------------------------------------------------------------------------------------
+// geometry of one convolution: image n, kernel k, padded circular size P per axis ([z,y,x])
+// ------------------------------------------------------------------------------------------
+struct SrcDesc {            // real input volume
+    const float* p = nullptr;
+    int dims[3] = {0, 0, 0};    // array dims  [z,y,x]
+    int origin[3] = {0, 0, 0};  // index = logical coordinate + origin
+    int ext = EXT_ZERO;
+    float ext_value = 0.f;
+};
+
+struct EpiDesc {            // what XInv does with the result
+    int epi = EPI_STORE;
+    float* dst = nullptr;
+    int dst_dims[3] = {0, 0, 0};
+    int dst_origin[3] = {0, 0, 0};
+    const float* img = nullptr;
+    const float* weight = nullptr;
+    float const_weight = 1.f;
+    double lambda = 0.0;
+    float min_value = 1e-4f;
+    int gen2_quotient = 1;
+    double* stat_sum = nullptr;
+    unsigned int* stat_max = nullptr;
+};
+
+class ConvPlan {
+public:
+    int n[3], k[3], hp[3], hm[3], P[3];
+    int pitch = 0, N2 = 0;
+    FftPlanHost fx, fy, fz;
+    unsigned short* d_pos = nullptr;
+    float2* d_wx = nullptr;
+    float2* spec = nullptr;       // work spectrum
+    size_t spec_elems = 0;
+    float* d_kernel = nullptr;    // staging for kernel uploads
+    size_t kernel_cap = 0;
+    rt::KernelTimer* timer = nullptr;
+
+    // periodic_exact: when the image dims themselves are supported FFT sizes, use P = n with no halo
+    // (pure circular convolution, the legacy JNA semantics on FFT-friendly block sizes)
+    void create(const int n_[3], const int k_[3], bool periodic_exact = false, bool alloc_spec = true) {
+        for (int d = 0; d < 3; ++d) {
+            n[d] = n_[d]; k[d] = k_[d];
+            hp[d] = k[d] / 2;
+            hm[d] = k[d] - 1 - k[d] / 2;
+            const bool even = (d == 2);
+            bool exact = false;
+            if (periodic_exact && n[d] >= 2 && n[d] >= k[d]) {
+                std::vector<int> r;
+                if ((!even || (n[d] % 2 == 0)) && is_smooth(n[d], 13) && plan_radices(even ? std::max(1, n[d] / 2) : n[d], r) ) exact = true;
+                if (even && n[d] == 2) exact = false;
+            }
+            if (exact) { P[d] = n[d]; hp[d] = hm[d] = 0; }
+            else P[d] = choose_fft_size(std::max(n[d] + k[d] - 1, even ? 4 : 2), even);
+        }
+        N2 = P[2] / 2;
+        pitch = ((N2 + 1 + TC - 1) / TC) * TC;
+        fx.create(N2); fy.create(P[1]); fz.create(P[0]);
+        const size_t need = std::max({(size_t)N2, (size_t)P[1], (size_t)P[0]}) * TC * sizeof(float2) + 512;
+        if (need > rt::max_smem()) throw rt::Error("FFT axis too long for one shared-memory tile");
+        d_pos = (unsigned short*)rt::dmalloc(sizeof(unsigned short) * N2);
+        rt::h2d(d_pos, fx.pos.data(), sizeof(unsigned short) * N2, 0);
+        const int nk = N2 / 2 + 1;
+        std::vector<float2> wx(nk);
+        for (int t = 0; t < nk; ++t) {
+            const double a = -2.0 * 3.14159265358979323846 * (double)t / (double)P[2];
+            wx[t] = make_float2((float)cos(a), (float)sin(a));
+        }
+        d_wx = (float2*)rt::dmalloc(sizeof(float2) * nk);
+        rt::h2d(d_wx, wx.data(), sizeof(float2) * nk, 0);
+        rt::stream_sync(0);
+        spec_elems = (size_t)pitch * P[1] * P[0];
+        if (alloc_spec) spec = (float2*)rt::dmalloc(spec_elems * sizeof(float2));
+    }
+    void destroy() {
+        fx.destroy(); fy.destroy(); fz.destroy();
+        rt::dfree(d_pos); rt::dfree(d_wx); rt::dfree(spec); rt::dfree(d_kernel);
+        d_pos = nullptr; d_wx = nullptr; spec = nullptr; d_kernel = nullptr; kernel_cap = 0;
+    }
+    size_t spec_bytes() const { return spec_elems * sizeof(float2); }
+    double kernel_scale() const { return 1.0 / (4.0 * (double)P[0] * (double)P[1] * (double)P[2]); }
+    long long padded_min_voxels() const {   // Np of SURVEY section 8d
+        return (long long)(n[0] + k[0] - 1) * (n[1] + k[1] - 1) * (n[2] + k[2] - 1);
+    }
+
+    // ---- sweeps -------------------------------------------------------------------------
+    struct Geom { int n[3], hp[3], hm[3]; };   // logical size + halos of whatever is being transformed
+
+    void x_forward(const SrcDesc& src, const Geom& g, float2* out, rt::Stream st) {
+        XFwdParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = src.p;
+        p.sz = src.dims[0]; p.sy = src.dims[1]; p.sx = src.dims[2];
+        p.oz = src.origin[0]; p.oy = src.origin[1]; p.ox = src.origin[2];
+        p.nz = g.n[0]; p.ny = g.n[1]; p.nx = g.n[2];
+        p.hpz = g.hp[0]; p.hpy = g.hp[1]; p.hpx = g.hp[2];
+        p.hmz = g.hm[0]; p.hmy = g.hm[1]; p.hmx = g.hm[2];
+        p.ext = src.ext; p.ext_value = src.ext_value;
+        p.Pz = P[0]; p.Py = P[1]; p.Px = P[2]; p.pitch = pitch;
+        p.spec = out;
+        p.plan = fx.dev; p.pos = d_pos; p.wx = d_wx;
+        p.LY = g.n[1] + g.hp[1] + g.hm[1];
+        p.LZ = g.n[0] + g.hp[0] + g.hm[0];
+        p.nlines = (long long)p.LY * p.LZ;
+        p.magic_m0 = magic_for(fx.dev.M[0]);
+        p.nk = N2 / 2 + 1;
+        p.magic_nk = magic_for(p.nk);
+        p.src_vec_ok = ((reinterpret_cast<uintptr_t>(src.p) & 7) == 0) && (p.sx % 2 == 0) && (p.ox % 2 == 0);
+        const long long grid = (p.nlines + TC - 1) / TC;
+        const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
+        if (timer) timer->begin(K_XFWD, st);
+        rt::launch<XFwd>(p, grid, kThreads, smem, st);
+        if (timer) timer->end(K_XFWD, st);
+    }
+
+    void col_pass(int id, float2* data, const float2* khat, int axis /*1=y,0=z*/, int mode, const Geom& g,
+                  int out_rows, int outer_valid_lo, int outer_count, int outer_P, rt::Stream st) {
+        ColPassParams p;
+        memset(&p, 0, sizeof(p));
+        p.data = data; p.khat = khat;
+        p.plan = (axis == 1) ? fy.dev : fz.dev;
+        p.ntx = pitch / TC;
+        if (axis == 1) { p.row_stride = pitch; p.outer_stride = (long long)pitch * P[1]; }
+        else { p.row_stride = (long long)pitch * P[1]; p.outer_stride = pitch; }
+        // outer index map: first outer_valid_lo indices map to themselves, the rest to the top of the axis
+        p.outer_split = outer_valid_lo;
+        p.outer_shift = outer_P - outer_count;
+        const int Pa = P[axis];
+        if (mode == COL_INV) { p.va = Pa; p.vb = Pa; }
+        else { p.va = g.n[axis] + g.hp[axis]; p.vb = Pa - g.hm[axis]; }
+        p.sa = out_rows;
+        p.mode = mode;
+        const long long grid = (long long)p.ntx * outer_count;
+        const size_t smem = (size_t)Pa * TC * sizeof(float2);
+        if (timer) timer->begin(id, st);
+        rt::launch<ColPass>(p, grid, kThreads, smem, st);
+        if (timer) timer->end(id, st);
+    }
+
+    void x_inverse(const float2* in, const EpiDesc& e, rt::Stream st) {
+        XInvParams p;
+        memset(&p, 0, sizeof(p));
+        p.spec = in; p.pitch = pitch; p.Px = P[2]; p.Py = P[1];
+        p.nz = n[0]; p.ny = n[1]; p.nx = n[2];
+        p.plan = fx.dev; p.pos = d_pos; p.wx = d_wx;
+        p.magic_m0 = magic_for(fx.dev.M[0]);
+        p.nk = N2 / 2 + 1;
+        p.magic_nk = magic_for(p.nk);
+        p.nlines = (long long)n[0] * n[1];
+        p.dst = e.dst;
+        p.dsy = e.dst_dims[1]; p.dsx = e.dst_dims[2];
+        p.doz = e.dst_origin[0]; p.doy = e.dst_origin[1]; p.dox = e.dst_origin[2];
+        p.epi = e.epi; p.img = e.img; p.weight = e.weight; p.const_weight = e.const_weight;
+        p.lambda = e.lambda; p.min_value = e.min_value; p.gen2_quotient = e.gen2_quotient;
+        p.stat_sum = e.stat_sum; p.stat_max = e.stat_max;
+        p.dst_vec_ok = ((reinterpret_cast<uintptr_t>(e.dst) & 7) == 0) && (p.dsx % 2 == 0) && (p.dox % 2 == 0);
+        p.aux_vec_ok = (n[2] % 2 == 0) && ((reinterpret_cast<uintptr_t>(e.img) & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(e.weight) & 7) == 0);
+        const long long grid = (p.nlines + TC - 1) / TC;
+        const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
+        if (timer) timer->begin(K_XINV, st);
+        rt::launch<XInv>(p, grid, kThreads, smem, st);
+        if (timer) timer->end(K_XINV, st);
+    }
+
+    // spectrum of a (host) kernel, pre-scaled by 1/(4 Px Py Pz), in the layout the mid pass expects
+    void kernel_spectrum(const float* h_kernel, float2* khat, rt::Stream st) {
+        const size_t kn = (size_t)k[0] * k[1] * k[2];
+        std::vector<float> scaled(kn);
+        const double s = kernel_scale();
+        for (size_t i = 0; i < kn; ++i) scaled[i] = (float)((double)h_kernel[i] * s);
+        if (kn > kernel_cap) {
+            rt::dfree(d_kernel);
+            d_kernel = (float*)rt::dmalloc(kn * sizeof(float));
+            kernel_cap = kn;
+        }
+        rt::h2d(d_kernel, scaled.data(), kn * sizeof(float), st);
+        rt::stream_sync(st);   // 'scaled' goes out of scope
+        SrcDesc src;
+        src.p = d_kernel;
+        Geom g;
+        for (int d = 0; d < 3; ++d) {
+            const int c = k[d] / 2;
+            src.dims[d] = k[d];
+            src.origin[d] = c;          // logical coordinate a in [-c, k-1-c] -> index a + c
+            g.n[d] = k[d] - c; g.hp[d] = 0; g.hm[d] = c;
+        }
+        src.ext = EXT_ZERO;
+        x_forward(src, g, khat, st);
+        const int LZ = g.n[0] + g.hm[0];
+        col_pass(K_YFWD, khat, nullptr, 1, COL_FWD, g, P[1], g.n[0], LZ, P[0], st);
+        col_pass(K_ZFWD, khat, nullptr, 0, COL_FWD, g, P[0], P[1], P[1], P[1], st);
+    }
+
+    // out = ext(src) (*) kernel, cropped to the logical image, through the epilogue
+    void convolve(const SrcDesc& src, const float2* khat, const EpiDesc& e, rt::Stream st) {
+        Geom g;
+        for (int d = 0; d < 3; ++d) { g.n[d] = n[d]; g.hp[d] = hp[d]; g.hm[d] = hm[d]; }
+        x_forward(src, g, spec, st);
+        const int LZ = n[0] + hp[0] + hm[0];
+        col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + hp[0], LZ, P[0], st);
+        col_pass(K_ZMID, spec, khat, 0, COL_MID, g, n[0], P[1], P[1], P[1], st);
+        col_pass(K_YINV, spec, nullptr, 1, COL_INV, g, n[1], n[0], n[0], P[0], st);
+        x_inverse(spec, e, st);
+    }
+};
+
+}  // namespace spim

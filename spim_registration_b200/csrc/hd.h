@@ -1,0 +1,45 @@
+// Portability shim: the kernel bodies in this directory are written once and compiled
+//  (a) by nvcc for sm_100a  -> the product library, and
+//  (b) by g++ with -DSPIM_HOST_EMU -> a *test-only* emulator (tests/emu) that executes each
+//      thread block's phases serially on the CPU so index math can be debugged without a GPU.
+// The emulator is never loaded by the package; the product path has no CPU fallback.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(SPIM_HOST_EMU)
+
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#define SPIM_DEV inline
+#define SPIM_HD inline
+#define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)
+#define SPIM_BARRIER() ((void)0)
+#define SPIM_NTHREADS 1
+#define SPIM_TID 0
+template <class T> static inline T spim_ldg(const T* p) { return *p; }
+static inline uint32_t spim_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+static inline float spim_fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float spim_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float spim_fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float spim_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+
+#else
+
+#include <cuda_runtime.h>
+#define SPIM_DEV __device__ __forceinline__
+#define SPIM_HD __host__ __device__ __forceinline__
+#define SPIM_FOR_ITEMS(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)
+#define SPIM_BARRIER() __syncthreads()
+#define SPIM_NTHREADS ((int)blockDim.x)
+#define SPIM_TID ((int)threadIdx.x)
+template <class T> __device__ __forceinline__ T spim_ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t spim_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// explicitly un-fused fp32 ops: the reference's Java float arithmetic has no FMA contraction
+__device__ __forceinline__ float spim_fadd_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float spim_fsub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float spim_fmul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float spim_fdiv_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+#endif

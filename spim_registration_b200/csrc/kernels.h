@@ -1,0 +1,658 @@
+// Kernel bodies of the FFT-convolution hot path.
+//
+// Data layout in HBM:
+//   real volumes      [z][y][x] fp32, x contiguous (exactly what the JNA boundary passes)
+//   spectrum / work   [zp][yp][pitch] float2, pitch = roundup(Px/2+1, 16); x-frequencies in natural
+//                     order, y- and z-frequencies in the digit-reversed order the in-place
+//                     decimation-in-frequency stages leave them in (the inverse passes are
+//                     decimation-in-time and consume exactly that order, so no permutation pass
+//                     ever touches HBM; the kernel spectrum is produced by the same forward passes
+//                     and therefore sits in the same order).
+//
+// One FFT-convolution = five sweeps, each one read + one write of the volume:
+//   XFwd   real -> half spectrum along x; out-of-bounds extension (mirror / constant / periodic /
+//          zero) is applied on load, the padded volume never exists in memory
+//   ColPass(fwd, y)   in-place column FFT over tiles of 16 x-frequencies
+//   ColPass(mid, z)   forward z-FFT, multiply with the kernel spectrum, inverse z-FFT in one kernel
+//   ColPass(inv, y)
+//   XInv   half spectrum -> real along x with the fused epilogue: plain store, ratio img/blur
+//          (computeQuotient) or the weighted Tikhonov update of psi + change statistics
+//          (computeFinalValues)
+//
+// Every block works on a shared-memory tile [rows][16] of float2.  A stage is a set of independent
+// radix-R butterflies executed in place; the first stage reads its operands straight from global
+// memory and the last one writes straight back, so a tile makes 2(S-1) shared-memory round trips
+// for S stages.  Bodies are written as "phases" of independent items separated by barriers so the
+// same source runs under the CPU emulator used by the unit tests (see hd.h).
+#pragma once
+#include "fft_math.h"
+
+namespace spim {
+
+constexpr int TC = 16;            // tile columns (float2) = one 128-byte segment per row
+constexpr int MAX_STAGES = 6;
+constexpr int kThreads = 256;
+
+enum ExtMode { EXT_ZERO = 0, EXT_CONSTANT = 1, EXT_MIRROR_SINGLE = 2, EXT_MIRROR_DOUBLE = 3, EXT_PERIODIC = 4 };
+enum EpiMode { EPI_STORE = 0, EPI_RATIO = 1, EPI_UPDATE = 2 };
+enum ColMode { COL_FWD = 0, COL_INV = 1, COL_MID = 2 };
+
+struct FftPlanDev {
+    int n;
+    int nstages;
+    int radix[MAX_STAGES];
+    int M[MAX_STAGES];            // sub-transform length after stage s: n / (radix[0]*...*radix[s])
+    uint32_t magicM[MAX_STAGES];  // floor(2^32 / M) + 1, for m / M with m < 2^16
+    const float2* tw;             // exp(-2 pi i t / n), t in [0, n)
+};
+
+SPIM_DEV int fastdiv(int m, uint32_t magic) { return (int)spim_umulhi((uint32_t)m, magic); }
+
+// ---------------------------------------------------------------------------------------------
+// out-of-bounds rules
+// ---------------------------------------------------------------------------------------------
+// logical coordinate a (any integer) -> index in [0,n) or -1 when the rule yields a constant
+SPIM_HD int ext_map(int a, int n, int mode) {
+    if ((unsigned)a < (unsigned)n) return a;
+    switch (mode) {
+        case EXT_PERIODIC: {
+            int m = a % n;
+            return m < 0 ? m + n : m;
+        }
+        case EXT_MIRROR_SINGLE: {
+            if (n == 1) return 0;
+            int p = 2 * (n - 1);
+            int m = a % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - m;
+        }
+        case EXT_MIRROR_DOUBLE: {
+            int p = 2 * n;
+            int m = a % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - 1 - m;
+        }
+        default: return -1;
+    }
+}
+
+constexpr int kGap = -0x40000000;
+// position u in the circular padded axis of length P -> logical coordinate, or kGap in the zero gap.
+// [0, n+hp) holds coordinates 0..n+hp-1, [P-hm, P) holds coordinates -hm..-1.
+SPIM_HD int pad_to_coord(int u, int n, int hp, int hm, int P) {
+    if (u < n + hp) return u;
+    if (u >= P - hm) return u - P;
+    return kGap;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic in-place radix stage on a [rows][16] tile
+// ---------------------------------------------------------------------------------------------
+struct GRows {          // the global-memory side of a column tile
+    float2* p;          // element (row 0, col 0)
+    long long stride;   // float2 units between consecutive rows
+    int va, vb;         // rows that hold data on load: [0, va) U [vb, n); others read as zero
+    int sa;             // rows written on store: [0, sa)
+};
+
+template <int R, bool INV>
+SPIM_DEV void apply_twiddles(float2 (&a)[R], const float2* tw, int t1) {
+    // a[p] *= w^(p), w = tw[t1] ; indices t1*p < n by construction
+#pragma unroll
+    for (int p = 1; p < R; ++p) {
+        const float2 w = spim_ldg(tw + t1 * p);
+        a[p] = INV ? cmulc(a[p], w) : cmul(a[p], w);
+    }
+}
+
+template <int R, bool INV>
+SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float2* tile, int swz, int src_g, int dst_g, const GRows& g) {
+    const int M = pl.M[s];
+    const int L = M * R;
+    const int nb = pl.n / R;
+    const int ts = pl.n / L;
+    const uint32_t magic = pl.magicM[s];
+    SPIM_FOR_ITEMS(i, nb * TC) {
+        const int c = i & (TC - 1);
+        const int m = i >> 4;
+        const int blk = (M == 1) ? m : fastdiv(m, magic);
+        const int j = m - blk * M;
+        const int base = blk * L + j;
+        float2 a[R];
+        if (src_g) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                a[q] = (row < g.va || row >= g.vb) ? spim_ldg(g.p + (long long)row * g.stride + c) : make_float2(0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                a[q] = tile[row * TC + (swz ? ((c + row) & (TC - 1)) : c)];
+            }
+        }
+        if (!INV) {
+            dft<R, false>(a);
+            if (M > 1) apply_twiddles<R, false>(a, pl.tw, j * ts);
+        } else {
+            if (M > 1) apply_twiddles<R, true>(a, pl.tw, j * ts);
+            dft<R, true>(a);
+        }
+        if (dst_g) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                if (row < g.sa) g.p[(long long)row * g.stride + c] = a[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                tile[row * TC + (swz ? ((c + row) & (TC - 1)) : c)] = a[q];
+            }
+        }
+    }
+    SPIM_BARRIER();
+}
+
+// last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
+template <int R>
+SPIM_DEV void mid_tile(const FftPlanDev& pl, float2* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
+    const int nb = pl.n / R;
+    SPIM_FOR_ITEMS(i, nb * TC) {
+        const int c = i & (TC - 1);
+        const int base = (i >> 4) * R;
+        float2 a[R];
+        if (src_g) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q;
+                a[q] = (row < g.va || row >= g.vb) ? spim_ldg(g.p + (long long)row * g.stride + c) : make_float2(0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) a[q] = tile[(base + q) * TC + c];
+        }
+        dft<R, false>(a);
+#pragma unroll
+        for (int q = 0; q < R; ++q) a[q] = cmul(a[q], spim_ldg(kh + (long long)(base + q) * g.stride + c));
+        dft<R, true>(a);
+        if (dst_g) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q;
+                if (row < g.sa) g.p[(long long)row * g.stride + c] = a[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) tile[(base + q) * TC + c] = a[q];
+        }
+    }
+    SPIM_BARRIER();
+}
+
+#define SPIM_RADIX_SWITCH(R_, CALL)                                                              \
+    switch (R_) {                                                                                \
+        case 2: { constexpr int RR = 2; CALL; } break;                                           \
+        case 3: { constexpr int RR = 3; CALL; } break;                                           \
+        case 4: { constexpr int RR = 4; CALL; } break;                                           \
+        case 5: { constexpr int RR = 5; CALL; } break;                                           \
+        case 6: { constexpr int RR = 6; CALL; } break;                                           \
+        case 7: { constexpr int RR = 7; CALL; } break;                                           \
+        case 8: { constexpr int RR = 8; CALL; } break;                                           \
+        case 9: { constexpr int RR = 9; CALL; } break;                                           \
+        case 10: { constexpr int RR = 10; CALL; } break;                                         \
+        case 11: { constexpr int RR = 11; CALL; } break;                                         \
+        case 12: { constexpr int RR = 12; CALL; } break;                                         \
+        case 13: { constexpr int RR = 13; CALL; } break;                                         \
+        case 14: { constexpr int RR = 14; CALL; } break;                                         \
+        case 15: { constexpr int RR = 15; CALL; } break;                                         \
+        case 16: { constexpr int RR = 16; CALL; } break;                                         \
+        default: break;                                                                          \
+    }
+
+template <bool INV>
+SPIM_DEV void stage_dispatch(const FftPlanDev& pl, int s, float2* tile, int swz, int src_g, int dst_g, const GRows& g) {
+    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(pl, s, tile, swz, src_g, dst_g, g)))
+}
+SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float2* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
+    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(pl, tile, src_g, dst_g, g, kh)))
+}
+
+// ---------------------------------------------------------------------------------------------
+// ColPass: column FFT along y or z over tiles of 16 x-frequencies
+// ---------------------------------------------------------------------------------------------
+struct ColPassParams {
+    float2* data;
+    const float2* khat;        // COL_MID only
+    FftPlanDev plan;
+    int ntx;                   // number of 16-column tiles along x (pitch / 16)
+    long long row_stride;      // between consecutive FFT rows
+    long long outer_stride;    // between consecutive outer indices
+    int outer_split, outer_shift;  // outer = o < split ? o : o + shift  (skips the zero gap)
+    int va, vb, sa;
+    int mode;
+};
+
+struct ColPass {
+    typedef ColPassParams Params;
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+        const int o = bid / p.ntx;
+        const int tx = bid - o * p.ntx;
+        const int outer = o < p.outer_split ? o : o + p.outer_shift;
+        const long long base = (long long)outer * p.outer_stride + (long long)tx * TC;
+        GRows g;
+        g.p = p.data + base;
+        g.stride = p.row_stride;
+        g.va = p.va; g.vb = p.vb; g.sa = p.sa;
+        const FftPlanDev& pl = p.plan;
+        const int S = pl.nstages;
+        if (p.mode == COL_FWD) {
+            for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, s == 0, s == S - 1, g);
+        } else if (p.mode == COL_INV) {
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, s == S - 1, s == 0, g);
+        } else {
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, s == 0, 0, g);
+            mid_dispatch(pl, tile, S == 1, S == 1, g, p.khat + base);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// XFwd: real lines -> half spectrum (R2C via one complex FFT of length Px/2 + split step)
+// ---------------------------------------------------------------------------------------------
+struct XFwdParams {
+    const float* src;
+    int sx, sy, sz;            // dims of the source array
+    int ox, oy, oz;            // array index = logical coordinate + origin
+    int nx, ny, nz;            // logical image size (coordinates [0,n) are 'inside' for the ext rule)
+    int hpx, hmx, hpy, hmy, hpz, hmz;  // halo after (+) / before (-) the image on each axis
+    int ext;
+    float ext_value;
+    int Px, Py, Pz, pitch;
+    float2* spec;
+    FftPlanDev plan;           // n = Px / 2
+    const unsigned short* pos; // pos[k] = tile row holding frequency k after the DIF stages
+    const float2* wx;          // exp(-2 pi i k / Px), k in [0, Px/4]
+    int LY, LZ;                // lines per axis that are not in the gap: n + hp + hm
+    long long nlines;          // LY * LZ
+    uint32_t magic_m0;         // for i / M[0]
+    int nk;                    // Px/4 + 1 (pairs handled by the split step)
+    uint32_t magic_nk;
+    int src_vec_ok;            // float2 loads allowed (alignment)
+};
+
+constexpr long long kLineInvalid = -2;
+constexpr long long kLineConst = -1;
+
+SPIM_DEV float xfwd_val(const XFwdParams& p, const float* line, bool is_const, float cval, int u) {
+    const int a = pad_to_coord(u, p.nx, p.hpx, p.hmx, p.Px);
+    if (a == kGap) return 0.f;
+    if (is_const) return cval;
+    int i = a + p.ox;
+    if ((unsigned)i >= (unsigned)p.sx) {
+        const int e = ext_map(a, p.nx, p.ext);
+        if (e < 0) return cval;
+        i = e + p.ox;
+    }
+    return spim_ldg(line + i);
+}
+
+SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
+    const int u0 = 2 * n;
+    const float cval = (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
+    if (so >= 0) {
+        const float* line = p.src + so;
+        if (u0 + 1 < p.nx) {   // interior fast path
+            const float* q = line + p.ox + u0;
+            if (p.src_vec_ok) return spim_ldg(reinterpret_cast<const float2*>(q));
+            return make_float2(spim_ldg(q), spim_ldg(q + 1));
+        }
+        return make_float2(xfwd_val(p, line, false, cval, u0), xfwd_val(p, line, false, cval, u0 + 1));
+    }
+    return make_float2(xfwd_val(p, nullptr, true, cval, u0), xfwd_val(p, nullptr, true, cval, u0 + 1));
+}
+
+template <int R>
+SPIM_DEV void xfwd_stage0(const XFwdParams& p, float2* tile, const long long* srcoff) {
+    const FftPlanDev& pl = p.plan;
+    const int M = pl.M[0];
+    SPIM_FOR_ITEMS(i, M * TC) {
+        const int b = (M == 1) ? i : fastdiv(i, p.magic_m0);
+        const int m = i - b * M;
+        const long long so = srcoff[b];
+        float2 a[R];
+        if (so == kLineInvalid) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) a[q] = make_float2(0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) a[q] = xfwd_pair(p, so, m + q * M);
+        }
+        dft<R, false>(a);
+        if (M > 1) apply_twiddles<R, false>(a, pl.tw, m);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int row = m + q * M;
+            tile[row * TC + ((b + row) & (TC - 1))] = a[q];
+        }
+    }
+    SPIM_BARRIER();
+}
+
+struct XFwd {
+    typedef XFwdParams Params;
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+        const FftPlanDev& pl = p.plan;
+        const int N2 = pl.n;
+        long long* srcoff = reinterpret_cast<long long*>(tile + (size_t)N2 * TC);
+        long long* dstoff = srcoff + TC;
+        // line descriptors for the 16 lines of this tile
+        SPIM_FOR_ITEMS(b, TC) {
+            const long long l = (long long)bid * TC + b;
+            long long so = kLineInvalid, d_o = -1;
+            if (l < p.nlines) {
+                const int iz = (int)(l / p.LY);
+                const int iy = (int)(l - (long long)iz * p.LY);
+                const int yp = iy < p.ny + p.hpy ? iy : iy + (p.Py - p.LY);
+                const int zp = iz < p.nz + p.hpz ? iz : iz + (p.Pz - p.LZ);
+                const int ay = iy < p.ny + p.hpy ? iy : iy - p.LY;
+                const int az = iz < p.nz + p.hpz ? iz : iz - p.LZ;
+                int jy = ay + p.oy, jz = az + p.oz;
+                bool cst = false;
+                if ((unsigned)jy >= (unsigned)p.sy) {
+                    const int e = ext_map(ay, p.ny, p.ext);
+                    if (e < 0) cst = true; else jy = e + p.oy;
+                }
+                if ((unsigned)jz >= (unsigned)p.sz) {
+                    const int e = ext_map(az, p.nz, p.ext);
+                    if (e < 0) cst = true; else jz = e + p.oz;
+                }
+                so = cst ? kLineConst : ((long long)jz * p.sy + jy) * (long long)p.sx;
+                d_o = ((long long)zp * p.Py + yp) * (long long)p.pitch;
+            }
+            srcoff[b] = so;
+            dstoff[b] = d_o;
+        }
+        SPIM_BARRIER();
+        SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR>(p, tile, srcoff)))
+        GRows g;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(pl, s, tile, 1, 0, 0, g);
+        // split step: X[k] = (Z[k] + conj Z[N2-k]) - i w^k (Z[k] - conj Z[N2-k])   (factor 1/2 folded into the kernel scale)
+        const int nk = p.nk;
+        SPIM_FOR_ITEMS(i, nk * TC) {
+            const int b = fastdiv(i, p.magic_nk);
+            const int k = i - b * nk;
+            const long long d_o = dstoff[b];
+            if (d_o < 0) continue;
+            const int km = N2 - k;
+            const int rk = spim_ldg(p.pos + k);
+            const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
+            const float2 zk = tile[rk * TC + ((b + rk) & (TC - 1))];
+            const float2 zm = tile[rm * TC + ((b + rm) & (TC - 1))];
+            const float2 w = spim_ldg(p.wx + k);
+            float2* out = p.spec + d_o;
+            {
+                const float2 s = make_float2(zk.x + zm.x, zk.y - zm.y);
+                const float2 d = make_float2(zk.x - zm.x, zk.y + zm.y);
+                const float2 t = cmul(w, d);
+                out[k] = make_float2(s.x + t.y, s.y - t.x);
+            }
+            if (km != k) {
+                const float2 s = make_float2(zm.x + zk.x, zm.y - zk.y);
+                const float2 d = make_float2(zm.x - zk.x, zm.y + zk.y);
+                const float2 t = cmulc(d, w);
+                out[km] = make_float2(s.x - t.y, s.y + t.x);
+            }
+        }
+        // zero the pad columns [N2+1, pitch)
+        const int npad = p.pitch - (N2 + 1);
+        SPIM_FOR_ITEMS(i, npad * TC) {
+            const int b = i / (npad > 0 ? npad : 1);
+            const int j = i - b * npad;
+            const long long d_o = dstoff[b];
+            if (d_o >= 0) p.spec[d_o + N2 + 1 + j] = make_float2(0.f, 0.f);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// XInv: half spectrum -> real lines + fused epilogue
+// ---------------------------------------------------------------------------------------------
+struct XInvParams {
+    const float2* spec;
+    int pitch, Px, Py;
+    int nx, ny, nz;            // output region (logical image size)
+    FftPlanDev plan;           // n = Px / 2
+    const unsigned short* pos;
+    const float2* wx;
+    uint32_t magic_m0;
+    int nk;
+    uint32_t magic_nk;
+    long long nlines;          // ny * nz
+    // destination real array (psi for EPI_UPDATE)
+    float* dst;
+    int dsx, dsy;              // dst row / plane dims
+    int dox, doy, doz;         // dst index = logical coordinate + origin
+    int epi;
+    const float* img;          // EPI_RATIO: observed view, unpadded [nz][ny][nx]
+    const float* weight;       // EPI_UPDATE: per-voxel weight (unpadded) or nullptr
+    float const_weight;
+    double lambda;
+    float min_value;
+    int gen2_quotient;         // 1: q = img > 0 ? img / blur : 1 ; 0: q = img / blur
+    double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
+    unsigned int* stat_max;    // max |change| as float bits
+    int dst_vec_ok, aux_vec_ok;
+};
+
+struct EpiAcc { double sum; float mx; };
+
+SPIM_DEV float tikhonov_next(float last, float integral, double lambda, float min_value) {
+    // computeNextValue, FD/MVDeconvolution.java:692-724 (same arithmetic as D2/BayesMVDeconvolution.java:452-476)
+    const float value = spim_fmul_rn(last, integral);
+    float adj;
+    if (value > 0.f) {
+        if (lambda > 0.0) {
+#if defined(SPIM_HOST_EMU)
+            volatile double t = 2.0 * lambda; t = t * (double)value; t = 1.0 + t;
+            volatile double r = sqrt(t) - 1.0; r = r / lambda;
+            adj = (float)r;
+#else
+            const double t = __dadd_rn(1.0, __dmul_rn(__dmul_rn(2.0, lambda), (double)value));
+            adj = (float)__ddiv_rn(__dadd_rn(__dsqrt_rn(t), -1.0), lambda);
+#endif
+        } else {
+            adj = value;
+        }
+    } else {
+        adj = min_value;
+    }
+    return (adj != adj) ? min_value : fmaxf(min_value, adj);
+}
+
+SPIM_DEV float epi_one(const XInvParams& p, float v, float imgv, float wv, float last, EpiAcc& acc) {
+    if (p.epi == EPI_RATIO) {
+        if (p.gen2_quotient) return imgv > 0.f ? spim_fdiv_rn(imgv, v) : 1.f;
+        return spim_fdiv_rn(imgv, v);
+    }
+    if (p.epi == EPI_UPDATE) {
+        const float next = tikhonov_next(last, v, p.lambda, p.min_value);
+        const float nw = spim_fadd_rn(last, spim_fmul_rn(spim_fsub_rn(next, last), wv));
+        const float ch = fabsf(spim_fsub_rn(nw, last));
+        acc.sum += (double)ch;
+        acc.mx = fmaxf(acc.mx, ch);
+        return nw;
+    }
+    return v;
+}
+
+// process output samples x = 2n, 2n+1 of one line
+SPIM_DEV void epi_pair(const XInvParams& p, long long aux0, long long dst0, int n, float2 v, EpiAcc& acc) {
+    const int u0 = 2 * n;
+    if (u0 >= p.nx) return;
+    const bool two = (u0 + 1 < p.nx);
+    const long long ai = aux0 + u0, di = dst0 + u0;
+    float im0 = 0.f, im1 = 0.f, w0 = p.const_weight, w1 = p.const_weight, l0 = 0.f, l1 = 0.f;
+    if (p.epi == EPI_RATIO) {
+        if (two && p.aux_vec_ok) { const float2 t = spim_ldg(reinterpret_cast<const float2*>(p.img + ai)); im0 = t.x; im1 = t.y; }
+        else { im0 = spim_ldg(p.img + ai); if (two) im1 = spim_ldg(p.img + ai + 1); }
+    } else if (p.epi == EPI_UPDATE) {
+        if (p.weight) {
+            if (two && p.aux_vec_ok) { const float2 t = spim_ldg(reinterpret_cast<const float2*>(p.weight + ai)); w0 = t.x; w1 = t.y; }
+            else { w0 = spim_ldg(p.weight + ai); if (two) w1 = spim_ldg(p.weight + ai + 1); }
+        }
+        if (two && p.dst_vec_ok) { const float2 t = *reinterpret_cast<const float2*>(p.dst + di); l0 = t.x; l1 = t.y; }
+        else { l0 = p.dst[di]; if (two) l1 = p.dst[di + 1]; }
+    }
+    const float r0 = epi_one(p, v.x, im0, w0, l0, acc);
+    if (two) {
+        const float r1 = epi_one(p, v.y, im1, w1, l1, acc);
+        if (p.dst_vec_ok) *reinterpret_cast<float2*>(p.dst + di) = make_float2(r0, r1);
+        else { p.dst[di] = r0; p.dst[di + 1] = r1; }
+    } else {
+        p.dst[di] = r0;
+    }
+}
+
+template <int R>
+SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
+    const FftPlanDev& pl = p.plan;
+    const int M = pl.M[0];
+    SPIM_FOR_ITEMS(i, M * TC) {
+        const int b = (M == 1) ? i : fastdiv(i, p.magic_m0);
+        const int m = i - b * M;
+        const long long d_o = dstoff[b];
+        if (d_o < 0) continue;
+        float2 a[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int row = m + q * M;
+            a[q] = tile[row * TC + ((b + row) & (TC - 1))];
+        }
+        if (M > 1) apply_twiddles<R, true>(a, pl.tw, m);
+        dft<R, true>(a);
+        const long long a_o = auxoff[b];
+#pragma unroll
+        for (int q = 0; q < R; ++q) epi_pair(p, a_o, d_o, m + q * M, a[q], acc);
+    }
+}
+
+SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
+    if (p.epi != EPI_UPDATE || p.stat_sum == nullptr) return;
+#if defined(SPIM_HOST_EMU)
+    (void)tile;
+    *p.stat_sum += acc.sum;
+    unsigned int bits; memcpy(&bits, &acc.mx, 4);
+    if (bits > *p.stat_max) *p.stat_max = bits;
+#else
+    double s = acc.sum; float m = acc.mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    __syncthreads();   // tile no longer in use
+    double* ssum = reinterpret_cast<double*>(tile);
+    float* smax = reinterpret_cast<float*>(ssum + 32);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { ssum[warp] = s; smax[warp] = m; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        s = lane < nw ? ssum[lane] : 0.0;
+        m = lane < nw ? smax[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        }
+        if (lane == 0) {
+            atomicAdd(p.stat_sum, s);
+            atomicMax(p.stat_max, __float_as_uint(m));
+        }
+    }
+#endif
+}
+
+struct XInv {
+    typedef XInvParams Params;
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+        const FftPlanDev& pl = p.plan;
+        const int N2 = pl.n;
+        long long* srcoff = reinterpret_cast<long long*>(tile + (size_t)N2 * TC);
+        long long* dstoff = srcoff + TC;
+        long long* auxoff = dstoff + TC;
+        SPIM_FOR_ITEMS(b, TC) {
+            const long long l = (long long)bid * TC + b;
+            long long so = -1, d_o = -1, a_o = -1;
+            if (l < p.nlines) {
+                const int z = (int)(l / p.ny);
+                const int y = (int)(l - (long long)z * p.ny);
+                so = ((long long)z * p.Py + y) * (long long)p.pitch;
+                d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
+                a_o = ((long long)z * p.ny + y) * (long long)p.nx;
+            }
+            srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
+        }
+        SPIM_BARRIER();
+        // pre-step: Z'[k] = (X[k] + conj X[N2-k]) + i conj(w^k) (X[k] - conj X[N2-k]), written to its DIT input row
+        const int nk = p.nk;
+        SPIM_FOR_ITEMS(i, nk * TC) {
+            const int b = fastdiv(i, p.magic_nk);
+            const int k = i - b * nk;
+            const long long so = srcoff[b];
+            const int km = N2 - k;
+            float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
+            if (so >= 0) {
+                A = spim_ldg(p.spec + so + k);
+                B = spim_ldg(p.spec + so + km);
+            }
+            const float2 w = spim_ldg(p.wx + k);
+            {
+                const float2 s = make_float2(A.x + B.x, A.y - B.y);
+                const float2 d = make_float2(A.x - B.x, A.y + B.y);
+                const float2 t = cmulc(d, w);
+                const int r = spim_ldg(p.pos + k);
+                tile[r * TC + ((b + r) & (TC - 1))] = make_float2(s.x - t.y, s.y + t.x);
+            }
+            if (k != 0 && km != k) {
+                const float2 s = make_float2(B.x + A.x, B.y - A.y);
+                const float2 d = make_float2(B.x - A.x, B.y + A.y);
+                const float2 t = cmul(d, w);
+                const int r = spim_ldg(p.pos + km);
+                tile[r * TC + ((b + r) & (TC - 1))] = make_float2(s.x + t.y, s.y - t.x);
+            }
+        }
+        SPIM_BARRIER();
+        GRows g;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(pl, s, tile, 1, 0, 0, g);
+        EpiAcc acc;
+        acc.sum = 0.0; acc.mx = 0.f;
+        SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR>(p, tile, auxoff, dstoff, acc)))
+        stats_commit(p, tile, acc);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// element-wise helpers (one-off initialisation work, a6-a9 of SURVEY section 8)
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_VIEWS = 64;
+
+struct FillParams { float* p; long long n; float v; };
+struct ScaleClampParams { float* p; long long n; float f; };           // w <- min(1, w*f)   (OSEM)
+struct ViewPtrs { const float* img[MAX_VIEWS]; const float* w[MAX_VIEWS]; int nviews; };
+struct InitStatsParams {     // psi initialisation statistics
+    ViewPtrs v; long long n; int gen;
+    double* sum;             // gen-2: sum over voxels of mean over views with img>0 ; gen-1: sum of intensities where >= 2 views
+    unsigned long long* cnt; // [0] gen-2: #voxels with data ; gen-1: sum of counts where >= 2 views
+                             // [1] gen-1: sum of counts where >= 1 view ; [2] gen-1: #voxels with >= 1 view
+    unsigned int* min_overlap;
+};
+struct MaskParams { ViewPtrs v; float* psi; long long n; };            // psi <- 0 where no view has img > 0
+
+}  // namespace spim

@@ -1,0 +1,142 @@
+// Thin runtime shim: device memory, copies, streams and kernel launch.
+// CUDA build: real device calls.  SPIM_HOST_EMU build (tests only): host memory + serial blocks.
+#pragma once
+#include "hd.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+namespace spim { namespace rt {
+
+struct Error : public std::runtime_error {
+    explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+#if defined(SPIM_HOST_EMU)
+
+typedef int Stream;
+inline int device_count() { return 1; }
+inline void set_device(int) {}
+inline void* dmalloc(size_t n) { void* p = calloc(1, n ? n : 1); if (!p) throw Error("emu: out of memory"); return p; }
+inline void dfree(void* p) { free(p); }
+inline void h2d(void* d, const void* h, size_t n, Stream) { memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, Stream) { memcpy(h, d, n); }
+inline void d2d(void* d, const void* s, size_t n, Stream) { memmove(d, s, n); }
+inline void dzero(void* d, size_t n, Stream) { memset(d, 0, n); }
+inline Stream stream_create() { return 0; }
+inline void stream_destroy(Stream) {}
+inline void stream_sync(Stream) {}
+inline size_t max_smem() { return 227 * 1024; }
+inline int sm_count() { return 148; }
+
+template <class Body>
+inline void launch(const typename Body::Params& p, long long grid, int /*block*/, size_t smem, Stream) {
+    std::vector<double> buf((smem + 7) / 8 + 1);
+    for (long long b = 0; b < grid; ++b) Body::run(p, (int)b, reinterpret_cast<float2*>(buf.data()));
+}
+
+struct KernelTimer {
+    void enable(bool) {}
+    void begin(int, Stream) {}
+    void end(int, Stream) {}
+    void collect(double*, long long*, int n) { (void)n; }
+    void reset() {}
+};
+
+#else
+
+#define SPIM_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            throw ::spim::rt::Error(std::string(#expr) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+typedef cudaStream_t Stream;
+inline int device_count() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+inline void set_device(int d) { SPIM_CUDA_CHECK(cudaSetDevice(d)); }
+inline void* dmalloc(size_t n) { void* p = nullptr; SPIM_CUDA_CHECK(cudaMalloc(&p, n ? n : 1)); return p; }
+inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void h2d(void* d, const void* h, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+inline void d2h(void* h, const void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+inline void d2d(void* d, const void* s_, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
+inline void dzero(void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemsetAsync(d, 0, n, s)); }
+inline Stream stream_create() { Stream s; SPIM_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
+inline void stream_destroy(Stream s) { cudaStreamDestroy(s); }
+inline void stream_sync(Stream s) { SPIM_CUDA_CHECK(cudaStreamSynchronize(s)); }
+inline size_t max_smem() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return (size_t)v;
+}
+inline int sm_count() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+}
+
+template <class Body>
+__global__ void __launch_bounds__(256) kernel_entry(const __grid_constant__ typename Body::Params p) {
+    extern __shared__ __align__(16) unsigned char spim_smem[];
+    Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
+}
+
+template <class Body>
+inline void launch(const typename Body::Params& p, long long grid, int block, size_t smem, Stream s) {
+    if (grid <= 0) return;
+    static thread_local size_t configured[64] = {0};   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && smem > configured[dev]) {
+        SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    kernel_entry<Body><<<(unsigned)grid, block, smem, s>>>(p);
+    SPIM_CUDA_CHECK(cudaGetLastError());
+}
+
+// optional per-kernel-class timing with CUDA events on the launching stream
+struct KernelTimer {
+    bool on = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t cur = nullptr;
+    void enable(bool v) { on = v; }
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; SPIM_CUDA_CHECK(cudaEventCreate(&e)); return e;
+    }
+    void begin(int, Stream s) { if (!on) return; cur = get(); SPIM_CUDA_CHECK(cudaEventRecord(cur, s)); }
+    void end(int id, Stream s) {
+        if (!on) return;
+        cudaEvent_t b = get();
+        SPIM_CUDA_CHECK(cudaEventRecord(b, s));
+        recs.push_back(Rec{id, cur, b});
+    }
+    // accumulate milliseconds and launch counts per id (caller synchronised the stream)
+    void collect(double* ms, long long* cnt, int n) {
+        for (auto& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.id < n) { ms[r.id] += t; cnt[r.id] += 1; }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() { for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); } recs.clear(); }
+    ~KernelTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+};
+
+#endif
+
+}}  // namespace spim::rt

@@ -1,0 +1,1005 @@
+// B200-native multi-view deconvolution library: C ABI (include/spim_fftconv.h, include/spim_mvdecon.h)
+// over the FFT-convolution engine (engine.h / kernels.h).
+//
+// Built two ways (see hd.h): nvcc -gencode arch=compute_100a,code=sm_100a -> the product .so;
+// g++ -x c++ -DSPIM_HOST_EMU -> tests/emu/libspim_emu.so, a test-only CPU emulator of the kernels.
+#include "engine.h"
+#include "../../include/spim_fftconv.h"
+#include "../../include/spim_mvdecon.h"
+
+#include <string>
+#include <vector>
+#include <mutex>
+#include <map>
+#include <array>
+
+using namespace spim;
+
+// ================================================================================================
+// element-wise kernels (initialisation work; not on the per-iteration path)
+// ================================================================================================
+namespace spim {
+
+constexpr int kChunk = 2048;
+
+struct EwGrid { long long n; int nblocks; };
+
+struct FillK {
+    struct Params { float* p; long long n; float v; int nblocks; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        for (long long base = (long long)bid * kChunk; base < p.n; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) { const long long idx = base + i; if (idx < p.n) p.p[idx] = p.v; }
+        }
+    }
+};
+
+struct ScaleClampK {   // adjustOSEMspeedup: w <- min(1, w * (float)osem)
+    struct Params { float* p; long long n; float f; int nblocks; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        for (long long base = (long long)bid * kChunk; base < p.n; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx < p.n) p.p[idx] = fminf(1.f, spim_fmul_rn(p.p[idx], p.f));
+            }
+        }
+    }
+};
+
+#if defined(SPIM_HOST_EMU)
+SPIM_DEV void atomic_add_d(double* p, double v) { *p += v; }
+SPIM_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+SPIM_DEV void atomic_min_u32(unsigned int* p, unsigned int v) { if (v < *p) *p = v; }
+SPIM_DEV double warp_sum_d(double v) { return v; }
+SPIM_DEV unsigned long long warp_sum_u64(unsigned long long v) { return v; }
+SPIM_DEV unsigned int warp_min_u32(unsigned int v) { return v; }
+SPIM_DEV bool warp_leader() { return true; }
+#else
+SPIM_DEV void atomic_add_d(double* p, double v) { atomicAdd(p, v); }
+SPIM_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+SPIM_DEV void atomic_min_u32(unsigned int* p, unsigned int v) { atomicMin(p, v); }
+SPIM_DEV double warp_sum_d(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+SPIM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+SPIM_DEV unsigned int warp_min_u32(unsigned int v) {
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+SPIM_DEV bool warp_leader() { return (threadIdx.x & 31) == 0; }
+#endif
+
+// psi initialisation statistics.
+//  gen-2 (FirstIteration.java:122-154): sum over voxels with >=1 view img>0 of the mean of those views.
+//  gen-1 (D2/AdjustInput.java:136-167): views counted where weight != 0; intensity sum where >= 2 views.
+struct InitStatsK {
+    struct Params { ViewPtrs v; long long n; int gen; int nblocks; double* sum; unsigned long long* cnt; unsigned int* min_overlap; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        double s = 0.0;
+        unsigned long long c0 = 0, c1 = 0, c2 = 0;
+        unsigned int mn = 0xffffffffu;
+        for (long long base = (long long)bid * kChunk; base < p.n; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= p.n) continue;
+                double loc = 0.0;
+                int cnt = 0;
+                for (int v = 0; v < p.v.nviews; ++v) {
+                    const float im = spim_ldg(p.v.img[v] + idx);
+                    bool use;
+                    if (p.gen == 2) use = im > 0.f;
+                    else use = p.v.w[v] ? (spim_ldg(p.v.w[v] + idx) != 0.f) : true;
+                    if (use) { loc += (double)im; ++cnt; }
+                }
+                if (p.gen == 2) {
+                    if (cnt > 0) { s += loc / (double)cnt; ++c0; }
+                } else {
+                    if (cnt > 1) { s += loc; c0 += (unsigned long long)cnt; }
+                    if (cnt > 0) { c1 += (unsigned long long)cnt; ++c2; if ((unsigned)cnt < mn) mn = (unsigned)cnt; }
+                }
+            }
+        }
+        s = warp_sum_d(s); c0 = warp_sum_u64(c0); c1 = warp_sum_u64(c1); c2 = warp_sum_u64(c2); mn = warp_min_u32(mn);
+        if (warp_leader()) {
+            atomic_add_d(p.sum, s);
+            atomic_add_u64(p.cnt + 0, c0); atomic_add_u64(p.cnt + 1, c1); atomic_add_u64(p.cnt + 2, c2);
+            atomic_min_u32(p.min_overlap, mn);
+        }
+    }
+};
+
+struct MaskK {   // MVDeconvolution.java:201-208: psi <- 0 where no view has img > 0
+    struct Params { ViewPtrs v; float* psi; int pdims[3]; int porigin[3]; int n[3]; int nblocks; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        const long long total = (long long)p.n[0] * p.n[1] * p.n[2];
+        for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= total) continue;
+                bool any = false;
+                for (int v = 0; v < p.v.nviews; ++v) any = any || (spim_ldg(p.v.img[v] + idx) > 0.f);
+                if (!any) {
+                    const int x = (int)(idx % p.n[2]);
+                    const long long r = idx / p.n[2];
+                    const int y = (int)(r % p.n[1]);
+                    const int z = (int)(r / p.n[1]);
+                    p.psi[((long long)(z + p.porigin[0]) * p.pdims[1] + (y + p.porigin[1])) * p.pdims[2] + x + p.porigin[2]] = 0.f;
+                }
+            }
+        }
+    }
+};
+
+// copy between an unpadded [n] volume and the interior of a haloed buffer
+struct CopyRegionK {
+    struct Params { const float* src; float* dst; int sdims[3], sorigin[3], ddims[3], dorigin[3], n[3]; int nblocks; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        const long long total = (long long)p.n[0] * p.n[1] * p.n[2];
+        for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= total) continue;
+                const int x = (int)(idx % p.n[2]);
+                const long long r = idx / p.n[2];
+                const int y = (int)(r % p.n[1]);
+                const int z = (int)(r / p.n[1]);
+                const float v = p.src[((long long)(z + p.sorigin[0]) * p.sdims[1] + (y + p.sorigin[1])) * p.sdims[2] + x + p.sorigin[2]];
+                p.dst[((long long)(z + p.dorigin[0]) * p.ddims[1] + (y + p.dorigin[1])) * p.ddims[2] + x + p.dorigin[2]] = v;
+            }
+        }
+    }
+};
+
+// brick mode: fill one halo face of a haloed buffer from its interior by the out-of-bounds rule
+struct HaloFillK {
+    struct Params { float* buf; int dims[3], origin[3], n[3]; int axis, side, width; int ext; float value; int nblocks; };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        int ext_[3] = {p.dims[0], p.dims[1], p.dims[2]};
+        ext_[p.axis] = p.width;
+        const long long total = (long long)ext_[0] * ext_[1] * ext_[2];
+        for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= total) continue;
+                int c[3];
+                c[2] = (int)(idx % ext_[2]);
+                const long long r = idx / ext_[2];
+                c[1] = (int)(r % ext_[1]);
+                c[0] = (int)(r / ext_[1]);
+                // coordinate along the axis (array index), lo side: [0, width), hi side: [origin+n, origin+n+width)
+                const int ai = p.side == 0 ? c[p.axis] : p.origin[p.axis] + p.n[p.axis] + c[p.axis];
+                const int a = ai - p.origin[p.axis];
+                const int e = ext_map(a, p.n[p.axis], p.ext);
+                int d[3] = {c[0], c[1], c[2]};
+                d[p.axis] = ai;
+                float v = p.value;
+                if (e >= 0) {
+                    int s[3] = {c[0], c[1], c[2]};
+                    s[p.axis] = e + p.origin[p.axis];
+                    v = p.buf[((long long)s[0] * p.dims[1] + s[1]) * p.dims[2] + s[2]];
+                }
+                p.buf[((long long)d[0] * p.dims[1] + d[1]) * p.dims[2] + d[2]] = v;
+            }
+        }
+    }
+};
+
+inline int ew_blocks(long long n) {
+    long long b = (n + kChunk - 1) / kChunk;
+    const long long cap = 148LL * 16;
+    return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+}  // namespace spim
+
+// ================================================================================================
+// error plumbing
+// ================================================================================================
+static thread_local std::string g_last_error;
+static int fail(const std::string& msg) {
+    g_last_error = msg;
+    return 1;
+}
+#define SPIM_API_BEGIN try {
+#define SPIM_API_END                                                                    \
+    }                                                                                   \
+    catch (const std::exception& e) { return fail(e.what()); }                          \
+    catch (...) { return fail("unknown error"); }
+
+// ================================================================================================
+// host-side kernel (PSF) helpers: LRFFT.init / MVDeconFFT.init
+// ================================================================================================
+namespace {
+
+struct HostVol {
+    int d[3] = {0, 0, 0};
+    std::vector<float> v;
+    size_t size() const { return (size_t)d[0] * d[1] * d[2]; }
+};
+
+// RealSum (mpicbg.util.RealSum / net.imglib2.util.RealSum): compensated fp64 summation
+double real_sum(const std::vector<float>& v) {
+    double sum = 0.0, comp = 0.0;
+    for (float f : v) {   // Neumaier variant
+        const double x = (double)f;
+        const double t = sum + x;
+        if (fabs(sum) >= fabs(x)) comp += (sum - t) + x; else comp += (x - t) + sum;
+        sum = t;
+    }
+    return sum + comp;
+}
+
+// AdjustInput.normImage D2/AdjustInput.java:53-59: t <- (float)((double)t / sum)
+void norm_image(HostVol& k) {
+    const double s = real_sum(k.v);
+    for (float& f : k.v) f = (float)((double)f / s);
+}
+
+// computeInvertedKernel: Mirror.mirror along every axis (FD/Mirror.java:52-129).  Exact flip for
+// odd sizes; for even sizes the reference swaps positions <= size/2 which un-swaps the middle pair.
+HostVol invert_kernel(const HostVol& k) {
+    HostVol o = k;
+    for (int ax = 0; ax < 3; ++ax) {
+        const int n = o.d[ax];
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        if (n % 2 == 1) { for (int i = 0; i < n; ++i) idx[i] = n - 1 - i; }
+        else { for (int pos = 0; pos <= n / 2; ++pos) std::swap(idx[pos], idx[n - 1 - pos]); }
+        HostVol t = o;
+        for (int z = 0; z < o.d[0]; ++z)
+            for (int y = 0; y < o.d[1]; ++y)
+                for (int x = 0; x < o.d[2]; ++x) {
+                    int c[3] = {z, y, x};
+                    int s[3] = {z, y, x};
+                    s[ax] = idx[c[ax]];
+                    t.v[((size_t)z * o.d[1] + y) * o.d[2] + x] = o.v[((size_t)s[0] * o.d[1] + s[1]) * o.d[2] + s[2]];
+                }
+        o = t;
+    }
+    return o;
+}
+
+// computeExponentialKernel + pow (LRFFT.java:361-391): repeated fp32 multiplication
+HostVol exponential_kernel(const HostVol& k, int num_views) {
+    HostVol o = k;
+    for (size_t i = 0; i < o.v.size(); ++i) {
+        volatile float r = k.v[i];
+        for (int j = 1; j < num_views; ++j) r = r * k.v[i];
+        o.v[i] = r;
+    }
+    return o;
+}
+
+struct DeviceGuard {
+    explicit DeviceGuard(int dev) { rt::set_device(dev); }
+};
+
+// stand-alone convolution on host buffers through the engine (used for the PSF-sized kernel-building
+// convolutions, by mvd_convolve and by the legacy JNA entry)
+struct ConvWorkspace {
+    ConvPlan plan;
+    bool valid = false;
+    int n[3] = {0, 0, 0}, k[3] = {0, 0, 0};
+    bool exact = false;
+    float* d_img = nullptr;
+    float2* d_khat = nullptr;
+    rt::Stream stream = 0;
+    bool have_stream = false;
+
+    void ensure(const int n_[3], const int k_[3], bool periodic_exact) {
+        if (valid && exact == periodic_exact && !memcmp(n, n_, sizeof(n)) && !memcmp(k, k_, sizeof(k))) return;
+        release();
+        if (!have_stream) { stream = rt::stream_create(); have_stream = true; }
+        plan.create(n_, k_, periodic_exact, true);
+        memcpy(n, n_, sizeof(n)); memcpy(k, k_, sizeof(k));
+        exact = periodic_exact;
+        d_img = (float*)rt::dmalloc((size_t)n[0] * n[1] * n[2] * sizeof(float));
+        d_khat = (float2*)rt::dmalloc(plan.spec_bytes());
+        valid = true;
+    }
+    void release() {
+        if (!valid) return;
+        plan.destroy();
+        rt::dfree(d_img); rt::dfree(d_khat);
+        d_img = nullptr; d_khat = nullptr;
+        valid = false;
+    }
+    // out may alias img
+    void run(const float* img, const float* kernel, int ext, float value, float* out) {
+        const size_t bytes = (size_t)n[0] * n[1] * n[2] * sizeof(float);
+        rt::h2d(d_img, img, bytes, stream);
+        plan.kernel_spectrum(kernel, d_khat, stream);
+        SrcDesc src;
+        src.p = d_img;
+        for (int d = 0; d < 3; ++d) { src.dims[d] = n[d]; src.origin[d] = 0; }
+        src.ext = ext; src.ext_value = value;
+        EpiDesc e;
+        e.epi = EPI_STORE; e.dst = d_img;
+        for (int d = 0; d < 3; ++d) { e.dst_dims[d] = n[d]; e.dst_origin[d] = 0; }
+        plan.convolve(src, d_khat, e, stream);
+        rt::d2h(out, d_img, bytes, stream);
+        rt::stream_sync(stream);
+    }
+    ~ConvWorkspace() {}
+};
+
+}  // namespace
+
+// ================================================================================================
+// session
+// ================================================================================================
+struct mvd_session {
+    mvd_params prm;
+    int n[3];
+    int kmax[3] = {0, 0, 0};
+    long long N = 0;
+    std::vector<HostVol> psf, k1, k2;
+    std::vector<float*> d_img, d_w;
+    std::vector<float2*> d_kh1, d_kh2;
+    float* d_psi = nullptr;    // dims pdims, origin porigin
+    float* d_tmp = nullptr;    // ratio buffer, same geometry
+    int pdims[3], porigin[3];
+    long long pelems = 0;
+    ConvPlan plan;
+    bool plan_ok = false, inited = false;
+    rt::Stream stream = 0;
+    rt::KernelTimer timer;
+    double* d_stat_sum = nullptr;
+    unsigned int* d_stat_max = nullptr;
+    size_t stat_cap = 0;
+    double avg = 0.0, osem = 1.0, avg_overlap = 0.0;
+    int min_overlap = 0;
+    long long dev_bytes = 0;
+    double t_ms[8] = {0};
+    long long t_cnt[8] = {0};
+    std::vector<std::unique_ptr<ConvWorkspace>> small;   // PSF-sized plans for kernel building
+
+    int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
+    int conv2_ext() const { return prm.conv2_ext >= 0 ? prm.conv2_ext : (prm.generation == 2 ? EXT_CONSTANT : EXT_MIRROR_SINGLE); }
+
+    void* dalloc(size_t bytes) { dev_bytes += (long long)bytes; return rt::dmalloc(bytes); }
+
+    HostVol small_conv(const HostVol& a, const HostVol& b) {   // zero-extended PSF-sized convolution
+        ConvWorkspace* ws = nullptr;
+        for (auto& w : small)
+            if (!memcmp(w->n, a.d, sizeof(a.d)) && !memcmp(w->k, b.d, sizeof(b.d))) ws = w.get();
+        if (!ws) {
+            small.emplace_back(new ConvWorkspace());
+            ws = small.back().get();
+            ws->ensure(a.d, b.d, false);
+        }
+        HostVol o = a;
+        ws->run(a.v.data(), b.v.data(), EXT_ZERO, 0.f, o.v.data());
+        return o;
+    }
+
+    // LRInput.init -> LRFFT.init per view in list order (LRFFT.java:214-325, MVDeconFFT.java:183-323)
+    void init_kernels() {
+        const int V = prm.num_views;
+        k1 = psf;
+        k2.assign(V, HostVol());
+        for (int v = 0; v < V; ++v) {
+            norm_image(k1[v]);
+            if (V == 1 || prm.iteration_type == MVD_INDEPENDENT) {
+                k2[v] = invert_kernel(k1[v]);
+            } else if (prm.iteration_type == MVD_EFFICIENT_BAYESIAN) {
+                HostVol tmp = invert_kernel(k1[v]);
+                for (int w = 0; w < V; ++w) {
+                    if (w == v) continue;
+                    HostVol c1 = small_conv(invert_kernel(k1[v]), k1[w]);
+                    HostVol c2 = small_conv(c1, invert_kernel(k1[w]));
+                    for (size_t i = 0; i < tmp.v.size(); ++i) { volatile float m = c2.v[i] * tmp.v[i]; tmp.v[i] = m; }
+                }
+                norm_image(tmp);
+                k2[v] = tmp;
+            } else if (prm.iteration_type == MVD_OPTIMIZATION_I) {
+                HostVol tmp = k1[v];
+                for (int w = 0; w < V; ++w) {
+                    if (w == v) continue;
+                    HostVol c = small_conv(k1[v], invert_kernel(k1[w]));
+                    for (size_t i = 0; i < tmp.v.size(); ++i) { volatile float m = c.v[i] * tmp.v[i]; tmp.v[i] = m; }
+                }
+                norm_image(tmp);
+                k2[v] = invert_kernel(tmp);
+            } else {
+                HostVol e = exponential_kernel(k1[v], V);
+                norm_image(e);
+                k2[v] = invert_kernel(e);
+            }
+        }
+        for (auto& w : small) w->release();
+        small.clear();
+    }
+
+    ViewPtrs view_ptrs() const {
+        ViewPtrs vp;
+        memset(&vp, 0, sizeof(vp));
+        vp.nviews = prm.num_views;
+        for (int v = 0; v < prm.num_views; ++v) { vp.img[v] = d_img[v]; vp.w[v] = d_w[v]; }
+        return vp;
+    }
+
+    void partials(double out[6]) {
+        double* d_sum = (double*)rt::dmalloc(sizeof(double));
+        unsigned long long* d_cnt = (unsigned long long*)rt::dmalloc(3 * sizeof(unsigned long long));
+        unsigned int* d_min = (unsigned int*)rt::dmalloc(sizeof(unsigned int));
+        rt::dzero(d_sum, sizeof(double), stream);
+        rt::dzero(d_cnt, 3 * sizeof(unsigned long long), stream);
+        const unsigned int big = 0xffffffffu;
+        rt::h2d(d_min, &big, sizeof(big), stream);
+        rt::stream_sync(stream);
+        InitStatsK::Params p;
+        p.v = view_ptrs(); p.n = N; p.gen = prm.generation; p.nblocks = ew_blocks(N);
+        p.sum = d_sum; p.cnt = d_cnt; p.min_overlap = d_min;
+        rt::launch<InitStatsK>(p, p.nblocks, kThreads, 0, stream);
+        double s = 0; unsigned long long c[3] = {0, 0, 0}; unsigned int mn = 0;
+        rt::d2h(&s, d_sum, sizeof(s), stream);
+        rt::d2h(c, d_cnt, sizeof(c), stream);
+        rt::d2h(&mn, d_min, sizeof(mn), stream);
+        rt::stream_sync(stream);
+        rt::dfree(d_sum); rt::dfree(d_cnt); rt::dfree(d_min);
+        out[0] = s; out[1] = (double)c[0]; out[2] = (double)c[1]; out[3] = (double)c[2];
+        out[4] = (mn == 0xffffffffu) ? 2147483647.0 : (double)mn; out[5] = 0.0;
+    }
+
+    // avg / overlap statistics from (all-reduced) partial sums
+    static void reduce_partials(int gen, const double p[6], double& avg, int& min_ov, double& avg_ov) {
+        if (gen == 2) {
+            avg = p[0] / p[1];            // NaN when no data at all (reference: falls back to 0.5)
+            if (avg != avg) avg = 0.5;
+            min_ov = 0; avg_ov = 0.0;
+        } else {
+            min_ov = (int)p[4];
+            avg_ov = p[2] / p[3];
+            avg = (p[1] == 0.0) ? 1.0 : (double)(float)(p[0] / p[1]);   // this.avg = (float)result[0]
+        }
+    }
+
+    void apply_avg(double avg_, double osem_) {
+        avg = avg_; osem = osem_;
+        if (osem != 1.0) {
+            for (int v = 0; v < prm.num_views; ++v) {
+                if (!d_w[v]) {   // constant-1 weight: min(1, 1*osem) = 1 for osem >= 1; materialise otherwise
+                    if (osem >= 1.0) continue;
+                    d_w[v] = (float*)dalloc((size_t)N * sizeof(float));
+                    FillK::Params f; f.p = d_w[v]; f.n = N; f.v = 1.f; f.nblocks = ew_blocks(N);
+                    rt::launch<FillK>(f, f.nblocks, kThreads, 0, stream);
+                }
+                ScaleClampK::Params p; p.p = d_w[v]; p.n = N; p.f = (float)osem; p.nblocks = ew_blocks(N);
+                rt::launch<ScaleClampK>(p, p.nblocks, kThreads, 0, stream);
+            }
+        }
+        FillK::Params f; f.p = d_psi; f.n = pelems; f.v = (float)avg; f.nblocks = ew_blocks(pelems);
+        rt::launch<FillK>(f, f.nblocks, kThreads, 0, stream);
+        rt::stream_sync(stream);
+        inited = true;
+    }
+
+    void phase(int v, int ph, double* d_sum, unsigned int* d_max) {
+        SrcDesc src;
+        for (int d = 0; d < 3; ++d) { src.dims[d] = pdims[d]; src.origin[d] = porigin[d]; }
+        EpiDesc e;
+        for (int d = 0; d < 3; ++d) { e.dst_dims[d] = pdims[d]; e.dst_origin[d] = porigin[d]; }
+        e.min_value = prm.min_value;
+        if (ph == 0) {
+            src.p = d_psi; src.ext = conv1_ext(); src.ext_value = 0.f;
+            e.epi = EPI_RATIO; e.dst = d_tmp; e.img = d_img[v]; e.gen2_quotient = (prm.generation == 2);
+            plan.convolve(src, d_kh1[v], e, stream);
+        } else {
+            src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = 1.f;
+            e.epi = EPI_UPDATE; e.dst = d_psi; e.weight = d_w[v]; e.const_weight = 1.f;
+            e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max;
+            plan.convolve(src, d_kh2[v], e, stream);
+        }
+    }
+
+    void ensure_stats(size_t slots) {
+        if (slots <= stat_cap) return;
+        rt::dfree(d_stat_sum); rt::dfree(d_stat_max);
+        d_stat_sum = (double*)rt::dmalloc(slots * sizeof(double));
+        d_stat_max = (unsigned int*)rt::dmalloc(slots * sizeof(unsigned int));
+        stat_cap = slots;
+    }
+};
+
+// ================================================================================================
+// session C ABI
+// ================================================================================================
+extern "C" {
+
+const char* mvd_last_error(void) { return g_last_error.c_str(); }
+const char* mvd_version(void) {
+#if defined(SPIM_HOST_EMU)
+    return "spim_registration_b200 0.1 (HOST EMULATOR - tests only)";
+#else
+    return "spim_registration_b200 0.1 (sm_100a)";
+#endif
+}
+
+void mvd_params_default(mvd_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->struct_size = (int)sizeof(mvd_params);
+    p->num_views = 1;
+    p->iteration_type = MVD_EFFICIENT_BAYESIAN;
+    p->generation = 2;
+    p->lambda = 0.006;
+    p->min_value = 0.0001f;
+    p->osem_speedup = 1.0;
+    p->osem_index = 0;
+    p->conv1_ext = -1;
+    p->conv2_ext = -1;
+    p->device = 0;
+    p->haloed = 0;
+}
+
+int mvd_session_create(const mvd_params* p, mvd_session** out) {
+    SPIM_API_BEGIN
+    if (!p || !out) return fail("mvd_session_create: null argument");
+    if (p->struct_size != (int)sizeof(mvd_params)) return fail("mvd_session_create: struct_size mismatch");
+    if (p->num_views < 1 || p->num_views > MAX_VIEWS) return fail("mvd_session_create: num_views out of range");
+    if (p->iteration_type < 0 || p->iteration_type > 3) return fail("mvd_session_create: bad iteration_type");
+    if (p->generation != 1 && p->generation != 2) return fail("mvd_session_create: generation must be 1 or 2");
+    for (int d = 0; d < 3; ++d) if (p->dims[d] < 1) return fail("mvd_session_create: bad dims");
+    const int ndev = rt::device_count();
+    if (ndev <= 0) return fail("mvd_session_create: no CUDA device available (this library has no CPU fallback)");
+    if (p->device < 0 || p->device >= ndev) return fail("mvd_session_create: bad device ordinal");
+    rt::set_device(p->device);
+    std::unique_ptr<mvd_session> s(new mvd_session());
+    s->prm = *p;
+    for (int d = 0; d < 3; ++d) s->n[d] = p->dims[d];
+    s->N = (long long)s->n[0] * s->n[1] * s->n[2];
+    const int V = p->num_views;
+    s->psf.assign(V, HostVol());
+    s->d_img.assign(V, nullptr); s->d_w.assign(V, nullptr);
+    s->d_kh1.assign(V, nullptr); s->d_kh2.assign(V, nullptr);
+    s->stream = rt::stream_create();
+    *out = s.release();
+    return 0;
+    SPIM_API_END
+}
+
+void mvd_session_destroy(mvd_session* s) {
+    if (!s) return;
+    try {
+        rt::set_device(s->prm.device);
+        rt::stream_sync(s->stream);
+        for (auto p : s->d_img) rt::dfree(p);
+        for (auto p : s->d_w) rt::dfree(p);
+        for (auto p : s->d_kh1) rt::dfree(p);
+        for (auto p : s->d_kh2) rt::dfree(p);
+        rt::dfree(s->d_psi); rt::dfree(s->d_tmp);
+        rt::dfree(s->d_stat_sum); rt::dfree(s->d_stat_max);
+        if (s->plan_ok) s->plan.destroy();
+        rt::stream_destroy(s->stream);
+    } catch (...) {}
+    delete s;
+}
+
+int mvd_set_view(mvd_session* s, int v, const float* img, const float* weight, const float* psf, const int psf_dims[3]) {
+    SPIM_API_BEGIN
+    if (!s || !img || !psf || !psf_dims) return fail("mvd_set_view: null argument");
+    if (v < 0 || v >= s->prm.num_views) return fail("mvd_set_view: view index out of range");
+    for (int d = 0; d < 3; ++d) if (psf_dims[d] < 1) return fail("mvd_set_view: bad psf dims");
+    rt::set_device(s->prm.device);
+    const size_t bytes = (size_t)s->N * sizeof(float);
+    if (!s->d_img[v]) s->d_img[v] = (float*)s->dalloc(bytes);
+    rt::h2d(s->d_img[v], img, bytes, s->stream);
+    if (weight) {
+        if (!s->d_w[v]) s->d_w[v] = (float*)s->dalloc(bytes);
+        rt::h2d(s->d_w[v], weight, bytes, s->stream);
+    } else if (s->d_w[v]) {
+        rt::dfree(s->d_w[v]); s->d_w[v] = nullptr;
+    }
+    HostVol& k = s->psf[v];
+    for (int d = 0; d < 3; ++d) k.d[d] = psf_dims[d];
+    k.v.assign(psf, psf + k.size());
+    rt::stream_sync(s->stream);
+    s->inited = false;
+    return 0;
+    SPIM_API_END
+}
+
+static int session_prepare(mvd_session* s) {
+    const int V = s->prm.num_views;
+    for (int v = 0; v < V; ++v) if (!s->d_img[v] || s->psf[v].v.empty()) return fail("mvd_init: view " + std::to_string(v) + " not set");
+    for (int d = 0; d < 3; ++d) {
+        s->kmax[d] = 0;
+        for (int v = 0; v < V; ++v) s->kmax[d] = std::max(s->kmax[d], s->psf[v].d[d]);
+    }
+    if (s->plan_ok) { s->plan.destroy(); s->plan_ok = false; }
+    s->plan.create(s->n, s->kmax, false, true);
+    s->plan.timer = &s->timer;
+    s->plan_ok = true;
+    s->dev_bytes += (long long)s->plan.spec_bytes();
+    for (int d = 0; d < 3; ++d) {
+        if (s->prm.haloed) { s->pdims[d] = s->n[d] + s->plan.hp[d] + s->plan.hm[d]; s->porigin[d] = s->plan.hm[d]; }
+        else { s->pdims[d] = s->n[d]; s->porigin[d] = 0; }
+    }
+    s->pelems = (long long)s->pdims[0] * s->pdims[1] * s->pdims[2];
+    if (!s->d_psi) s->d_psi = (float*)s->dalloc((size_t)s->pelems * sizeof(float));
+    if (!s->d_tmp) s->d_tmp = (float*)s->dalloc((size_t)s->pelems * sizeof(float));
+    s->init_kernels();
+    for (int v = 0; v < V; ++v) {
+        if (!s->d_kh1[v]) s->d_kh1[v] = (float2*)s->dalloc(s->plan.spec_bytes());
+        if (!s->d_kh2[v]) s->d_kh2[v] = (float2*)s->dalloc(s->plan.spec_bytes());
+        // kernels smaller than kmax are spectrum-transformed with their own dims
+        ConvPlan& pl = s->plan;
+        int save[3] = {pl.k[0], pl.k[1], pl.k[2]};
+        for (int d = 0; d < 3; ++d) pl.k[d] = s->k1[v].d[d];
+        pl.kernel_spectrum(s->k1[v].v.data(), s->d_kh1[v], s->stream);
+        pl.kernel_spectrum(s->k2[v].v.data(), s->d_kh2[v], s->stream);
+        for (int d = 0; d < 3; ++d) pl.k[d] = save[d];
+    }
+    rt::stream_sync(s->stream);
+    return 0;
+}
+
+int mvd_init(mvd_session* s) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_init: null session");
+    rt::set_device(s->prm.device);
+    if (int rc = session_prepare(s)) return rc;
+    if (s->prm.haloed) return 0;   // brick mode: caller all-reduces mvd_init_partials and calls mvd_set_avg
+    double part[6];
+    s->partials(part);
+    double avg; int mn; double av;
+    mvd_session::reduce_partials(s->prm.generation, part, avg, mn, av);
+    s->min_overlap = mn; s->avg_overlap = av;
+    double osem = s->prm.osem_speedup;
+    if (s->prm.generation == 1) {
+        if (s->prm.osem_index == 1) osem = std::max(1.0, (double)mn);
+        else if (s->prm.osem_index == 2) osem = std::max(1.0, av);
+    }
+    s->apply_avg(avg, osem);
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_init_partials(mvd_session* s, double partial[6]) {
+    SPIM_API_BEGIN
+    if (!s || !partial) return fail("mvd_init_partials: null argument");
+    if (!s->plan_ok) return fail("mvd_init_partials: call mvd_init first");
+    rt::set_device(s->prm.device);
+    s->partials(partial);
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_set_avg(mvd_session* s, double avg, double osem) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_set_avg: null session");
+    if (!s->plan_ok) return fail("mvd_set_avg: call mvd_init first");
+    rt::set_device(s->prm.device);
+    s->apply_avg(avg, osem);
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_run(mvd_session* s, int n_iterations, double* sum_change, double* max_change) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_run: null session");
+    if (!s->inited) return fail("mvd_run: session not initialised (mvd_init)");
+    if (s->prm.haloed) return fail("mvd_run: brick-mode sessions are driven with mvd_view_phase");
+    if (n_iterations < 0) return fail("mvd_run: negative iteration count");
+    rt::set_device(s->prm.device);
+    const int V = s->prm.num_views;
+    const size_t slots = (size_t)n_iterations * V;
+    if (slots == 0) return 0;
+    s->ensure_stats(slots);
+    rt::dzero(s->d_stat_sum, slots * sizeof(double), s->stream);
+    rt::dzero(s->d_stat_max, slots * sizeof(unsigned int), s->stream);
+    for (int it = 0; it < n_iterations; ++it)
+        for (int v = 0; v < V; ++v) {
+            const size_t slot = (size_t)it * V + v;
+            s->phase(v, 0, nullptr, nullptr);
+            s->phase(v, 1, s->d_stat_sum + slot, s->d_stat_max + slot);
+        }
+    if (sum_change || max_change) {
+        std::vector<double> hs(slots);
+        std::vector<unsigned int> hm(slots);
+        rt::d2h(hs.data(), s->d_stat_sum, slots * sizeof(double), s->stream);
+        rt::d2h(hm.data(), s->d_stat_max, slots * sizeof(unsigned int), s->stream);
+        rt::stream_sync(s->stream);
+        for (size_t i = 0; i < slots; ++i) {
+            if (sum_change) sum_change[i] = hs[i];
+            if (max_change) { float f; memcpy(&f, &hm[i], 4); max_change[i] = (double)f; }
+        }
+    } else {
+        rt::stream_sync(s->stream);
+    }
+    s->timer.collect(s->t_ms, s->t_cnt, 8);
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_view_phase(mvd_session* s, int view, int phase, double* stats) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_view_phase: null session");
+    if (!s->inited) return fail("mvd_view_phase: session not initialised");
+    if (view < 0 || view >= s->prm.num_views || (phase != 0 && phase != 1)) return fail("mvd_view_phase: bad view/phase");
+    rt::set_device(s->prm.device);
+    if (phase == 1) {
+        s->ensure_stats(1);
+        rt::dzero(s->d_stat_sum, sizeof(double), s->stream);
+        rt::dzero(s->d_stat_max, sizeof(unsigned int), s->stream);
+        s->phase(view, 1, s->d_stat_sum, s->d_stat_max);
+        if (stats) {
+            double hs; unsigned int hm;
+            rt::d2h(&hs, s->d_stat_sum, sizeof(double), s->stream);
+            rt::d2h(&hm, s->d_stat_max, sizeof(unsigned int), s->stream);
+            rt::stream_sync(s->stream);
+            float f; memcpy(&f, &hm, 4);
+            stats[0] = hs; stats[1] = (double)f;
+        }
+    } else {
+        s->phase(view, 0, nullptr, nullptr);
+    }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_finish(mvd_session* s) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_finish: null session");
+    if (!s->inited) return fail("mvd_finish: session not initialised");
+    rt::set_device(s->prm.device);
+    if (s->prm.generation == 2) {
+        MaskK::Params p;
+        p.v = s->view_ptrs(); p.psi = s->d_psi;
+        for (int d = 0; d < 3; ++d) { p.pdims[d] = s->pdims[d]; p.porigin[d] = s->porigin[d]; p.n[d] = s->n[d]; }
+        p.nblocks = ew_blocks(s->N);
+        rt::launch<MaskK>(p, p.nblocks, kThreads, 0, s->stream);
+    }
+    rt::stream_sync(s->stream);
+    return 0;
+    SPIM_API_END
+}
+
+static void copy_region(mvd_session* s, const float* src, const int sd[3], const int so[3], float* dst, const int dd[3], const int dof[3]) {
+    CopyRegionK::Params p;
+    p.src = src; p.dst = dst;
+    for (int d = 0; d < 3; ++d) { p.sdims[d] = sd[d]; p.sorigin[d] = so[d]; p.ddims[d] = dd[d]; p.dorigin[d] = dof[d]; p.n[d] = s->n[d]; }
+    p.nblocks = ew_blocks(s->N);
+    rt::launch<CopyRegionK>(p, p.nblocks, kThreads, 0, s->stream);
+}
+
+int mvd_get_psi(mvd_session* s, float* out) {
+    SPIM_API_BEGIN
+    if (!s || !out) return fail("mvd_get_psi: null argument");
+    if (!s->d_psi) return fail("mvd_get_psi: session not initialised");
+    rt::set_device(s->prm.device);
+    const size_t bytes = (size_t)s->N * sizeof(float);
+    if (!s->prm.haloed) {
+        rt::d2h(out, s->d_psi, bytes, s->stream);
+        rt::stream_sync(s->stream);
+    } else {
+        float* t = (float*)rt::dmalloc(bytes);
+        const int zero[3] = {0, 0, 0};
+        copy_region(s, s->d_psi, s->pdims, s->porigin, t, s->n, zero);
+        rt::d2h(out, t, bytes, s->stream);
+        rt::stream_sync(s->stream);
+        rt::dfree(t);
+    }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_set_psi(mvd_session* s, const float* in) {
+    SPIM_API_BEGIN
+    if (!s || !in) return fail("mvd_set_psi: null argument");
+    if (!s->d_psi) return fail("mvd_set_psi: session not initialised");
+    rt::set_device(s->prm.device);
+    const size_t bytes = (size_t)s->N * sizeof(float);
+    if (!s->prm.haloed) {
+        rt::h2d(s->d_psi, in, bytes, s->stream);
+        rt::stream_sync(s->stream);
+    } else {
+        float* t = (float*)rt::dmalloc(bytes);
+        rt::h2d(t, in, bytes, s->stream);
+        const int zero[3] = {0, 0, 0};
+        copy_region(s, t, s->n, zero, s->d_psi, s->pdims, s->porigin);
+        rt::stream_sync(s->stream);
+        rt::dfree(t);
+    }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_get_kernel(mvd_session* s, int view, int which, float* out) {
+    SPIM_API_BEGIN
+    if (!s || !out) return fail("mvd_get_kernel: null argument");
+    if (view < 0 || view >= s->prm.num_views || (which != 1 && which != 2)) return fail("mvd_get_kernel: bad view/which");
+    if (s->k1.empty()) return fail("mvd_get_kernel: call mvd_init first");
+    const HostVol& k = which == 1 ? s->k1[view] : s->k2[view];
+    memcpy(out, k.v.data(), k.v.size() * sizeof(float));
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_get_info(mvd_session* s, mvd_info* o) {
+    SPIM_API_BEGIN
+    if (!s || !o) return fail("mvd_get_info: null argument");
+    memset(o, 0, sizeof(*o));
+    o->avg = s->avg; o->osem = s->osem; o->min_overlap = s->min_overlap; o->avg_overlap = s->avg_overlap;
+    o->n_voxels = s->N;
+    o->device_bytes = s->dev_bytes;
+    if (s->plan_ok) {
+        for (int d = 0; d < 3; ++d) { o->fft_dims[d] = s->plan.P[d]; o->halo_lo[d] = s->plan.hm[d]; o->halo_hi[d] = s->plan.hp[d]; }
+        o->pitch = s->plan.pitch;
+        o->np_voxels = s->plan.padded_min_voxels();
+    }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_sync(mvd_session* s) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_sync: null session");
+    rt::set_device(s->prm.device);
+    rt::stream_sync(s->stream);
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_set_timing(mvd_session* s, int on) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_set_timing: null session");
+    rt::set_device(s->prm.device);
+    rt::stream_sync(s->stream);
+    s->timer.reset();
+    s->timer.enable(on != 0);
+    for (int i = 0; i < 8; ++i) { s->t_ms[i] = 0; s->t_cnt[i] = 0; }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_get_timing(mvd_session* s, double ms[8], long long launches[8]) {
+    SPIM_API_BEGIN
+    if (!s || !ms || !launches) return fail("mvd_get_timing: null argument");
+    rt::set_device(s->prm.device);
+    rt::stream_sync(s->stream);
+    s->timer.collect(s->t_ms, s->t_cnt, 8);
+    for (int i = 0; i < 8; ++i) { ms[i] = s->t_ms[i]; launches[i] = s->t_cnt[i]; }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_get_device_buffer(mvd_session* s, int which, void** dptr, int dims[3], int origin[3]) {
+    SPIM_API_BEGIN
+    if (!s || !dptr || !dims || !origin) return fail("mvd_get_device_buffer: null argument");
+    if (!s->d_psi) return fail("mvd_get_device_buffer: call mvd_init first");
+    *dptr = which == 0 ? (void*)s->d_psi : (void*)s->d_tmp;
+    for (int d = 0; d < 3; ++d) { dims[d] = s->pdims[d]; origin[d] = s->porigin[d]; }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_fill_halo: null session");
+    if (!s->prm.haloed || !s->d_psi) return fail("mvd_fill_halo: not a brick-mode session / not initialised");
+    rt::set_device(s->prm.device);
+    const int ext = which == 0 ? s->conv1_ext() : s->conv2_ext();
+    const float value = which == 0 ? 0.f : 1.f;
+    for (int axis = 2; axis >= 0; --axis) {
+        for (int side = 0; side < 2; ++side) {
+            const int mask = side == 0 ? lo_mask : hi_mask;
+            if (!(mask & (1 << axis))) continue;
+            const int width = side == 0 ? s->plan.hm[axis] : s->plan.hp[axis];
+            if (width <= 0) continue;
+            HaloFillK::Params p;
+            p.buf = which == 0 ? s->d_psi : s->d_tmp;
+            for (int d = 0; d < 3; ++d) { p.dims[d] = s->pdims[d]; p.origin[d] = s->porigin[d]; p.n[d] = s->n[d]; }
+            p.axis = axis; p.side = side; p.width = width; p.ext = ext; p.value = value;
+            long long total = (long long)width;
+            for (int d = 0; d < 3; ++d) if (d != axis) total *= s->pdims[d];
+            p.nblocks = ew_blocks(total);
+            rt::launch<HaloFillK>(p, p.nblocks, kThreads, 0, s->stream);
+        }
+    }
+    return 0;
+    SPIM_API_END
+}
+
+// ---- stand-alone helpers ---------------------------------------------------------------------
+static std::mutex g_ws_mutex[64];
+static ConvWorkspace* g_ws[64][2] = {{nullptr}};   // per device: [0] general, [1] legacy (periodic-exact)
+
+static int convolve_common(const float* img, const int im_dims[3], const float* kernel, const int kdims[3],
+                           int ext, float value, float* out, int device, bool legacy) {
+    if (!img || !im_dims || !kernel || !kdims || !out) return fail("convolve: null argument");
+    for (int d = 0; d < 3; ++d) if (im_dims[d] < 1 || kdims[d] < 1) return fail("convolve: bad dims");
+    const int ndev = rt::device_count();
+    if (ndev <= 0) return fail("convolve: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev || device >= 64) return fail("convolve: bad device ordinal");
+    std::lock_guard<std::mutex> lock(g_ws_mutex[device]);
+    rt::set_device(device);
+    ConvWorkspace*& ws = g_ws[device][legacy ? 1 : 0];
+    if (!ws) ws = new ConvWorkspace();
+    ws->ensure(im_dims, kdims, legacy);
+    ws->run(img, kernel, ext, value, out);
+    return 0;
+}
+
+int mvd_convolve(const float* img, const int im_dims[3], const float* kernel, const int kernel_dims[3],
+                 int ext, float ext_value, float* out, int device) {
+    SPIM_API_BEGIN
+    if (ext < 0 || ext > 4) return fail("mvd_convolve: bad extension mode");
+    return convolve_common(img, im_dims, kernel, kernel_dims, ext, ext_value, out, device, false);
+    SPIM_API_END
+}
+
+int mvd_fft_size(int min_n, int need_even) { return choose_fft_size(min_n, need_even != 0); }
+
+// ================================================================================================
+// legacy JNA boundary (include/spim_fftconv.h)
+// ================================================================================================
+const char* spim_fftconv_last_error(void) { return g_last_error.c_str(); }
+
+int getNumDevicesCUDA(void) { return rt::device_count(); }
+
+#if defined(SPIM_HOST_EMU)
+int getCUDAcomputeCapabilityMajorVersion(int) { return 10; }
+int getCUDAcomputeCapabilityMinorVersion(int) { return 0; }
+void getNameDeviceCUDA(int, char* name) { if (name) { memset(name, 0, 256); strcpy(name, "HOST EMULATOR (tests only)"); } }
+long long getMemDeviceCUDA(int) { return 1LL << 34; }
+long long getFreeMemDeviceCUDA(int) { return 1LL << 34; }
+#else
+static bool dev_prop(int dev, cudaDeviceProp& p) {
+    const int n = rt::device_count();
+    if (dev < 0 || dev >= n) return false;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+int getCUDAcomputeCapabilityMajorVersion(int dev) { cudaDeviceProp p; return dev_prop(dev, p) ? p.major : -1; }
+int getCUDAcomputeCapabilityMinorVersion(int dev) { cudaDeviceProp p; return dev_prop(dev, p) ? p.minor : -1; }
+void getNameDeviceCUDA(int dev, char* name) {
+    if (!name) return;
+    memset(name, 0, 256);
+    cudaDeviceProp p;
+    if (dev_prop(dev, p)) strncpy(name, p.name, 255);
+}
+long long getMemDeviceCUDA(int dev) { cudaDeviceProp p; return dev_prop(dev, p) ? (long long)p.totalGlobalMem : -1; }
+long long getFreeMemDeviceCUDA(int dev) {
+    const int n = rt::device_count();
+    if (dev < 0 || dev >= n) return -1;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cudaSetDevice(cur);
+    return (long long)fr;
+}
+#endif
+
+void convolution3DfftCUDAInPlace(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA) {
+    int rc = 1;
+    try {
+        rc = convolve_common(im, imDim, kernel, kernelDim, EXT_PERIODIC, 0.f, im, devCUDA, true);
+    } catch (const std::exception& e) { fail(e.what()); }
+    catch (...) { fail("unknown error"); }
+    if (rc) fprintf(stderr, "convolution3DfftCUDAInPlace failed: %s (buffer left untouched)\n", g_last_error.c_str());
+}
+
+float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA) {
+    if (!im || !imDim) { fail("convolution3DfftCUDA: null argument"); return nullptr; }
+    const size_t nvox = (size_t)imDim[0] * imDim[1] * imDim[2];
+    float* out = (float*)malloc(nvox * sizeof(float));
+    if (!out) { fail("convolution3DfftCUDA: out of host memory"); return nullptr; }
+    int rc = 1;
+    try {
+        rc = convolve_common(im, imDim, kernel, kernelDim, EXT_PERIODIC, 0.f, out, devCUDA, true);
+    } catch (const std::exception& e) { fail(e.what()); }
+    catch (...) { fail("unknown error"); }
+    if (rc) {
+        fprintf(stderr, "convolution3DfftCUDA failed: %s\n", g_last_error.c_str());
+        free(out);
+        return nullptr;
+    }
+    return out;
+}
+
+}  // extern "C"
