@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- multi-view deconvolution throughput (voxel-view-iterations/s) on N B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): per GPU a
+512x512x256 fp32 volume, 7 views, 31^3 PSFs, Efficient-Bayesian, Tikhonov lambda 0.006,
+synthetic specimen data.  One step = one full iteration (7 view-steps = 14 FFT convolutions with
+their fused ratio / update epilogues).  At N > 1 the global volume is N bricks of that size
+(2 -> 1024x512x256, 4 -> 1024x1024x256, 8 -> 1024x1024x512 = the size of configs[2]) with the
+PSF/2-wide halos exchanged over NCCL every convolution: weak scaling.
+
+value    = N_voxels(global) * views * K / device time of K iterations, inputs resident in HBM.
+e2e      = the same metric through the reference-facing call (the MVDeconvolution constructor
+           equivalent: session create + upload of all views from pinned host memory + init +
+           K iterations + mask + download of psi), host<->device copies inside the timed region.
+roofline = dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+BRICK = (256, 512, 512)      # (z, y, x) per GPU
+VIEWS = 7
+PSF = 31
+LAMBDA = 0.006
+ITER_TYPE = 2                # EFFICIENT_BAYESIAN
+METRIC = "MV deconvolution voxel-view-iterations/s"
+UNIT = "voxel-view-iterations/s"
+KERNEL_NAMES = ["x_fwd_r2c", "y_fwd", "z_fwd_mul_inv", "y_inv", "x_inv_c2r_epilogue"]
+KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor * Np
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(shape, rank_seed=0):
+    """Synthetic specimen views for one brick; the forward blur runs on the GPU through mvd_convolve."""
+    from spim_registration_b200 import native, synthetic
+    lib = native.load_library()
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def blur(t, k):
+        return native.convolve(t, k, 2, 0.0, device=dev, lib=lib)
+
+    truth = synthetic.specimen_truth(shape, seed=2929 + rank_seed)
+    psfs = synthetic.make_psfs(VIEWS, PSF)
+    imgs, ws = synthetic.make_views(truth, psfs, seed=7 + rank_seed, blur=blur)
+    return imgs, ws, psfs
+
+
+def cpu_reference_step(imgs, ws, psfs, psi, k1, k2, v):
+    """One view-step of the oracle (SciPy pocketfft on every host core) -- the CPU restatement of the
+    reference's Java path (the JVM and its jars are not available)."""
+    from oracle import mvdecon_oracle as O
+    p = O.DeconParams(iteration_type=ITER_TYPE, lam=LAMBDA, gen=O.GEN2)
+    new, _, _ = O.view_step(psi, imgs[v], ws[v], k1[v], k2[v], p)
+    return new
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement, all host threads, one view-step per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import mvdecon_oracle as O
+    from spim_registration_b200 import synthetic
+    shape = BRICK
+    truth = synthetic.specimen_truth(shape)
+    psfs = synthetic.make_psfs(VIEWS, PSF)
+    nsample = min(VIEWS, 2)                          # views actually materialised for the sample
+    imgs, ws = synthetic.make_views(truth, psfs[:nsample], seed=7)
+    k1, k2 = O.init_kernels(psfs, ITER_TYPE)
+    psi = np.full(shape, np.float32(0.05), np.float32)
+    for i in range(args.warmup):
+        psi = cpu_reference_step(imgs, ws, psfs, psi, k1, k2, i % nsample)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        psi = cpu_reference_step(imgs, ws, psfs, psi, k1, k2, i % nsample)
+    dt = time.perf_counter() - t0
+    nvox = int(np.prod(shape))
+    value = nvox * args.steps / dt                   # one view-step = N voxel-view-iterations
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "7-view 512x512x256 fp32, 31^3 PSFs, Efficient-Bayesian, lambda 0.006; "
+                               "each step = ONE view-step (1/7 iteration) of that workload on the host CPU",
+                   "l2": "inputs (256 MiB per volume) larger than any cache"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} view-steps of the 512x512x256 workload, CPU restatement of the "
+                                   "reference (NumPy + SciPy pocketfft, workers = all cores); reference JVM unavailable"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
+    ap.add_argument("--views", type=int, default=None)
+    args = ap.parse_args()
+    global BRICK, VIEWS
+    if args.brick:
+        BRICK = tuple(args.brick)
+    if args.views:
+        VIEWS = args.views
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from spim_registration_b200 import build as b
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        b.build_cuda_library()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    if world != args.gpus:
+        if rank == 0:
+            sys.stderr.write(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE\n")
+    N = world
+
+    from spim_registration_b200 import native
+    from spim_registration_b200.deconvolution import Session
+    from spim_registration_b200 import bricks
+
+    grid = bricks.grid_for(N)                        # bricks along (z, y, x)
+    coords = bricks.rank_coords(rank, grid)
+    gshape = tuple(BRICK[d] * grid[d] for d in range(3))
+    imgs, ws, psfs = make_inputs(BRICK, rank_seed=rank)
+    nvox_brick = int(np.prod(BRICK))
+    nvox_global = nvox_brick * N
+
+    # pinned host copies (the hand-over format of the reference: materialised fp32 arrays)
+    pin_img = [torch.from_numpy(a).pin_memory() for a in imgs]
+    pin_w = [torch.from_numpy(a).pin_memory() for a in ws]
+    pin_out = torch.empty(BRICK, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for t in pin_img + pin_w) + sum(p.size * 4 for p in psfs)
+    d2h_bytes = pin_out.numel() * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def new_runner():
+        r = bricks.BrickRunner(BRICK, VIEWS, ITER_TYPE, generation=2, lam=LAMBDA, device=local, rank=rank,
+                               world=N, grid=grid, dist=dist)
+        return r
+
+    def upload(r):
+        for v in range(VIEWS):
+            r.session.set_view_ptr(v, pin_img[v].data_ptr(), pin_w[v].data_ptr(), psfs[v])
+
+    # ---------------- device-resident throughput -------------------------------------------------
+    runner = new_runner()
+    upload(runner)
+    runner.init()
+    info = runner.session.info()
+    np_brick = int(info.np_voxels)
+    stream = torch.cuda.ExternalStream(runner.session.stream(), device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        runner.run(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    runner.run(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = nvox_global * VIEWS * args.steps / (ms * 1e-3)
+    launches = 10 * VIEWS * args.steps * 1 + runner.extra_launches_per_iteration() * args.steps
+
+    # ---------------- per-kernel timing for the roofline (separate run, events around every launch) -----
+    runner.session.set_timing(True)
+    runner.run(max(2, min(args.steps, 5)))
+    kms, kcnt = runner.session.get_timing()
+    runner.session.set_timing(False)
+    peak, peak_src = peaks()
+    per_kernel = {}
+    for i, name in enumerate(KERNEL_NAMES):
+        if kcnt[i] > 0:
+            avg_ms = kms[i] / kcnt[i]
+            alg = KERNEL_ALG_FACTOR[i] * np_brick
+            per_kernel[name] = {"avg_ms": avg_ms, "launches": int(kcnt[i]), "alg_bytes": alg,
+                                "gbs": alg / (avg_ms * 1e-3) / 1e9}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = None
+    conv_pass = None
+    if dom:
+        a = per_kernel[dom]["gbs"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_kernel[dom]["alg_bytes"], "avg_ms": per_kernel[dom]["avg_ms"]}
+        tot_ms = sum(per_kernel[k]["avg_ms"] for k in per_kernel)
+        a2 = 44 * np_brick / (tot_ms * 1e-3) / 1e9
+        conv_pass = {"achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "ms_per_conv": tot_ms,
+                     "alg_bytes": 44 * np_brick, "per_kernel": per_kernel}
+    runner.close()
+    del runner
+
+    # ---------------- end to end through the reference-facing call -------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    r2 = new_runner()
+    upload(r2)
+    r2.init()
+    r2.run(args.steps)
+    r2.finish()
+    r2.session.get_psi_ptr(pin_out.data_ptr())
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    r2.close()
+    e2e_value = nvox_global * VIEWS * args.steps / t_e2e
+
+    # ---------------- CPU baseline: the oracle on a bounded sample (rank 0, N = 1 only) --------------------
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        from oracle import mvdecon_oracle as O
+        k1, k2 = O.init_kernels(psfs, ITER_TYPE)
+        psi = np.full(BRICK, np.float32(info.avg), np.float32)
+        nsteps = 2
+        t0 = time.perf_counter()
+        for v in range(nsteps):
+            psi = cpu_reference_step(imgs, ws, psfs, psi, k1, k2, v)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nvox_brick * nsteps / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nsteps} view-steps (of {VIEWS * args.steps}) of the same {BRICK[2]}x{BRICK[1]}x{BRICK[0]} "
+                         "workload; CPU restatement of the reference (NumPy + SciPy pocketfft, all cores); "
+                         "reference JVM unavailable"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{VIEWS}-view {gshape[2]}x{gshape[1]}x{gshape[0]} fp32 "
+                                   f"({N} brick(s) of {BRICK[2]}x{BRICK[1]}x{BRICK[0]}), {PSF}^3 PSFs, "
+                                   "Efficient-Bayesian, lambda 0.006, gen-2 semantics; step = one iteration over all views",
+                       "fft_dims_zyx": list(info.fft_dims), "np_voxels_per_brick": np_brick,
+                       "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), NCCL halo exchange" if N > 1 else "single GPU",
+                       "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / args.steps,
+                    "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e,
+                    "note": "whole call: create + upload all views from pinned memory + init + K iterations + mask + download psi"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_conv_pass": conv_pass,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

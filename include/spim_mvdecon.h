@@ -88,6 +88,8 @@ int mvd_set_psi(mvd_session* s, const float* in);     /* 'initialImage' hook */
 int mvd_get_kernel(mvd_session* s, int view, int which /*1 or 2*/, float* out);  /* getKernel1/2 */
 int mvd_get_info(mvd_session* s, mvd_info* out);
 int mvd_sync(mvd_session* s);
+/* the CUDA stream (cudaStream_t) every kernel of this session is launched on, for event timing */
+int mvd_get_stream(mvd_session* s, void** stream);
 
 /* per-kernel-class CUDA-event timing (bench.py's roofline leg): ids 0 x-fwd, 1 y-fwd,
  * 2 z-fwd*K*z-inv, 3 y-inv, 4 x-inv+epilogue, 5 z-fwd (kernel spectra), 6 misc */

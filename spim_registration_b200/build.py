@@ -15,7 +15,7 @@ OUT = os.path.join(HERE, "libConvolution3D_fftCUDAlib.so")
 ALIAS = os.path.join(HERE, "libFourierConvolutionCUDALib.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared"]
+              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def is_stale() -> bool:

@@ -844,6 +844,14 @@ int mvd_sync(mvd_session* s) {
     SPIM_API_END
 }
 
+int mvd_get_stream(mvd_session* s, void** stream) {
+    SPIM_API_BEGIN
+    if (!s || !stream) return fail("mvd_get_stream: null argument");
+    *stream = (void*)(uintptr_t)s->stream;
+    return 0;
+    SPIM_API_END
+}
+
 int mvd_set_timing(mvd_session* s, int on) {
     SPIM_API_BEGIN
     if (!s) return fail("mvd_set_timing: null session");

@@ -145,6 +145,11 @@ class Session:
     def sync(self):
         native.check(self.lib, self.lib.mvd_sync(self._h), "mvd_sync")
 
+    def stream(self) -> int:
+        st = C.c_void_p()
+        native.check(self.lib, self.lib.mvd_get_stream(self._h, C.byref(st)), "mvd_get_stream")
+        return st.value or 0
+
     def set_timing(self, on: bool):
         native.check(self.lib, self.lib.mvd_set_timing(self._h, 1 if on else 0), "mvd_set_timing")
 

@@ -68,7 +68,7 @@ LEGACY_SYMBOLS = (
 )
 SESSION_SYMBOLS = (
     "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_init", "mvd_run",
-    "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_set_timing",
+    "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_get_stream", "mvd_set_timing",
     "mvd_get_timing", "mvd_get_device_buffer", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
     "mvd_set_avg", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
 )
@@ -127,6 +127,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_get_info.restype = C.c_int
     lib.mvd_sync.argtypes = [S]
     lib.mvd_sync.restype = C.c_int
+    lib.mvd_get_stream.argtypes = [S, C.POINTER(C.c_void_p)]
+    lib.mvd_get_stream.restype = C.c_int
     lib.mvd_set_timing.argtypes = [S, C.c_int]
     lib.mvd_set_timing.restype = C.c_int
     lib.mvd_get_timing.argtypes = [S, c_double_p, C.POINTER(C.c_longlong)]
