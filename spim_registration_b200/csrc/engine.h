@@ -46,7 +46,7 @@ inline bool plan_radices(int n, std::vector<int>& best) {
             if (!best.empty() && cur.size() + 1 > best.size()) return;
             for (int i = start; i < 15; ++i) {
                 int r = allowed[i];
-                if (rem % r) continue;
+                if (r > SPIM_MAX_RADIX || rem % r) continue;
                 cur.push_back(r);
                 go(rem / r, i, cur, best, best_sum);
                 cur.pop_back();
@@ -94,15 +94,23 @@ struct FftPlanHost {
             dev.M[s] = n / prod;
             dev.magicM[s] = dev.M[s] > 1 ? (uint32_t)((0x100000000ull / (uint64_t)dev.M[s]) + 1ull) : 0u;
         }
-        std::vector<float2> tw(n);
-        for (int t = 0; t < n; ++t) {
-            const double a = -2.0 * 3.14159265358979323846 * (double)t / (double)n;
-            tw[t] = make_float2((float)cos(a), (float)sin(a));
+        // per-stage twiddle tables, contiguous per butterfly: [j][p-1] = exp(-2 pi i j p / (M*R))
+        std::vector<float2> tw;
+        for (int s = 0; s < dev.nstages; ++s) {
+            const int R = dev.radix[s], M = dev.M[s], L = M * R;
+            dev.tw_off[s] = (int)tw.size();
+            if (M == 1) continue;
+            for (int j = 0; j < M; ++j)
+                for (int p = 1; p < R; ++p) {
+                    const double a = -2.0 * 3.14159265358979323846 * (double)j * (double)p / (double)L;
+                    tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+                }
         }
-        d_tw = (float2*)rt::dmalloc(sizeof(float2) * n);
-        rt::h2d(d_tw, tw.data(), sizeof(float2) * n, 0);
+        if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+        d_tw = (float2*)rt::dmalloc(sizeof(float2) * tw.size());
+        rt::h2d(d_tw, tw.data(), sizeof(float2) * tw.size(), 0);
         rt::stream_sync(0);
-        dev.tw = d_tw;
+        dev.tws = d_tw;
         pos.resize(n);
         for (int k = 0; k < n; ++k) {
             int rem = k, p = 0;
@@ -116,6 +124,17 @@ struct FftPlanHost {
     }
     void destroy() { rt::dfree(d_tw); d_tw = nullptr; }
 };
+
+// block sizes (tunable through the environment for experiments; defaults chosen from ncu runs)
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int r = atoi(v);
+    return (r >= 32 && r <= 256 && r % 32 == 0) ? r : dflt;
+}
+inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 256); return t; }
+inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 256); return t; }
+inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 256); return t; }
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
 
@@ -231,7 +250,7 @@ public:
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         if (timer) timer->begin(K_XFWD, st);
-        rt::launch<XFwd>(p, grid, kThreads, smem, st);
+        rt::launch<XFwd>(p, grid, threads_xfwd(), smem, st);
         if (timer) timer->end(K_XFWD, st);
     }
 
@@ -255,7 +274,7 @@ public:
         const long long grid = (long long)p.ntx * outer_count;
         const size_t smem = (size_t)Pa * TC * sizeof(float2);
         if (timer) timer->begin(id, st);
-        rt::launch<ColPass>(p, grid, kThreads, smem, st);
+        rt::launch<ColPass>(p, grid, threads_col(), smem, st);
         if (timer) timer->end(id, st);
     }
 
@@ -281,7 +300,7 @@ public:
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
         if (timer) timer->begin(K_XINV, st);
-        rt::launch<XInv>(p, grid, kThreads, smem, st);
+        rt::launch<XInv>(p, grid, threads_xinv(), smem, st);
         if (timer) timer->end(K_XINV, st);
     }
 

@@ -12,6 +12,8 @@
 
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #define SPIM_DEV inline
 #define SPIM_HD inline
 #define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)

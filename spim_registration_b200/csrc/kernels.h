@@ -30,6 +30,7 @@
 namespace spim {
 
 constexpr int TC = 16;            // tile columns (float2) = one 128-byte segment per row
+constexpr int TP = 8;             // the same row as float4 column pairs
 constexpr int MAX_STAGES = 6;
 constexpr int kThreads = 256;
 
@@ -43,7 +44,8 @@ struct FftPlanDev {
     int radix[MAX_STAGES];
     int M[MAX_STAGES];            // sub-transform length after stage s: n / (radix[0]*...*radix[s])
     uint32_t magicM[MAX_STAGES];  // floor(2^32 / M) + 1, for m / M with m < 2^16
-    const float2* tw;             // exp(-2 pi i t / n), t in [0, n)
+    int tw_off[MAX_STAGES];       // offset of stage s in tws
+    const float2* tws;            // per-stage twiddles: tws[tw_off[s] + j*(R-1) + (p-1)] = exp(-2 pi i j p / (M*R))
 };
 
 SPIM_DEV int fastdiv(int m, uint32_t magic) { return (int)spim_umulhi((uint32_t)m, magic); }
@@ -86,70 +88,105 @@ SPIM_HD int pad_to_coord(int u, int n, int hp, int hm, int P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// generic in-place radix stage on a [rows][16] tile
+// generic in-place radix stage on a [rows][8] tile of float4 (= 16 float2 columns).
+// One work item = one radix-R butterfly on TWO adjacent columns (one 128-bit access per row).
 // ---------------------------------------------------------------------------------------------
 struct GRows {          // the global-memory side of a column tile
-    float2* p;          // element (row 0, col 0)
-    long long stride;   // float2 units between consecutive rows
+    float2* p;          // element (row 0, col 0), 16-byte aligned
+    long long stride;   // float2 units between consecutive rows (even)
     int va, vb;         // rows that hold data on load: [0, va) U [vb, n); others read as zero
     int sa;             // rows written on store: [0, sa)
 };
 
+SPIM_HD float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+SPIM_HD float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+SPIM_HD float4 pack4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+
 template <int R, bool INV>
-SPIM_DEV void apply_twiddles(float2 (&a)[R], const float2* tw, int t1) {
-    // a[p] *= w^(p), w = tw[t1] ; indices t1*p < n by construction
+SPIM_DEV void apply_twiddles2(float2 (&a)[R], float2 (&b)[R], const float2* tw) {
 #pragma unroll
     for (int p = 1; p < R; ++p) {
-        const float2 w = spim_ldg(tw + t1 * p);
+        const float2 w = spim_ldg(tw + (p - 1));
+        a[p] = INV ? cmulc(a[p], w) : cmul(a[p], w);
+        b[p] = INV ? cmulc(b[p], w) : cmul(b[p], w);
+    }
+}
+template <int R, bool INV>
+SPIM_DEV void apply_twiddles1(float2 (&a)[R], const float2* tw) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) {
+        const float2 w = spim_ldg(tw + (p - 1));
         a[p] = INV ? cmulc(a[p], w) : cmul(a[p], w);
     }
 }
 
+// physical float4 slot of column pair c2 in row `row` (x kernels rotate the pairs so that the
+// transposing first / last phases are conflict-free)
+SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
+
 template <int R, bool INV>
-SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float2* tile, int swz, int src_g, int dst_g, const GRows& g) {
+SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     const int M = pl.M[s];
     const int L = M * R;
     const int nb = pl.n / R;
-    const int ts = pl.n / L;
     const uint32_t magic = pl.magicM[s];
-    SPIM_FOR_ITEMS(i, nb * TC) {
-        const int c = i & (TC - 1);
-        const int m = i >> 4;
+    const float2* twp = pl.tws + pl.tw_off[s];
+    const long long gs4 = g.stride >> 1;
+    const long long gstep = (long long)M * gs4;
+    SPIM_FOR_ITEMS(i, nb * TP) {
+        const int c2 = i & (TP - 1);
+        const int m = i >> 3;
         const int blk = (M == 1) ? m : fastdiv(m, magic);
         const int j = m - blk * M;
         const int base = blk * L + j;
-        float2 a[R];
+        float2 a[R], b[R];
         if (src_g) {
+            const float4* gp = reinterpret_cast<const float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                a[q] = (row < g.va || row >= g.vb) ? spim_ldg(g.p + (long long)row * g.stride + c) : make_float2(0.f, 0.f);
+                const float4 v = spim_ldg(gp + q * gstep);   // gap rows hold stale data: load anyway, select zero
+                const bool ok = (row < g.va) || (row >= g.vb);
+                a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
+                b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
             }
+        } else if (!swz) {
+            const float4* sp = tile + base * TP + c2;
+#pragma unroll
+            for (int q = 0; q < R; ++q) { const float4 v = sp[q * M * TP]; a[q] = lo2(v); b[q] = hi2(v); }
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                a[q] = tile[row * TC + (swz ? ((c + row) & (TC - 1)) : c)];
+                const float4 v = tile[row * TP + ((c2 + row) & (TP - 1))];
+                a[q] = lo2(v); b[q] = hi2(v);
             }
         }
         if (!INV) {
             dft<R, false>(a);
-            if (M > 1) apply_twiddles<R, false>(a, pl.tw, j * ts);
+            dft<R, false>(b);
+            if (M > 1) apply_twiddles2<R, false>(a, b, twp + j * (R - 1));
         } else {
-            if (M > 1) apply_twiddles<R, true>(a, pl.tw, j * ts);
+            if (M > 1) apply_twiddles2<R, true>(a, b, twp + j * (R - 1));
             dft<R, true>(a);
+            dft<R, true>(b);
         }
         if (dst_g) {
+            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                if (row < g.sa) g.p[(long long)row * g.stride + c] = a[q];
+                if (row < g.sa) gp[q * gstep] = pack4(a[q], b[q]);
             }
+        } else if (!swz) {
+            float4* sp = tile + base * TP + c2;
+#pragma unroll
+            for (int q = 0; q < R; ++q) sp[q * M * TP] = pack4(a[q], b[q]);
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                tile[row * TC + (swz ? ((c + row) & (TC - 1)) : c)] = a[q];
+                tile[row * TP + ((c2 + row) & (TP - 1))] = pack4(a[q], b[q]);
             }
         }
     }
@@ -158,65 +195,75 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float2* tile, int swz, int
 
 // last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
 template <int R>
-SPIM_DEV void mid_tile(const FftPlanDev& pl, float2* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
+SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
     const int nb = pl.n / R;
-    SPIM_FOR_ITEMS(i, nb * TC) {
-        const int c = i & (TC - 1);
-        const int base = (i >> 4) * R;
-        float2 a[R];
+    const long long gs4 = g.stride >> 1;
+    SPIM_FOR_ITEMS(i, nb * TP) {
+        const int c2 = i & (TP - 1);
+        const int base = (i >> 3) * R;
+        float2 a[R], b[R];
+        const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * gs4 + c2;
+        float4 kv[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) kv[q] = spim_ldg(kp + q * gs4);
         if (src_g) {
+            const float4* gp = reinterpret_cast<const float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q;
-                a[q] = (row < g.va || row >= g.vb) ? spim_ldg(g.p + (long long)row * g.stride + c) : make_float2(0.f, 0.f);
+                const float4 v = spim_ldg(gp + q * gs4);
+                const bool ok = (row < g.va) || (row >= g.vb);
+                a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
+                b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
             }
         } else {
+            const float4* sp = tile + base * TP + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) a[q] = tile[(base + q) * TC + c];
+            for (int q = 0; q < R; ++q) { const float4 v = sp[q * TP]; a[q] = lo2(v); b[q] = hi2(v); }
         }
         dft<R, false>(a);
+        dft<R, false>(b);
 #pragma unroll
-        for (int q = 0; q < R; ++q) a[q] = cmul(a[q], spim_ldg(kh + (long long)(base + q) * g.stride + c));
+        for (int q = 0; q < R; ++q) { a[q] = cmul(a[q], lo2(kv[q])); b[q] = cmul(b[q], hi2(kv[q])); }
         dft<R, true>(a);
+        dft<R, true>(b);
         if (dst_g) {
+            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q;
-                if (row < g.sa) g.p[(long long)row * g.stride + c] = a[q];
+                if (row < g.sa) gp[q * gs4] = pack4(a[q], b[q]);
             }
         } else {
+            float4* sp = tile + base * TP + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) tile[(base + q) * TC + c] = a[q];
+            for (int q = 0; q < R; ++q) sp[q * TP] = pack4(a[q], b[q]);
         }
     }
     SPIM_BARRIER();
 }
 
+// radix dispatch.  SPIM_MAX_RADIX bounds the radices the planner may use (and therefore the code paths
+// ptxas has to allocate registers for: a two-column radix-16 butterfly needs ~180 registers).
+#ifndef SPIM_MAX_RADIX
+#define SPIM_MAX_RADIX 10
+#endif
+#define SPIM_RADIX_CASE(N, CALL) case N: if constexpr (N <= SPIM_MAX_RADIX) { constexpr int RR = N; CALL; } break;
 #define SPIM_RADIX_SWITCH(R_, CALL)                                                              \
     switch (R_) {                                                                                \
-        case 2: { constexpr int RR = 2; CALL; } break;                                           \
-        case 3: { constexpr int RR = 3; CALL; } break;                                           \
-        case 4: { constexpr int RR = 4; CALL; } break;                                           \
-        case 5: { constexpr int RR = 5; CALL; } break;                                           \
-        case 6: { constexpr int RR = 6; CALL; } break;                                           \
-        case 7: { constexpr int RR = 7; CALL; } break;                                           \
-        case 8: { constexpr int RR = 8; CALL; } break;                                           \
-        case 9: { constexpr int RR = 9; CALL; } break;                                           \
-        case 10: { constexpr int RR = 10; CALL; } break;                                         \
-        case 11: { constexpr int RR = 11; CALL; } break;                                         \
-        case 12: { constexpr int RR = 12; CALL; } break;                                         \
-        case 13: { constexpr int RR = 13; CALL; } break;                                         \
-        case 14: { constexpr int RR = 14; CALL; } break;                                         \
-        case 15: { constexpr int RR = 15; CALL; } break;                                         \
-        case 16: { constexpr int RR = 16; CALL; } break;                                         \
+        SPIM_RADIX_CASE(2, CALL) SPIM_RADIX_CASE(3, CALL) SPIM_RADIX_CASE(4, CALL)               \
+        SPIM_RADIX_CASE(5, CALL) SPIM_RADIX_CASE(6, CALL) SPIM_RADIX_CASE(7, CALL)               \
+        SPIM_RADIX_CASE(8, CALL) SPIM_RADIX_CASE(9, CALL) SPIM_RADIX_CASE(10, CALL)              \
+        SPIM_RADIX_CASE(11, CALL) SPIM_RADIX_CASE(12, CALL) SPIM_RADIX_CASE(13, CALL)            \
+        SPIM_RADIX_CASE(14, CALL) SPIM_RADIX_CASE(15, CALL) SPIM_RADIX_CASE(16, CALL)            \
         default: break;                                                                          \
     }
 
 template <bool INV>
-SPIM_DEV void stage_dispatch(const FftPlanDev& pl, int s, float2* tile, int swz, int src_g, int dst_g, const GRows& g) {
+SPIM_DEV void stage_dispatch(const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(pl, s, tile, swz, src_g, dst_g, g)))
 }
-SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float2* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
+SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
     SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(pl, tile, src_g, dst_g, g, kh)))
 }
 
@@ -237,7 +284,8 @@ struct ColPassParams {
 
 struct ColPass {
     typedef ColPassParams Params;
-    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        float4* tile = reinterpret_cast<float4*>(tile2);
         const int o = bid / p.ntx;
         const int tx = bid - o * p.ntx;
         const int outer = o < p.outer_split ? o : o + p.outer_shift;
@@ -262,6 +310,7 @@ struct ColPass {
 
 // ---------------------------------------------------------------------------------------------
 // XFwd: real lines -> half spectrum (R2C via one complex FFT of length Px/2 + split step)
+// Tile = [Px/2 rows][16 lines]; line pair bp of row r lives in float4 slot (bp + r) & 7.
 // ---------------------------------------------------------------------------------------------
 struct XFwdParams {
     const float* src;
@@ -302,52 +351,55 @@ SPIM_DEV float xfwd_val(const XFwdParams& p, const float* line, bool is_const, f
 
 SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
     const int u0 = 2 * n;
-    const float cval = (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
-    if (so >= 0) {
-        const float* line = p.src + so;
-        if (u0 + 1 < p.nx) {   // interior fast path
-            const float* q = line + p.ox + u0;
-            if (p.src_vec_ok) return spim_ldg(reinterpret_cast<const float2*>(q));
-            return make_float2(spim_ldg(q), spim_ldg(q + 1));
-        }
-        return make_float2(xfwd_val(p, line, false, cval, u0), xfwd_val(p, line, false, cval, u0 + 1));
+    if (so >= 0 && u0 + 1 < p.nx) {   // interior fast path
+        const float* q = p.src + so + p.ox + u0;
+        if (p.src_vec_ok) return spim_ldg(reinterpret_cast<const float2*>(q));
+        return make_float2(spim_ldg(q), spim_ldg(q + 1));
     }
-    return make_float2(xfwd_val(p, nullptr, true, cval, u0), xfwd_val(p, nullptr, true, cval, u0 + 1));
+    if (so == kLineInvalid) return make_float2(0.f, 0.f);
+    const float cval = (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
+    const bool cst = so < 0;
+    const float* line = cst ? nullptr : p.src + so;
+    return make_float2(xfwd_val(p, line, cst, cval, u0), xfwd_val(p, line, cst, cval, u0 + 1));
 }
 
 template <int R>
-SPIM_DEV void xfwd_stage0(const XFwdParams& p, float2* tile, const long long* srcoff) {
+SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* srcoff) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
-    SPIM_FOR_ITEMS(i, M * TC) {
-        const int b = (M == 1) ? i : fastdiv(i, p.magic_m0);
-        const int m = i - b * M;
-        const long long so = srcoff[b];
-        float2 a[R];
-        if (so == kLineInvalid) {
+    const float2* twp = pl.tws + pl.tw_off[0];
+    SPIM_FOR_ITEMS(i, M * TP) {
+        const int bp = (M == 1) ? i : fastdiv(i, p.magic_m0);
+        const int m = i - bp * M;
+        const long long so0 = srcoff[2 * bp], so1 = srcoff[2 * bp + 1];
+        float2 a[R], b[R];
 #pragma unroll
-            for (int q = 0; q < R; ++q) a[q] = make_float2(0.f, 0.f);
-        } else {
-#pragma unroll
-            for (int q = 0; q < R; ++q) a[q] = xfwd_pair(p, so, m + q * M);
+        for (int q = 0; q < R; ++q) {
+            a[q] = xfwd_pair(p, so0, m + q * M);
+            b[q] = xfwd_pair(p, so1, m + q * M);
         }
         dft<R, false>(a);
-        if (M > 1) apply_twiddles<R, false>(a, pl.tw, m);
+        dft<R, false>(b);
+        if (M > 1) apply_twiddles2<R, false>(a, b, twp + m * (R - 1));
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
-            tile[row * TC + ((b + row) & (TC - 1))] = a[q];
+            tile[row * TP + ((bp + row) & (TP - 1))] = pack4(a[q], b[q]);
         }
     }
     SPIM_BARRIER();
 }
 
+// float2 view of line b in row `row` of a rotated tile
+SPIM_HD int xelem(int b, int row) { return row * TC + ((((b >> 1) + row) & (TP - 1)) << 1) + (b & 1); }
+
 struct XFwd {
     typedef XFwdParams Params;
-    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        float4* tile = reinterpret_cast<float4*>(tile2);
         const FftPlanDev& pl = p.plan;
         const int N2 = pl.n;
-        long long* srcoff = reinterpret_cast<long long*>(tile + (size_t)N2 * TC);
+        long long* srcoff = reinterpret_cast<long long*>(tile2 + (size_t)N2 * TC);
         long long* dstoff = srcoff + TC;
         // line descriptors for the 16 lines of this tile
         SPIM_FOR_ITEMS(b, TC) {
@@ -391,8 +443,8 @@ struct XFwd {
             const int km = N2 - k;
             const int rk = spim_ldg(p.pos + k);
             const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
-            const float2 zk = tile[rk * TC + ((b + rk) & (TC - 1))];
-            const float2 zm = tile[rm * TC + ((b + rm) & (TC - 1))];
+            const float2 zk = tile2[xelem(b, rk)];
+            const float2 zm = tile2[xelem(b, rm)];
             const float2 w = spim_ldg(p.wx + k);
             float2* out = p.spec + d_o;
             {
@@ -474,15 +526,15 @@ SPIM_DEV float tikhonov_next(float last, float integral, double lambda, float mi
     return (adj != adj) ? min_value : fmaxf(min_value, adj);
 }
 
-SPIM_DEV float epi_one(const XInvParams& p, float v, float imgv, float wv, float last, EpiAcc& acc) {
-    if (p.epi == EPI_RATIO) {
-        if (p.gen2_quotient) return imgv > 0.f ? spim_fdiv_rn(imgv, v) : 1.f;
-        return spim_fdiv_rn(imgv, v);
+SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, EpiAcc& acc) {
+    if (p.epi == EPI_RATIO) {          // x1 = observed image value
+        if (p.gen2_quotient) return x1 > 0.f ? spim_fdiv_rn(x1, v) : 1.f;
+        return spim_fdiv_rn(x1, v);
     }
-    if (p.epi == EPI_UPDATE) {
-        const float next = tikhonov_next(last, v, p.lambda, p.min_value);
-        const float nw = spim_fadd_rn(last, spim_fmul_rn(spim_fsub_rn(next, last), wv));
-        const float ch = fabsf(spim_fsub_rn(nw, last));
+    if (p.epi == EPI_UPDATE) {         // x1 = psi (last), x2 = weight
+        const float next = tikhonov_next(x1, v, p.lambda, p.min_value);
+        const float nw = spim_fadd_rn(x1, spim_fmul_rn(spim_fsub_rn(next, x1), x2));
+        const float ch = fabsf(spim_fsub_rn(nw, x1));
         acc.sum += (double)ch;
         acc.mx = fmaxf(acc.mx, ch);
         return nw;
@@ -490,27 +542,35 @@ SPIM_DEV float epi_one(const XInvParams& p, float v, float imgv, float wv, float
     return v;
 }
 
-// process output samples x = 2n, 2n+1 of one line
-SPIM_DEV void epi_pair(const XInvParams& p, long long aux0, long long dst0, int n, float2 v, EpiAcc& acc) {
+// epilogue inputs for output samples x = 2n, 2n+1 of one line, fetched BEFORE the butterfly so that the
+// global-memory latency overlaps the shared-memory stage
+SPIM_DEV void epi_fetch(const XInvParams& p, long long aux0, long long dst0, int n, float2& x1, float2& x2) {
     const int u0 = 2 * n;
-    if (u0 >= p.nx) return;
+    x1 = make_float2(0.f, 0.f);
+    x2 = make_float2(p.const_weight, p.const_weight);
+    if (u0 >= p.nx || p.epi == EPI_STORE) return;
     const bool two = (u0 + 1 < p.nx);
     const long long ai = aux0 + u0, di = dst0 + u0;
-    float im0 = 0.f, im1 = 0.f, w0 = p.const_weight, w1 = p.const_weight, l0 = 0.f, l1 = 0.f;
     if (p.epi == EPI_RATIO) {
-        if (two && p.aux_vec_ok) { const float2 t = spim_ldg(reinterpret_cast<const float2*>(p.img + ai)); im0 = t.x; im1 = t.y; }
-        else { im0 = spim_ldg(p.img + ai); if (two) im1 = spim_ldg(p.img + ai + 1); }
-    } else if (p.epi == EPI_UPDATE) {
+        if (two && p.aux_vec_ok) x1 = spim_ldg(reinterpret_cast<const float2*>(p.img + ai));
+        else { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
+    } else {
         if (p.weight) {
-            if (two && p.aux_vec_ok) { const float2 t = spim_ldg(reinterpret_cast<const float2*>(p.weight + ai)); w0 = t.x; w1 = t.y; }
-            else { w0 = spim_ldg(p.weight + ai); if (two) w1 = spim_ldg(p.weight + ai + 1); }
+            if (two && p.aux_vec_ok) x2 = spim_ldg(reinterpret_cast<const float2*>(p.weight + ai));
+            else { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
         }
-        if (two && p.dst_vec_ok) { const float2 t = *reinterpret_cast<const float2*>(p.dst + di); l0 = t.x; l1 = t.y; }
-        else { l0 = p.dst[di]; if (two) l1 = p.dst[di + 1]; }
+        if (two && p.dst_vec_ok) x1 = *reinterpret_cast<const float2*>(p.dst + di);
+        else { x1.x = p.dst[di]; if (two) x1.y = p.dst[di + 1]; }
     }
-    const float r0 = epi_one(p, v.x, im0, w0, l0, acc);
-    if (two) {
-        const float r1 = epi_one(p, v.y, im1, w1, l1, acc);
+}
+
+SPIM_DEV void epi_store(const XInvParams& p, long long dst0, int n, float2 v, float2 x1, float2 x2, EpiAcc& acc) {
+    const int u0 = 2 * n;
+    if (u0 >= p.nx) return;
+    const long long di = dst0 + u0;
+    const float r0 = epi_one(p, v.x, x1.x, x2.x, acc);
+    if (u0 + 1 < p.nx) {
+        const float r1 = epi_one(p, v.y, x1.y, x2.y, acc);
         if (p.dst_vec_ok) *reinterpret_cast<float2*>(p.dst + di) = make_float2(r0, r1);
         else { p.dst[di] = r0; p.dst[di + 1] = r1; }
     } else {
@@ -519,25 +579,26 @@ SPIM_DEV void epi_pair(const XInvParams& p, long long aux0, long long dst0, int 
 }
 
 template <int R>
-SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
+SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
+    const float2* twp = pl.tws + pl.tw_off[0];
     SPIM_FOR_ITEMS(i, M * TC) {
         const int b = (M == 1) ? i : fastdiv(i, p.magic_m0);
         const int m = i - b * M;
         const long long d_o = dstoff[b];
         if (d_o < 0) continue;
+        const long long a_o = auxoff[b];
+        float2 x1[R], x2[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) epi_fetch(p, a_o, d_o, m + q * M, x1[q], x2[q]);
         float2 a[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int row = m + q * M;
-            a[q] = tile[row * TC + ((b + row) & (TC - 1))];
-        }
-        if (M > 1) apply_twiddles<R, true>(a, pl.tw, m);
+        for (int q = 0; q < R; ++q) a[q] = tile2[xelem(b, m + q * M)];
+        if (M > 1) apply_twiddles1<R, true>(a, twp + m * (R - 1));
         dft<R, true>(a);
-        const long long a_o = auxoff[b];
 #pragma unroll
-        for (int q = 0; q < R; ++q) epi_pair(p, a_o, d_o, m + q * M, a[q], acc);
+        for (int q = 0; q < R; ++q) epi_store(p, d_o, m + q * M, a[q], x1[q], x2[q], acc);
     }
 }
 
@@ -580,10 +641,11 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
 
 struct XInv {
     typedef XInvParams Params;
-    SPIM_DEV static void run(const Params& p, int bid, float2* tile) {
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        float4* tile = reinterpret_cast<float4*>(tile2);
         const FftPlanDev& pl = p.plan;
         const int N2 = pl.n;
-        long long* srcoff = reinterpret_cast<long long*>(tile + (size_t)N2 * TC);
+        long long* srcoff = reinterpret_cast<long long*>(tile2 + (size_t)N2 * TC);
         long long* dstoff = srcoff + TC;
         long long* auxoff = dstoff + TC;
         SPIM_FOR_ITEMS(b, TC) {
@@ -599,32 +661,46 @@ struct XInv {
             srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
         }
         SPIM_BARRIER();
-        // pre-step: Z'[k] = (X[k] + conj X[N2-k]) + i conj(w^k) (X[k] - conj X[N2-k]), written to its DIT input row
+        // pre-step: Z'[k] = (X[k] + conj X[N2-k]) + i conj(w^k) (X[k] - conj X[N2-k]), written to its DIT input row.
+        // Four items per thread are loaded before any is consumed (memory-level parallelism).
         const int nk = p.nk;
-        SPIM_FOR_ITEMS(i, nk * TC) {
-            const int b = fastdiv(i, p.magic_nk);
-            const int k = i - b * nk;
-            const long long so = srcoff[b];
-            const int km = N2 - k;
-            float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
-            if (so >= 0) {
-                A = spim_ldg(p.spec + so + k);
-                B = spim_ldg(p.spec + so + km);
+        const int total = nk * TC;
+        for (int i0 = SPIM_TID; i0 < total; i0 += 4 * SPIM_NTHREADS) {
+            float2 A[4], B[4];
+            int bb[4], kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * SPIM_NTHREADS;
+                A[u] = make_float2(0.f, 0.f); B[u] = make_float2(0.f, 0.f);
+                bb[u] = -1; kk[u] = 0;
+                if (i < total) {
+                    const int b = fastdiv(i, p.magic_nk);
+                    const int k = i - b * nk;
+                    bb[u] = b; kk[u] = k;
+                    const long long so = srcoff[b];
+                    if (so >= 0) {
+                        A[u] = spim_ldg(p.spec + so + k);
+                        B[u] = spim_ldg(p.spec + so + (N2 - k));
+                    }
+                }
             }
-            const float2 w = spim_ldg(p.wx + k);
-            {
-                const float2 s = make_float2(A.x + B.x, A.y - B.y);
-                const float2 d = make_float2(A.x - B.x, A.y + B.y);
-                const float2 t = cmulc(d, w);
-                const int r = spim_ldg(p.pos + k);
-                tile[r * TC + ((b + r) & (TC - 1))] = make_float2(s.x - t.y, s.y + t.x);
-            }
-            if (k != 0 && km != k) {
-                const float2 s = make_float2(B.x + A.x, B.y - A.y);
-                const float2 d = make_float2(B.x - A.x, B.y + A.y);
-                const float2 t = cmul(d, w);
-                const int r = spim_ldg(p.pos + km);
-                tile[r * TC + ((b + r) & (TC - 1))] = make_float2(s.x + t.y, s.y - t.x);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (bb[u] < 0) continue;
+                const int b = bb[u], k = kk[u], km = N2 - k;
+                const float2 w = spim_ldg(p.wx + k);
+                {
+                    const float2 s = make_float2(A[u].x + B[u].x, A[u].y - B[u].y);
+                    const float2 d = make_float2(A[u].x - B[u].x, A[u].y + B[u].y);
+                    const float2 t = cmulc(d, w);
+                    tile2[xelem(b, spim_ldg(p.pos + k))] = make_float2(s.x - t.y, s.y + t.x);
+                }
+                if (k != 0 && km != k) {
+                    const float2 s = make_float2(B[u].x + A[u].x, B[u].y - A[u].y);
+                    const float2 d = make_float2(B[u].x - A[u].x, B[u].y + A[u].y);
+                    const float2 t = cmul(d, w);
+                    tile2[xelem(b, spim_ldg(p.pos + km))] = make_float2(s.x + t.y, s.y - t.x);
+                }
             }
         }
         SPIM_BARRIER();
@@ -633,8 +709,8 @@ struct XInv {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR>(p, tile, auxoff, dstoff, acc)))
-        stats_commit(p, tile, acc);
+        SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR>(p, tile2, auxoff, dstoff, acc)))
+        stats_commit(p, tile2, acc);
     }
 };
 
