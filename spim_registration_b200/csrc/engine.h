@@ -130,11 +130,13 @@ inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
     const int r = atoi(v);
-    return (r >= 32 && r <= 256 && r % 32 == 0) ? r : dflt;
+    return (r >= 0 && r <= 1024) ? r : dflt;
 }
-inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 256); return t; }
-inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 256); return t; }
-inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 256); return t; }
+inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 128); return t; }
+inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
+inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
+inline int threads_colp() { static int t = env_int("SPIM_THREADS_COLP", 512); return t; }
+inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct, 1 persistent double-buffered, 2 one-shot async tile
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
 
@@ -274,7 +276,21 @@ public:
         const long long grid = (long long)p.ntx * outer_count;
         const size_t smem = (size_t)Pa * TC * sizeof(float2);
         if (timer) timer->begin(id, st);
-        rt::launch<ColPass>(p, grid, threads_col(), smem, st);
+        // persistent double-buffered variant when two (or, with the kernel spectrum staged, four) tiles fit
+        const size_t lim = rt::max_smem();
+        if (use_colp() == 1 && 2 * smem <= lim && grid <= 0x7fffffff) {
+            p.kstage = (mode == COL_MID && 4 * smem <= lim) ? 1 : 0;
+            p.ntiles = (int)grid;
+            p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
+            rt::launch<ColPassP, 512>(p, p.nctas, threads_colp(), (p.kstage ? 4 : 2) * smem, st);
+        } else if (use_colp() == 2) {
+            p.ntiles = -1;    // async mode flag
+            static int ks = env_int("SPIM_KSTAGE", 1);
+            p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
+            rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+        } else {
+            rt::launch<ColPass>(p, grid, threads_col(), smem, st);
+        }
         if (timer) timer->end(id, st);
     }
 

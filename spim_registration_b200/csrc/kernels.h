@@ -145,7 +145,7 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                const float4 v = spim_ldg(gp + q * gstep);   // gap rows hold stale data: load anyway, select zero
+                const float4 v = ldg_stream(gp + q * gstep);   // gap rows hold stale data: load anyway, select zero
                 const bool ok = (row < g.va) || (row >= g.vb);
                 a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
                 b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
@@ -176,7 +176,7 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                if (row < g.sa) gp[q * gstep] = pack4(a[q], b[q]);
+                if (row < g.sa) stg_stream(gp + q * gstep, pack4(a[q], b[q]));
             }
         } else if (!swz) {
             float4* sp = tile + base * TP + c2;
@@ -195,23 +195,29 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int
 
 // last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
 template <int R>
-SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
+SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
     const int nb = pl.n / R;
     const long long gs4 = g.stride >> 1;
     SPIM_FOR_ITEMS(i, nb * TP) {
         const int c2 = i & (TP - 1);
         const int base = (i >> 3) * R;
         float2 a[R], b[R];
-        const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * gs4 + c2;
         float4 kv[R];
+        if (ks) {      // kernel-spectrum tile staged in shared memory
+            const float4* kp = ks + base * TP + c2;
 #pragma unroll
-        for (int q = 0; q < R; ++q) kv[q] = spim_ldg(kp + q * gs4);
+            for (int q = 0; q < R; ++q) kv[q] = kp[q * TP];
+        } else {
+            const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * ks4 + c2;
+#pragma unroll
+            for (int q = 0; q < R; ++q) kv[q] = ldg_stream(kp + q * ks4);
+        }
         if (src_g) {
             const float4* gp = reinterpret_cast<const float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q;
-                const float4 v = spim_ldg(gp + q * gs4);
+                const float4 v = ldg_stream(gp + q * gs4);
                 const bool ok = (row < g.va) || (row >= g.vb);
                 a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
                 b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
@@ -232,7 +238,7 @@ SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g,
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q;
-                if (row < g.sa) gp[q * gs4] = pack4(a[q], b[q]);
+                if (row < g.sa) stg_stream(gp + q * gs4, pack4(a[q], b[q]));
             }
         } else {
             float4* sp = tile + base * TP + c2;
@@ -263,8 +269,8 @@ template <bool INV>
 SPIM_DEV void stage_dispatch(const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(pl, s, tile, swz, src_g, dst_g, g)))
 }
-SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh) {
-    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(pl, tile, src_g, dst_g, g, kh)))
+SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
+    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(pl, tile, src_g, dst_g, g, kh, ks, ks4)))
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +286,26 @@ struct ColPassParams {
     int outer_split, outer_shift;  // outer = o < split ? o : o + shift  (skips the zero gap)
     int va, vb, sa;
     int mode;
+    int ntiles, nctas;         // ColPassP (persistent): tiles in total / CTAs launched
+    int kstage;                // ColPassP, COL_MID: kernel-spectrum tile staged in shared memory too
 };
+
+// asynchronous copy of tile rows [row_lo, row_hi) (16 float2 = 8 x 16 B each) from global to shared memory.
+// Each thread keeps its column pair and walks rows with a constant stride: ~4 instructions per 16-byte chunk.
+SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_lo, int row_hi) {
+#if defined(SPIM_HOST_EMU)
+    for (int row = row_lo; row < row_hi; ++row)
+        for (int c2 = 0; c2 < TP; ++c2) cp_async16(buf + row * TP + c2, gp + (long long)row * gs4 + c2);
+#else
+    const int c2 = threadIdx.x & (TP - 1);
+    const int rstep = blockDim.x >> 3;
+    int row = row_lo + (threadIdx.x >> 3);
+    float4* d = buf + row * TP + c2;
+    const float4* g = gp + (long long)row * gs4 + c2;
+    const long long gstep = (long long)rstep * gs4;
+    for (; row < row_hi; row += rstep, d += rstep * TP, g += gstep) cp_async16(d, g);
+#endif
+}
 
 struct ColPass {
     typedef ColPassParams Params;
@@ -296,14 +321,114 @@ struct ColPass {
         g.va = p.va; g.vb = p.vb; g.sa = p.sa;
         const FftPlanDev& pl = p.plan;
         const int S = pl.nstages;
+        int sg = 1;                       // first stage reads global memory directly ...
+        const float4* ks = nullptr;
+        if (p.ntiles < 0) {               // ... or (async mode) the whole tile is staged with one burst of cp.async
+            const int P = pl.n;
+            const long long gs4 = p.row_stride >> 1;
+            const float4* gp = reinterpret_cast<const float4*>(g.p);
+            if (p.va < p.vb) {
+                async_rows(tile, gp, gs4, 0, p.va);
+                async_rows(tile, gp, gs4, p.vb, P);
+            } else {
+                async_rows(tile, gp, gs4, 0, P);
+            }
+            if (p.mode == COL_MID && p.kstage) {
+                float4* kb = tile + (size_t)P * TP;
+                async_rows(kb, reinterpret_cast<const float4*>(p.khat + base), gs4, 0, P);
+                ks = kb;
+            }
+            cp_async_commit();
+            if (p.va < p.vb) {
+                SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            cp_async_wait<0>();
+            SPIM_BARRIER();
+            sg = 0;
+            g.va = P; g.vb = P;
+        }
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, s == 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, sg && s == 0, s == S - 1, g);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, s == S - 1, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, sg && s == S - 1, s == 0, g);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, s == 0, 0, g);
-            mid_dispatch(pl, tile, S == 1, S == 1, g, p.khat + base);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, sg && s == 0, 0, g);
+            mid_dispatch(pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
             for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+        }
+    }
+};
+
+// Persistent, double-buffered variant: each CTA walks tiles bid, bid+nctas, ...; while the FFT stages of
+// tile t run out of one shared-memory buffer, the rows of tile t+1 stream into the other one with
+// cp.async (LDGSTS), so the global-memory latency is off the critical path.  Results leave straight from
+// the registers of the last stage.
+struct ColPassP {
+    typedef ColPassParams Params;
+    SPIM_DEV static void tile_base(const Params& p, int t, long long& base) {
+        const int o = t / p.ntx;
+        const int tx = t - o * p.ntx;
+        const int outer = o < p.outer_split ? o : o + p.outer_shift;
+        base = (long long)outer * p.outer_stride + (long long)tx * TC;
+    }
+    SPIM_DEV static void issue(const Params& p, int t, float4* buf, float4* kbuf) {
+        long long base;
+        tile_base(p, t, base);
+        const int P = p.plan.n;
+        const long long gs4 = p.row_stride >> 1;
+        const bool gap = p.va < p.vb;
+        const int nvalid = gap ? P - (p.vb - p.va) : P;
+        const float4* gp = reinterpret_cast<const float4*>(p.data + base);
+        SPIM_FOR_ITEMS(i, nvalid * TP) {
+            const int r = i >> 3, c2 = i & (TP - 1);
+            const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
+            cp_async16(buf + row * TP + c2, gp + (long long)row * gs4 + c2);
+        }
+        if (p.mode == COL_MID && p.kstage) {
+            const float4* kp = reinterpret_cast<const float4*>(p.khat + base);
+            SPIM_FOR_ITEMS(i, P * TP) {
+                const int r = i >> 3, c2 = i & (TP - 1);
+                cp_async16(kbuf + i, kp + (long long)r * gs4 + c2);
+            }
+        }
+        cp_async_commit();
+    }
+    SPIM_DEV static void run(const Params& p, int bid, float2* smem2) {
+        const FftPlanDev& pl = p.plan;
+        const int P = pl.n;
+        const int S = pl.nstages;
+        float4* smem = reinterpret_cast<float4*>(smem2);
+        float4* buf[2] = {smem, smem + (size_t)P * TP};
+        float4* kbuf[2] = {smem + 2 * (size_t)P * TP, smem + 3 * (size_t)P * TP};
+        int t = bid;
+        if (t >= p.ntiles) return;
+        issue(p, t, buf[0], kbuf[0]);
+        for (int cur = 0; t < p.ntiles; t += p.nctas, cur ^= 1) {
+            const int tn = t + p.nctas;
+            if (tn < p.ntiles) { issue(p, tn, buf[cur ^ 1], kbuf[cur ^ 1]); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            float4* tile = buf[cur];
+            if (p.va < p.vb) {   // rows of the zero gap are not loaded
+                SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            SPIM_BARRIER();
+            long long base;
+            tile_base(p, t, base);
+            GRows g;
+            g.p = p.data + base;
+            g.stride = p.row_stride;
+            g.va = P; g.vb = P; g.sa = p.sa;
+            if (p.mode == COL_FWD) {
+                for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, 0, s == S - 1, g);
+            } else if (p.mode == COL_INV) {
+                for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+            } else {
+                for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, 0, 0, g);
+                if (p.kstage) mid_dispatch(pl, tile, 0, S == 1, g, nullptr, kbuf[cur], 0);
+                else mid_dispatch(pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
+                for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+            }
+            // every stage ends with a barrier, so buf[cur] is free for the loads issued next iteration
         }
     }
 };
@@ -353,7 +478,7 @@ SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
     const int u0 = 2 * n;
     if (so >= 0 && u0 + 1 < p.nx) {   // interior fast path
         const float* q = p.src + so + p.ox + u0;
-        if (p.src_vec_ok) return spim_ldg(reinterpret_cast<const float2*>(q));
+        if (p.src_vec_ok) return ldg_stream(reinterpret_cast<const float2*>(q));
         return make_float2(spim_ldg(q), spim_ldg(q + 1));
     }
     if (so == kLineInvalid) return make_float2(0.f, 0.f);
@@ -552,11 +677,11 @@ SPIM_DEV void epi_fetch(const XInvParams& p, long long aux0, long long dst0, int
     const bool two = (u0 + 1 < p.nx);
     const long long ai = aux0 + u0, di = dst0 + u0;
     if (p.epi == EPI_RATIO) {
-        if (two && p.aux_vec_ok) x1 = spim_ldg(reinterpret_cast<const float2*>(p.img + ai));
+        if (two && p.aux_vec_ok) x1 = ldg_stream(reinterpret_cast<const float2*>(p.img + ai));
         else { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
     } else {
         if (p.weight) {
-            if (two && p.aux_vec_ok) x2 = spim_ldg(reinterpret_cast<const float2*>(p.weight + ai));
+            if (two && p.aux_vec_ok) x2 = ldg_stream(reinterpret_cast<const float2*>(p.weight + ai));
             else { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
         }
         if (two && p.dst_vec_ok) x1 = *reinterpret_cast<const float2*>(p.dst + di);
@@ -679,8 +804,8 @@ struct XInv {
                     bb[u] = b; kk[u] = k;
                     const long long so = srcoff[b];
                     if (so >= 0) {
-                        A[u] = spim_ldg(p.spec + so + k);
-                        B[u] = spim_ldg(p.spec + so + (N2 - k));
+                        A[u] = ldg_stream(p.spec + so + k);
+                        B[u] = ldg_stream(p.spec + so + (N2 - k));
                     }
                 }
             }
