@@ -45,7 +45,10 @@ typedef struct mvd_params {
     int device;            /* CUDA device ordinal */
     int haloed;            /* 1 = brick mode: psi / ratio carry a kernel-sized halo that the caller
                               fills (neighbour exchange + mvd_fill_halo) before every convolution */
-    int reserved[8];
+    int exact_tikhonov;    /* 0 (default): Tikhonov step in the algebraically identical, cancellation-free fp32 form
+                              2v/(1+sqrt(1+2*lambda*v)) (<= 2 ulp from the reference's fp64 expression);
+                              1: evaluate (sqrt(1+2*lambda*v)-1)/lambda in fp64 exactly like the Java code */
+    int reserved[7];
 } mvd_params;
 
 typedef struct mvd_info {

@@ -8,6 +8,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <tuple>
 
 namespace spim {
 
@@ -132,7 +133,7 @@ inline int env_int(const char* name, int dflt) {
     const int r = atoi(v);
     return (r >= 0 && r <= 1024) ? r : dflt;
 }
-inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 128); return t; }
+inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); return t; }
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
 inline int threads_colp() { static int t = env_int("SPIM_THREADS_COLP", 512); return t; }
@@ -162,6 +163,7 @@ struct EpiDesc {            // what XInv does with the result
     double lambda = 0.0;
     float min_value = 1e-4f;
     int gen2_quotient = 1;
+    int exact_tikhonov = 0;
     double* stat_sum = nullptr;
     unsigned int* stat_max = nullptr;
 };
@@ -218,12 +220,40 @@ public:
     void destroy() {
         fx.destroy(); fy.destroy(); fz.destroy();
         rt::dfree(d_pos); rt::dfree(d_wx); rt::dfree(spec); rt::dfree(d_kernel);
+        for (auto& kv : xtables) rt::dfree(kv.second);
+        xtables.clear();
         d_pos = nullptr; d_wx = nullptr; spec = nullptr; d_kernel = nullptr; kernel_cap = 0;
     }
     size_t spec_bytes() const { return spec_elems * sizeof(float2); }
     double kernel_scale() const { return 1.0 / (4.0 * (double)P[0] * (double)P[1] * (double)P[2]); }
     long long padded_min_voxels() const {   // Np of SURVEY section 8d
         return (long long)(n[0] + k[0] - 1) * (n[1] + k[1] - 1) * (n[2] + k[2] - 1);
+    }
+
+    // x-position -> source-index tables of the x-forward loader, cached per geometry
+    struct XKey { int nx, hp, hm, sx, ox, ext; bool operator<(const XKey& o) const {
+        return std::tie(nx, hp, hm, sx, ox, ext) < std::tie(o.nx, o.hp, o.hm, o.sx, o.ox, o.ext); } };
+    std::map<XKey, int*> xtables;
+    const int* x_index_table(int nx, int hp, int hm, int sx, int ox, int ext, rt::Stream st) {
+        const XKey key{nx, hp, hm, sx, ox, ext};
+        auto it = xtables.find(key);
+        if (it != xtables.end()) return it->second;
+        std::vector<int> t(P[2]);
+        for (int u = 0; u < P[2]; ++u) {
+            const int a = pad_to_coord(u, nx, hp, hm, P[2]);
+            if (a == kGap) { t[u] = -1; continue; }
+            int i = a + ox;
+            if ((unsigned)i >= (unsigned)sx) {
+                const int e = ext_map(a, nx, ext);
+                i = e < 0 ? -2 : e + ox;
+            }
+            t[u] = i;
+        }
+        int* d = (int*)rt::dmalloc(sizeof(int) * P[2]);
+        rt::h2d(d, t.data(), sizeof(int) * P[2], st);
+        rt::stream_sync(st);
+        xtables[key] = d;
+        return d;
     }
 
     // ---- sweeps -------------------------------------------------------------------------
@@ -249,6 +279,7 @@ public:
         p.nk = N2 / 2 + 1;
         p.magic_nk = magic_for(p.nk);
         p.src_vec_ok = ((reinterpret_cast<uintptr_t>(src.p) & 7) == 0) && (p.sx % 2 == 0) && (p.ox % 2 == 0);
+        p.xidx = x_index_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, st);
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         if (timer) timer->begin(K_XFWD, st);
@@ -285,7 +316,7 @@ public:
             rt::launch<ColPassP, 512>(p, p.nctas, threads_colp(), (p.kstage ? 4 : 2) * smem, st);
         } else if (use_colp() == 2) {
             p.ntiles = -1;    // async mode flag
-            static int ks = env_int("SPIM_KSTAGE", 1);
+            static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
             rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
         } else {
@@ -309,14 +340,19 @@ public:
         p.doz = e.dst_origin[0]; p.doy = e.dst_origin[1]; p.dox = e.dst_origin[2];
         p.epi = e.epi; p.img = e.img; p.weight = e.weight; p.const_weight = e.const_weight;
         p.lambda = e.lambda; p.min_value = e.min_value; p.gen2_quotient = e.gen2_quotient;
+        p.two_lambda = (float)(2.0 * e.lambda);
+        p.exact_tikhonov = e.exact_tikhonov;
         p.stat_sum = e.stat_sum; p.stat_max = e.stat_max;
-        p.dst_vec_ok = ((reinterpret_cast<uintptr_t>(e.dst) & 7) == 0) && (p.dsx % 2 == 0) && (p.dox % 2 == 0);
-        p.aux_vec_ok = (n[2] % 2 == 0) && ((reinterpret_cast<uintptr_t>(e.img) & 7) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(e.weight) & 7) == 0);
+        auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
+        p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
         if (timer) timer->begin(K_XINV, st);
-        rt::launch<XInv>(p, grid, threads_xinv(), smem, st);
+        const int T = threads_xinv();
+        if (e.epi == EPI_STORE) rt::launch<XInvT<EPI_STORE, false>>(p, grid, T, smem, st);
+        else if (e.epi == EPI_RATIO) rt::launch<XInvT<EPI_RATIO, false>>(p, grid, T, smem, st);
+        else if (e.exact_tikhonov) rt::launch<XInvT<EPI_UPDATE, true>>(p, grid, T, smem, st);
+        else rt::launch<XInvT<EPI_UPDATE, false>>(p, grid, T, smem, st);
         if (timer) timer->end(K_XINV, st);
     }
 

@@ -15,6 +15,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #define SPIM_DEV inline
+#define SPIM_NOINLINE_DEV __attribute__((noinline))
 #define SPIM_HD inline
 #define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)
 #define SPIM_BARRIER() ((void)0)
@@ -33,11 +34,14 @@ static inline float spim_fadd_rn(float a, float b) { volatile float r = a + b; r
 static inline float spim_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float spim_fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float spim_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float spim_fsqrt_rn(float a) { volatile float r = sqrtf(a); return r; }
+static inline float spim_fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 
 #else
 
 #include <cuda_runtime.h>
 #define SPIM_DEV __device__ __forceinline__
+#define SPIM_NOINLINE_DEV __device__ __noinline__
 #define SPIM_HD __host__ __device__ __forceinline__
 #define SPIM_FOR_ITEMS(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)
 #define SPIM_BARRIER() __syncthreads()
@@ -71,5 +75,7 @@ __device__ __forceinline__ float spim_fadd_rn(float a, float b) { return __fadd_
 __device__ __forceinline__ float spim_fsub_rn(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float spim_fmul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float spim_fdiv_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float spim_fsqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float spim_fmaf_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
 #endif

@@ -456,22 +456,19 @@ struct XFwdParams {
     int nk;                    // Px/4 + 1 (pairs handled by the split step)
     uint32_t magic_nk;
     int src_vec_ok;            // float2 loads allowed (alignment)
+    const int* xidx;           // [Px] x-position -> source index / -1 gap / -2 constant
 };
 
 constexpr long long kLineInvalid = -2;
 constexpr long long kLineConst = -1;
 
-SPIM_DEV float xfwd_val(const XFwdParams& p, const float* line, bool is_const, float cval, int u) {
-    const int a = pad_to_coord(u, p.nx, p.hpx, p.hmx, p.Px);
-    if (a == kGap) return 0.f;
-    if (is_const) return cval;
-    int i = a + p.ox;
-    if ((unsigned)i >= (unsigned)p.sx) {
-        const int e = ext_map(a, p.nx, p.ext);
-        if (e < 0) return cval;
-        i = e + p.ox;
-    }
-    return spim_ldg(line + i);
+// x-forward loader.  Interior pairs are one 8-byte load; everything else (halo, gap, constant or invalid
+// lines) goes through a per-geometry index table: xidx[u] >= 0 source index, -1 zero gap, -2 ext constant.
+SPIM_DEV float xfwd_val(const XFwdParams& p, long long so, int u) {
+    const int i = spim_ldg(p.xidx + u);
+    if (so >= 0 && i >= 0) return spim_ldg(p.src + so + i);
+    if (i == -1 || so == kLineInvalid) return 0.f;
+    return (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
 }
 
 SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
@@ -481,11 +478,7 @@ SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
         if (p.src_vec_ok) return ldg_stream(reinterpret_cast<const float2*>(q));
         return make_float2(spim_ldg(q), spim_ldg(q + 1));
     }
-    if (so == kLineInvalid) return make_float2(0.f, 0.f);
-    const float cval = (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
-    const bool cst = so < 0;
-    const float* line = cst ? nullptr : p.src + so;
-    return make_float2(xfwd_val(p, line, cst, cval, u0), xfwd_val(p, line, cst, cval, u0 + 1));
+    return make_float2(xfwd_val(p, so, u0), xfwd_val(p, so, u0 + 1));
 }
 
 template <int R>
@@ -517,6 +510,25 @@ SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* sr
 
 // float2 view of line b in row `row` of a rotated tile
 SPIM_HD int xelem(int b, int row) { return row * TC + ((((b >> 1) + row) & (TP - 1)) << 1) + (b & 1); }
+
+// forward split of one line: X[k] = (Zk + conj Zm) - i w (Zk - conj Zm); X[N2-k] = (Zm + conj Zk) + i conj(w) (Zm - conj Zk)
+SPIM_DEV void split_fwd(float2 zk, float2 zm, float2 w, float2& xk, float2& xm) {
+    const float2 s = make_float2(zk.x + zm.x, zk.y - zm.y);
+    const float2 d = make_float2(zk.x - zm.x, zk.y + zm.y);
+    const float2 t = cmul(w, d);
+    xk = make_float2(s.x + t.y, s.y - t.x);
+    // second output: s2 = conj(s), d2 = -conj(d)  ->  t2 = d2 * conj(w) = -conj(d w) = -conj(t)
+    xm = make_float2(s.x - t.y, -s.y - t.x);
+}
+// inverse pre-step: Z'[k] = (A + conj B) + i conj(w)(A - conj B); Z'[N2-k] = (B + conj A) - i w (B - conj A)
+SPIM_DEV void split_inv(float2 A, float2 B, float2 w, float2& zk, float2& zm) {
+    const float2 s = make_float2(A.x + B.x, A.y - B.y);
+    const float2 d = make_float2(A.x - B.x, A.y + B.y);
+    const float2 t = cmulc(d, w);
+    zk = make_float2(s.x - t.y, s.y + t.x);
+    // s2 = conj(s), d2 = -conj(d), t2 = d2 * w = -conj(d conj(w)) = -conj(t):  zm = s2 + (-i) t2... evaluated directly:
+    zm = make_float2(s.x + t.y, -s.y + t.x);
+}
 
 struct XFwd {
     typedef XFwdParams Params;
@@ -558,31 +570,29 @@ struct XFwd {
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
         for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(pl, s, tile, 1, 0, 0, g);
-        // split step: X[k] = (Z[k] + conj Z[N2-k]) - i w^k (Z[k] - conj Z[N2-k])   (factor 1/2 folded into the kernel scale)
+        // split step on line pairs (factor 1/2 folded into the kernel scale)
         const int nk = p.nk;
-        SPIM_FOR_ITEMS(i, nk * TC) {
-            const int b = fastdiv(i, p.magic_nk);
-            const int k = i - b * nk;
-            const long long d_o = dstoff[b];
-            if (d_o < 0) continue;
+        SPIM_FOR_ITEMS(i, nk * TP) {
+            const int bp = fastdiv(i, p.magic_nk);
+            const int k = i - bp * nk;
+            const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
+            if (d0 < 0 && d1 < 0) continue;
             const int km = N2 - k;
             const int rk = spim_ldg(p.pos + k);
             const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
-            const float2 zk = tile2[xelem(b, rk)];
-            const float2 zm = tile2[xelem(b, rm)];
+            const float4 zk = tile[rk * TP + ((bp + rk) & (TP - 1))];
+            const float4 zm = tile[rm * TP + ((bp + rm) & (TP - 1))];
             const float2 w = spim_ldg(p.wx + k);
-            float2* out = p.spec + d_o;
-            {
-                const float2 s = make_float2(zk.x + zm.x, zk.y - zm.y);
-                const float2 d = make_float2(zk.x - zm.x, zk.y + zm.y);
-                const float2 t = cmul(w, d);
-                out[k] = make_float2(s.x + t.y, s.y - t.x);
+            float2 xk, xm;
+            if (d0 >= 0) {
+                split_fwd(lo2(zk), lo2(zm), w, xk, xm);
+                p.spec[d0 + k] = xk;
+                if (km != k) p.spec[d0 + km] = xm;
             }
-            if (km != k) {
-                const float2 s = make_float2(zm.x + zk.x, zm.y - zk.y);
-                const float2 d = make_float2(zm.x - zk.x, zm.y + zk.y);
-                const float2 t = cmulc(d, w);
-                out[km] = make_float2(s.x - t.y, s.y + t.x);
+            if (d1 >= 0) {
+                split_fwd(hi2(zk), hi2(zm), w, xk, xm);
+                p.spec[d1 + k] = xk;
+                if (km != k) p.spec[d1 + km] = xm;
             }
         }
         // zero the pad columns [N2+1, pitch)
@@ -597,7 +607,7 @@ struct XFwd {
 };
 
 // ---------------------------------------------------------------------------------------------
-// XInv: half spectrum -> real lines + fused epilogue
+// XInv: half spectrum -> real lines + fused epilogue (specialised at compile time per epilogue mode)
 // ---------------------------------------------------------------------------------------------
 struct XInvParams {
     const float2* spec;
@@ -619,49 +629,61 @@ struct XInvParams {
     const float* weight;       // EPI_UPDATE: per-voxel weight (unpadded) or nullptr
     float const_weight;
     double lambda;
+    float two_lambda;          // (float)(2*lambda)
     float min_value;
     int gen2_quotient;         // 1: q = img > 0 ? img / blur : 1 ; 0: q = img / blur
+    int exact_tikhonov;        // 1: evaluate (sqrt(1+2 lambda v)-1)/lambda in fp64 exactly like the Java code
     double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
     unsigned int* stat_max;    // max |change| as float bits
-    int dst_vec_ok, aux_vec_ok;
+    int vec_ok;                // float2 accesses to dst / img / weight allowed and nx even
 };
 
 struct EpiAcc { double sum; float mx; };
 
-SPIM_DEV float tikhonov_next(float last, float integral, double lambda, float min_value) {
-    // computeNextValue, FD/MVDeconvolution.java:692-724 (same arithmetic as D2/BayesMVDeconvolution.java:452-476)
+SPIM_DEV float tikhonov_fp64(float value, double lambda) {
+    // (float)((Math.sqrt(1.0 + 2.0*lambda*value) - 1.0) / lambda), FD/MVDeconvolution.java:726
+#if defined(SPIM_HOST_EMU)
+    volatile double t = 2.0 * lambda; t = t * (double)value; t = 1.0 + t;
+    volatile double r = sqrt(t) - 1.0; r = r / lambda;
+    return (float)r;
+#else
+    const double t = __dadd_rn(1.0, __dmul_rn(__dmul_rn(2.0, lambda), (double)value));
+    return (float)__ddiv_rn(__dadd_rn(__dsqrt_rn(t), -1.0), lambda);
+#endif
+}
+
+// next psi value, computeNextValue FD/MVDeconvolution.java:692-724 (= D2/BayesMVDeconvolution.java:452-476).
+// Default: the algebraically identical cancellation-free fp32 form 2v / (1 + sqrt(1 + 2 lambda v))
+// (<= 2 ulp from the fp64 expression for lambda >= 0.006 on v in [1e-5, 10]); EXACT selects the fp64 path.
+template <bool EXACT>
+SPIM_DEV float next_value(const XInvParams& p, float last, float integral) {
     const float value = spim_fmul_rn(last, integral);
     float adj;
     if (value > 0.f) {
-        if (lambda > 0.0) {
-#if defined(SPIM_HOST_EMU)
-            volatile double t = 2.0 * lambda; t = t * (double)value; t = 1.0 + t;
-            volatile double r = sqrt(t) - 1.0; r = r / lambda;
-            adj = (float)r;
-#else
-            const double t = __dadd_rn(1.0, __dmul_rn(__dmul_rn(2.0, lambda), (double)value));
-            adj = (float)__ddiv_rn(__dadd_rn(__dsqrt_rn(t), -1.0), lambda);
-#endif
+        if (p.lambda > 0.0) {
+            if (EXACT) adj = tikhonov_fp64(value, p.lambda);
+            else adj = spim_fdiv_rn(value + value, 1.f + spim_fsqrt_rn(spim_fmaf_rn(p.two_lambda, value, 1.f)));
         } else {
             adj = value;
         }
     } else {
-        adj = min_value;
+        adj = p.min_value;
     }
-    return (adj != adj) ? min_value : fmaxf(min_value, adj);
+    return fmaxf(p.min_value, adj);       // fmaxf returns the non-NaN operand: NaN -> minValue
 }
 
-SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, EpiAcc& acc) {
-    if (p.epi == EPI_RATIO) {          // x1 = observed image value
+template <int EPI, bool EXACT>
+SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, float& csum, float& cmax) {
+    if (EPI == EPI_RATIO) {            // x1 = observed image value
         if (p.gen2_quotient) return x1 > 0.f ? spim_fdiv_rn(x1, v) : 1.f;
         return spim_fdiv_rn(x1, v);
     }
-    if (p.epi == EPI_UPDATE) {         // x1 = psi (last), x2 = weight
-        const float next = tikhonov_next(x1, v, p.lambda, p.min_value);
+    if (EPI == EPI_UPDATE) {           // x1 = psi (last), x2 = weight
+        const float next = next_value<EXACT>(p, x1, v);
         const float nw = spim_fadd_rn(x1, spim_fmul_rn(spim_fsub_rn(next, x1), x2));
         const float ch = fabsf(spim_fsub_rn(nw, x1));
-        acc.sum += (double)ch;
-        acc.mx = fmaxf(acc.mx, ch);
+        csum += ch;
+        cmax = fmaxf(cmax, ch);
         return nw;
     }
     return v;
@@ -669,41 +691,45 @@ SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, EpiAcc&
 
 // epilogue inputs for output samples x = 2n, 2n+1 of one line, fetched BEFORE the butterfly so that the
 // global-memory latency overlaps the shared-memory stage
+template <int EPI, bool VEC>
 SPIM_DEV void epi_fetch(const XInvParams& p, long long aux0, long long dst0, int n, float2& x1, float2& x2) {
     const int u0 = 2 * n;
     x1 = make_float2(0.f, 0.f);
     x2 = make_float2(p.const_weight, p.const_weight);
-    if (u0 >= p.nx || p.epi == EPI_STORE) return;
-    const bool two = (u0 + 1 < p.nx);
+    if (EPI == EPI_STORE || u0 >= p.nx) return;
     const long long ai = aux0 + u0, di = dst0 + u0;
-    if (p.epi == EPI_RATIO) {
-        if (two && p.aux_vec_ok) x1 = ldg_stream(reinterpret_cast<const float2*>(p.img + ai));
-        else { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
-    } else {
-        if (p.weight) {
-            if (two && p.aux_vec_ok) x2 = ldg_stream(reinterpret_cast<const float2*>(p.weight + ai));
-            else { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
+    if (VEC) {
+        if (EPI == EPI_RATIO) x1 = ldg_stream(reinterpret_cast<const float2*>(p.img + ai));
+        else {
+            if (p.weight) x2 = ldg_stream(reinterpret_cast<const float2*>(p.weight + ai));
+            x1 = *reinterpret_cast<const float2*>(p.dst + di);
         }
-        if (two && p.dst_vec_ok) x1 = *reinterpret_cast<const float2*>(p.dst + di);
-        else { x1.x = p.dst[di]; if (two) x1.y = p.dst[di + 1]; }
+    } else {
+        const bool two = (u0 + 1 < p.nx);
+        if (EPI == EPI_RATIO) { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
+        else {
+            if (p.weight) { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
+            x1.x = p.dst[di]; if (two) x1.y = p.dst[di + 1];
+        }
     }
 }
 
-SPIM_DEV void epi_store(const XInvParams& p, long long dst0, int n, float2 v, float2 x1, float2 x2, EpiAcc& acc) {
+template <int EPI, bool EXACT, bool VEC>
+SPIM_DEV void epi_store(const XInvParams& p, long long dst0, int n, float2 v, float2 x1, float2 x2, float& csum, float& cmax) {
     const int u0 = 2 * n;
     if (u0 >= p.nx) return;
     const long long di = dst0 + u0;
-    const float r0 = epi_one(p, v.x, x1.x, x2.x, acc);
-    if (u0 + 1 < p.nx) {
-        const float r1 = epi_one(p, v.y, x1.y, x2.y, acc);
-        if (p.dst_vec_ok) *reinterpret_cast<float2*>(p.dst + di) = make_float2(r0, r1);
-        else { p.dst[di] = r0; p.dst[di + 1] = r1; }
+    const float r0 = epi_one<EPI, EXACT>(p, v.x, x1.x, x2.x, csum, cmax);
+    if (VEC) {
+        const float r1 = epi_one<EPI, EXACT>(p, v.y, x1.y, x2.y, csum, cmax);
+        *reinterpret_cast<float2*>(p.dst + di) = make_float2(r0, r1);
     } else {
         p.dst[di] = r0;
+        if (u0 + 1 < p.nx) p.dst[di + 1] = epi_one<EPI, EXACT>(p, v.y, x1.y, x2.y, csum, cmax);
     }
 }
 
-template <int R>
+template <int R, int EPI, bool EXACT, bool VEC>
 SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
@@ -716,19 +742,21 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
         const long long a_o = auxoff[b];
         float2 x1[R], x2[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) epi_fetch(p, a_o, d_o, m + q * M, x1[q], x2[q]);
+        for (int q = 0; q < R; ++q) epi_fetch<EPI, VEC>(p, a_o, d_o, m + q * M, x1[q], x2[q]);
         float2 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = tile2[xelem(b, m + q * M)];
         if (M > 1) apply_twiddles1<R, true>(a, twp + m * (R - 1));
         dft<R, true>(a);
+        float csum = 0.f, cmax = 0.f;
 #pragma unroll
-        for (int q = 0; q < R; ++q) epi_store(p, d_o, m + q * M, a[q], x1[q], x2[q], acc);
+        for (int q = 0; q < R; ++q) epi_store<EPI, EXACT, VEC>(p, d_o, m + q * M, a[q], x1[q], x2[q], csum, cmax);
+        if (EPI == EPI_UPDATE) { acc.sum += (double)csum; acc.mx = fmaxf(acc.mx, cmax); }
     }
 }
 
 SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
-    if (p.epi != EPI_UPDATE || p.stat_sum == nullptr) return;
+    if (p.stat_sum == nullptr) return;
 #if defined(SPIM_HOST_EMU)
     (void)tile;
     *p.stat_sum += acc.sum;
@@ -764,7 +792,8 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
 #endif
 }
 
-struct XInv {
+template <int EPI, bool EXACT>
+struct XInvT {
     typedef XInvParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         float4* tile = reinterpret_cast<float4*>(tile2);
@@ -786,45 +815,39 @@ struct XInv {
             srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
         }
         SPIM_BARRIER();
-        // pre-step: Z'[k] = (X[k] + conj X[N2-k]) + i conj(w^k) (X[k] - conj X[N2-k]), written to its DIT input row.
-        // Four items per thread are loaded before any is consumed (memory-level parallelism).
+        // pre-step on line pairs; two items (8 loads) per thread are in flight before any is consumed
         const int nk = p.nk;
-        const int total = nk * TC;
-        for (int i0 = SPIM_TID; i0 < total; i0 += 4 * SPIM_NTHREADS) {
-            float2 A[4], B[4];
-            int bb[4], kk[4];
+        const int total = nk * TP;
+        for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
+            float2 A0[2], B0[2], A1[2], B1[2];
+            int bpv[2], kk[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int i = i0 + u * SPIM_NTHREADS;
-                A[u] = make_float2(0.f, 0.f); B[u] = make_float2(0.f, 0.f);
-                bb[u] = -1; kk[u] = 0;
+                A0[u] = B0[u] = A1[u] = B1[u] = make_float2(0.f, 0.f);
+                bpv[u] = -1; kk[u] = 0;
                 if (i < total) {
-                    const int b = fastdiv(i, p.magic_nk);
-                    const int k = i - b * nk;
-                    bb[u] = b; kk[u] = k;
-                    const long long so = srcoff[b];
-                    if (so >= 0) {
-                        A[u] = ldg_stream(p.spec + so + k);
-                        B[u] = ldg_stream(p.spec + so + (N2 - k));
-                    }
+                    const int bp = fastdiv(i, p.magic_nk);
+                    const int k = i - bp * nk;
+                    bpv[u] = bp; kk[u] = k;
+                    const long long s0 = srcoff[2 * bp], s1 = srcoff[2 * bp + 1];
+                    if (s0 >= 0) { A0[u] = ldg_stream(p.spec + s0 + k); B0[u] = ldg_stream(p.spec + s0 + (N2 - k)); }
+                    if (s1 >= 0) { A1[u] = ldg_stream(p.spec + s1 + k); B1[u] = ldg_stream(p.spec + s1 + (N2 - k)); }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (bb[u] < 0) continue;
-                const int b = bb[u], k = kk[u], km = N2 - k;
+            for (int u = 0; u < 2; ++u) {
+                if (bpv[u] < 0) continue;
+                const int bp = bpv[u], k = kk[u], km = N2 - k;
                 const float2 w = spim_ldg(p.wx + k);
-                {
-                    const float2 s = make_float2(A[u].x + B[u].x, A[u].y - B[u].y);
-                    const float2 d = make_float2(A[u].x - B[u].x, A[u].y + B[u].y);
-                    const float2 t = cmulc(d, w);
-                    tile2[xelem(b, spim_ldg(p.pos + k))] = make_float2(s.x - t.y, s.y + t.x);
-                }
+                float2 zk0, zm0, zk1, zm1;
+                split_inv(A0[u], B0[u], w, zk0, zm0);
+                split_inv(A1[u], B1[u], w, zk1, zm1);
+                const int rk = spim_ldg(p.pos + k);
+                tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
                 if (k != 0 && km != k) {
-                    const float2 s = make_float2(B[u].x + A[u].x, B[u].y - A[u].y);
-                    const float2 d = make_float2(B[u].x - A[u].x, B[u].y + A[u].y);
-                    const float2 t = cmul(d, w);
-                    tile2[xelem(b, spim_ldg(p.pos + km))] = make_float2(s.x + t.y, s.y - t.x);
+                    const int rm = spim_ldg(p.pos + km);
+                    tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
                 }
             }
         }
@@ -834,8 +857,9 @@ struct XInv {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR>(p, tile2, auxoff, dstoff, acc)))
-        stats_commit(p, tile2, acc);
+        if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, EXACT, true>(p, tile2, auxoff, dstoff, acc))) }
+        else { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, EXACT, false>(p, tile2, auxoff, dstoff, acc))) }
+        if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }
 };
 

@@ -491,7 +491,7 @@ struct mvd_session {
         } else {
             src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = 1.f;
             e.epi = EPI_UPDATE; e.dst = d_psi; e.weight = d_w[v]; e.const_weight = 1.f;
-            e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max;
+            e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max; e.exact_tikhonov = prm.exact_tikhonov;
             plan.convolve(src, d_kh2[v], e, stream);
         }
     }

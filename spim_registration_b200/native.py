@@ -40,7 +40,8 @@ class MvdParams(C.Structure):
         ("conv2_ext", C.c_int),
         ("device", C.c_int),
         ("haloed", C.c_int),
-        ("reserved", C.c_int * 8),
+        ("exact_tikhonov", C.c_int),
+        ("reserved", C.c_int * 7),
     ]
 
 

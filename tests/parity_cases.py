@@ -90,6 +90,20 @@ def decon_case(lib, shape, V, ks, typ, gen, iters, kind="beads", lam=0.006, weig
     return per, l2
 
 
+def exact_tikhonov_case(lib, shape=(14, 16, 18)):
+    """exact_tikhonov=1 evaluates the reference's fp64 expression; the default fp32 form must agree with
+    it to a few ulp and both must meet the parity bar."""
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, 2, 5, kind="beads")
+    ref = O.deconvolve(imgs, ws, psfs, O.DeconParams(iteration_type=3, num_iterations=3, lam=0.006, gen=2))
+    a, *_ = run_session(lib, imgs, ws, psfs, 3, 2, 3, exact_tikhonov=True)
+    b, *_ = run_session(lib, imgs, ws, psfs, 3, 2, 3, exact_tikhonov=False)
+    for psi in (a, b):
+        per, l2 = O.parity_errors(psi, ref.psi)
+        assert per <= TOL_PER_VOXEL and l2 <= TOL_L2
+    per, l2 = O.parity_errors(a, b)
+    assert per <= 2e-5 and l2 <= 2e-6, (per, l2)
+
+
 def golden_case(lib, gen, typ):
     d = np.load(os.path.join(G, "decon_small.npz"))
     V = int(d["num_views"])
