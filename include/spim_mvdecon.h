@@ -102,6 +102,10 @@ int mvd_get_timing(mvd_session* s, double ms[8], long long launches[8]);
 /* ---- brick mode (one session per GPU) -------------------------------- */
 /* device pointer + geometry of a session buffer: which 0 = psi, 1 = ratio/tmp */
 int mvd_get_device_buffer(mvd_session* s, int which, void** dptr, int dims[3], int origin[3]);
+/* declare which sides of the brick have a neighbour (bit d = axis d of (z,y,x)): the convolution loader
+ * reads the halo there (the caller refreshes it before every convolution) and applies the convolution's
+ * own out-of-bounds rule on all other sides (volume faces).  Default: no neighbours. */
+int mvd_set_halo_mask(mvd_session* s, int lo_mask, int hi_mask);
 /* fill the halo faces flagged in lo_mask / hi_mask (bit d = axis d of (z,y,x)) of buffer `which`
  * from the brick's own interior using the convolution's out-of-bounds rule (volume faces) */
 int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask);

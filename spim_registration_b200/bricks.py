@@ -16,6 +16,7 @@ and the initial average are 2-6 scalar all-reduces.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -76,6 +77,9 @@ class BrickRunner:
                                osem_speedup=osem_speedup, device=device, haloed=self.haloed, lib=lib)
         self._bufs = None
         self._tmp = {}
+        self._graph = None
+        self._graph_failed = False
+        self.use_graph = (not cpu) and os.environ.get("SPIM_BRICK_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------------------------------
     def _wrap(self, ptr: int, dims):
@@ -127,6 +131,7 @@ class BrickRunner:
         i = s.info()
         self.halo_lo = tuple(i.halo_lo)
         self.halo_hi = tuple(i.halo_hi)
+        self._plan_exchange()
 
     # ------------------------------------------------------------------------------------------
     def _neighbour(self, axis: int, step: int) -> Optional[int]:
@@ -136,64 +141,109 @@ class BrickRunner:
             return None
         return coords_rank(c, self.grid)
 
+    def _plan_exchange(self):
+        """Neighbour list for the one-shot exchange: every existing neighbour at offset (dz,dy,dx) in
+        {-1,0,1}^3 gets the interior cells it needs (face, edge or corner piece) and sends back the
+        matching piece for my halo.  Volume faces need nothing: the convolution loader applies the
+        out-of-bounds rule there (mvd_set_halo_mask)."""
+        import itertools
+        n = self.session.dims
+        _, dims, origin = self._bufs[0]
+        plan = []
+        for off in itertools.product((-1, 0, 1), repeat=3):
+            if off == (0, 0, 0):
+                continue
+            c = [self.coords[d] + off[d] for d in range(3)]
+            if any(c[d] < 0 or c[d] >= self.grid[d] for d in range(3)):
+                continue
+            send, recv = [], []
+            empty = False
+            for d in range(3):
+                o, wlo, whi = origin[d], self.halo_lo[d], self.halo_hi[d]
+                if off[d] == 0:
+                    send.append(slice(o, o + n[d])); recv.append(slice(o, o + n[d]))
+                elif off[d] < 0:       # neighbour below: it needs my first `whi` interior cells; I get its last `wlo`
+                    send.append(slice(o, o + whi)); recv.append(slice(o - wlo, o))
+                    empty = empty or whi == 0 or wlo == 0
+                else:                   # neighbour above: it needs my last `wlo` interior cells; I get its first `whi`
+                    send.append(slice(o + n[d] - wlo, o + n[d])); recv.append(slice(o + n[d], o + n[d] + whi))
+                    empty = empty or whi == 0 or wlo == 0
+            if not empty:
+                plan.append((coords_rank(c, self.grid), tuple(send), tuple(recv)))
+        self._xplan = plan
+        lo_mask = sum(1 << d for d in range(3) if self._neighbour(d, -1) is not None)
+        hi_mask = sum(1 << d for d in range(3) if self._neighbour(d, +1) is not None)
+        self.session.set_halo_mask(lo_mask, hi_mask)
+
     def exchange(self, which: int):
-        """Refresh the halo of buffer ``which`` (0 = psi, 1 = ratio): x, then y, then z."""
+        """Refresh the halo of buffer ``which`` (0 = psi, 1 = ratio) from all neighbours in ONE batch of
+        NCCL send/recv (faces, edges and corners together)."""
         import torch
         t, dims, origin = self._bufs[which]
-        n = self.session.dims
+        if not self._xplan:
+            return
         with self._stream_ctx():
-            for axis in (2, 1, 0):
-                lo_n = self._neighbour(axis, -1)
-                hi_n = self._neighbour(axis, +1)
-                wlo, whi = self.halo_lo[axis], self.halo_hi[axis]
-                o = origin[axis]
-                ops, recvs = [], []
+            ops, recvs = [], []
+            for peer, ssl, rsl in self._xplan:
+                send = t[ssl].contiguous()
+                buf = torch.empty(tuple(s_.stop - s_.start for s_ in rsl), dtype=t.dtype, device=t.device)
+                ops.append(self.dist.P2POp(self.dist.isend, send, peer))
+                ops.append(self.dist.P2POp(self.dist.irecv, buf, peer))
+                recvs.append((buf, rsl))
+            for r in self.dist.batch_isend_irecv(ops):
+                r.wait()
+            for buf, rsl in recvs:
+                t[rsl].copy_(buf)
 
-                def sl(a, b):
-                    idx = [slice(None)] * 3
-                    idx[axis] = slice(a, b)
-                    return tuple(idx)
+    def _iteration(self, stats: bool = False, out=None):
+        for v in range(self.num_views):
+            self.exchange(0)
+            self.session.view_phase(v, 0)
+            self.exchange(1)
+            st = self.session.view_phase(v, 1, want_stats=stats)
+            if stats:
+                out.append(st)
 
-                # my last `wlo` interior planes fill the hi-neighbour's lo halo; its first `whi` fill my hi halo
-                if hi_n is not None:
-                    if wlo > 0:
-                        send = t[sl(o + n[axis] - wlo, o + n[axis])].contiguous()
-                        ops.append(self.dist.P2POp(self.dist.isend, send, hi_n))
-                    if whi > 0:
-                        buf = torch.empty_like(t[sl(o + n[axis], o + n[axis] + whi)])
-                        buf = buf.contiguous()
-                        ops.append(self.dist.P2POp(self.dist.irecv, buf, hi_n))
-                        recvs.append((buf, sl(o + n[axis], o + n[axis] + whi)))
-                if lo_n is not None:
-                    if whi > 0:
-                        send = t[sl(o, o + whi)].contiguous()
-                        ops.append(self.dist.P2POp(self.dist.isend, send, lo_n))
-                    if wlo > 0:
-                        buf = torch.empty_like(t[sl(0, wlo)]).contiguous()
-                        ops.append(self.dist.P2POp(self.dist.irecv, buf, lo_n))
-                        recvs.append((buf, sl(0, wlo)))
-                if ops:
-                    for r in self.dist.batch_isend_irecv(ops):
-                        r.wait()
-                    for buf, dst in recvs:
-                        t[dst].copy_(buf)
-                lo_mask = (1 << axis) if lo_n is None else 0
-                hi_mask = (1 << axis) if hi_n is None else 0
-                if lo_mask or hi_mask:
-                    self.session.fill_halo(which, lo_mask, hi_mask)
+    def _capture(self):
+        """Capture one whole iteration (all kernels of every view-step + the NCCL halo exchanges) into a
+        CUDA graph on the session's stream: the host then issues ONE launch per iteration."""
+        import torch
+        try:
+            stream = torch.cuda.ExternalStream(self.session.stream(), device=torch.device("cuda", self.device))
+            self._iteration()            # warm-up outside capture (allocations, index tables, NCCL channels)
+            self.session.sync()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                self._iteration()
+            self._graph = g
+        except Exception as e:       # stay correct: fall back to eager launches
+            self._graph = None
+            self._graph_failed = True
+            if self.rank == 0:
+                print(f"[bricks] CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eagerly", flush=True)
+            torch.cuda.synchronize()
 
     def run(self, n_iterations: int, stats: bool = False):
         if not self.haloed:
             return self.session.run(n_iterations, stats=stats)
-        out = []
-        for _ in range(n_iterations):
-            for v in range(self.num_views):
-                self.exchange(0)
-                self.session.view_phase(v, 0)
-                self.exchange(1)
-                st = self.session.view_phase(v, 1, want_stats=stats)
-                if stats:
-                    out.append(st)
+        if stats or not self.use_graph:
+            out = []
+            for _ in range(n_iterations):
+                self._iteration(stats, out)
+        else:
+            done = 0
+            if self._graph is None and not self._graph_failed:
+                self._capture()          # runs one eager iteration as its warm-up
+                done = 1 if n_iterations > 0 else 0
+                if n_iterations == 0:
+                    raise RuntimeError("BrickRunner.run(0) before the first real iteration is not supported")
+            for _ in range(n_iterations - done):
+                if self._graph is not None:
+                    self._graph.replay()
+                else:
+                    self._iteration()
+            out = None
         if stats:
             import torch
             a = np.array(out, dtype=np.float64).reshape(n_iterations, self.num_views, 2)
@@ -206,14 +256,15 @@ class BrickRunner:
                 return s.cpu().numpy(), m.cpu().numpy()
             return a[..., 0], a[..., 1]
         self.session.sync()
+        if not self.cpu:
+            import torch
+            torch.cuda.current_stream().synchronize()
         return None
 
     def extra_launches_per_iteration(self) -> int:
         if not self.haloed:
             return 0
-        faces = sum(1 for axis in range(3) for step in (-1, 1)
-                    if self._neighbour(axis, step) is None and (self.halo_lo[axis] if step < 0 else self.halo_hi[axis]) > 0)
-        return 2 * self.num_views * faces
+        return 0     # halo refresh = NCCL send/recv + torch slab copies; no kernel of this library
 
     def finish(self):
         self.session.finish()

@@ -150,6 +150,7 @@ struct SrcDesc {            // real input volume
     int origin[3] = {0, 0, 0};  // index = logical coordinate + origin
     int ext = EXT_ZERO;
     float ext_value = 0.f;
+    int halo_lo = 7, halo_hi = 7;   // bit d: array cells outside [0,n) on that side of axis d are valid data
 };
 
 struct EpiDesc {            // what XInv does with the result
@@ -231,11 +232,11 @@ public:
     }
 
     // x-position -> source-index tables of the x-forward loader, cached per geometry
-    struct XKey { int nx, hp, hm, sx, ox, ext; bool operator<(const XKey& o) const {
-        return std::tie(nx, hp, hm, sx, ox, ext) < std::tie(o.nx, o.hp, o.hm, o.sx, o.ox, o.ext); } };
+    struct XKey { int nx, hp, hm, sx, ox, ext, vlo, vhi; bool operator<(const XKey& o) const {
+        return std::tie(nx, hp, hm, sx, ox, ext, vlo, vhi) < std::tie(o.nx, o.hp, o.hm, o.sx, o.ox, o.ext, o.vlo, o.vhi); } };
     std::map<XKey, int*> xtables;
-    const int* x_index_table(int nx, int hp, int hm, int sx, int ox, int ext, rt::Stream st) {
-        const XKey key{nx, hp, hm, sx, ox, ext};
+    const int* x_index_table(int nx, int hp, int hm, int sx, int ox, int ext, int vlo, int vhi, rt::Stream st) {
+        const XKey key{nx, hp, hm, sx, ox, ext, vlo, vhi};
         auto it = xtables.find(key);
         if (it != xtables.end()) return it->second;
         std::vector<int> t(P[2]);
@@ -243,7 +244,7 @@ public:
             const int a = pad_to_coord(u, nx, hp, hm, P[2]);
             if (a == kGap) { t[u] = -1; continue; }
             int i = a + ox;
-            if ((unsigned)i >= (unsigned)sx) {
+            if ((unsigned)i >= (unsigned)sx || (a < 0 && !vlo) || (a >= nx && !vhi)) {
                 const int e = ext_map(a, nx, ext);
                 i = e < 0 ? -2 : e + ox;
             }
@@ -269,6 +270,7 @@ public:
         p.hpz = g.hp[0]; p.hpy = g.hp[1]; p.hpx = g.hp[2];
         p.hmz = g.hm[0]; p.hmy = g.hm[1]; p.hmx = g.hm[2];
         p.ext = src.ext; p.ext_value = src.ext_value;
+        p.halo_lo = src.halo_lo; p.halo_hi = src.halo_hi;
         p.Pz = P[0]; p.Py = P[1]; p.Px = P[2]; p.pitch = pitch;
         p.spec = out;
         p.plan = fx.dev; p.pos = d_pos; p.wx = d_wx;
@@ -279,7 +281,7 @@ public:
         p.nk = N2 / 2 + 1;
         p.magic_nk = magic_for(p.nk);
         p.src_vec_ok = ((reinterpret_cast<uintptr_t>(src.p) & 7) == 0) && (p.sx % 2 == 0) && (p.ox % 2 == 0);
-        p.xidx = x_index_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, st);
+        p.xidx = x_index_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         if (timer) timer->begin(K_XFWD, st);

@@ -445,6 +445,8 @@ struct XFwdParams {
     int hpx, hmx, hpy, hmy, hpz, hmz;  // halo after (+) / before (-) the image on each axis
     int ext;
     float ext_value;
+    int halo_lo, halo_hi;      // bit d (0=z,1=y,2=x): the source array holds valid neighbour data before / after the
+                               // image on axis d (brick mode); otherwise the out-of-bounds rule applies there
     int Px, Py, Pz, pitch;
     float2* spec;
     FftPlanDev plan;           // n = Px / 2
@@ -551,11 +553,11 @@ struct XFwd {
                 const int az = iz < p.nz + p.hpz ? iz : iz - p.LZ;
                 int jy = ay + p.oy, jz = az + p.oz;
                 bool cst = false;
-                if ((unsigned)jy >= (unsigned)p.sy) {
+                if ((unsigned)jy >= (unsigned)p.sy || (ay < 0 && !(p.halo_lo & 2)) || (ay >= p.ny && !(p.halo_hi & 2))) {
                     const int e = ext_map(ay, p.ny, p.ext);
                     if (e < 0) cst = true; else jy = e + p.oy;
                 }
-                if ((unsigned)jz >= (unsigned)p.sz) {
+                if ((unsigned)jz >= (unsigned)p.sz || (az < 0 && !(p.halo_lo & 1)) || (az >= p.nz && !(p.halo_hi & 1))) {
                     const int e = ext_map(az, p.nz, p.ext);
                     if (e < 0) cst = true; else jz = e + p.oz;
                 }

@@ -342,6 +342,7 @@ struct mvd_session {
     float* d_psi = nullptr;    // dims pdims, origin porigin
     float* d_tmp = nullptr;    // ratio buffer, same geometry
     int pdims[3], porigin[3];
+    int halo_lo_mask = 0, halo_hi_mask = 0;   // brick mode: sides whose halo is filled by a neighbour
     long long pelems = 0;
     ConvPlan plan;
     bool plan_ok = false, inited = false;
@@ -481,6 +482,7 @@ struct mvd_session {
     void phase(int v, int ph, double* d_sum, unsigned int* d_max) {
         SrcDesc src;
         for (int d = 0; d < 3; ++d) { src.dims[d] = pdims[d]; src.origin[d] = porigin[d]; }
+        src.halo_lo = halo_lo_mask; src.halo_hi = halo_hi_mask;
         EpiDesc e;
         for (int d = 0; d < 3; ++d) { e.dst_dims[d] = pdims[d]; e.dst_origin[d] = porigin[d]; }
         e.min_value = prm.min_value;
@@ -881,6 +883,16 @@ int mvd_get_device_buffer(mvd_session* s, int which, void** dptr, int dims[3], i
     if (!s->d_psi) return fail("mvd_get_device_buffer: call mvd_init first");
     *dptr = which == 0 ? (void*)s->d_psi : (void*)s->d_tmp;
     for (int d = 0; d < 3; ++d) { dims[d] = s->pdims[d]; origin[d] = s->porigin[d]; }
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_set_halo_mask(mvd_session* s, int lo_mask, int hi_mask) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_set_halo_mask: null session");
+    if (!s->prm.haloed) return fail("mvd_set_halo_mask: not a brick-mode session");
+    s->halo_lo_mask = lo_mask & 7;
+    s->halo_hi_mask = hi_mask & 7;
     return 0;
     SPIM_API_END
 }

@@ -169,6 +169,9 @@ class Session:
                      "mvd_get_device_buffer")
         return ptr.value, tuple(dims), tuple(origin)
 
+    def set_halo_mask(self, lo_mask: int, hi_mask: int):
+        native.check(self.lib, self.lib.mvd_set_halo_mask(self._h, lo_mask, hi_mask), "mvd_set_halo_mask")
+
     def fill_halo(self, which: int, lo_mask: int, hi_mask: int):
         native.check(self.lib, self.lib.mvd_fill_halo(self._h, which, lo_mask, hi_mask), "mvd_fill_halo")
 

@@ -70,7 +70,7 @@ LEGACY_SYMBOLS = (
 SESSION_SYMBOLS = (
     "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_init", "mvd_run",
     "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_get_stream", "mvd_set_timing",
-    "mvd_get_timing", "mvd_get_device_buffer", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
+    "mvd_get_timing", "mvd_get_device_buffer", "mvd_set_halo_mask", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
     "mvd_set_avg", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
 )
 
@@ -136,6 +136,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_get_timing.restype = C.c_int
     lib.mvd_get_device_buffer.argtypes = [S, C.c_int, C.POINTER(C.c_void_p), c_int_p, c_int_p]
     lib.mvd_get_device_buffer.restype = C.c_int
+    lib.mvd_set_halo_mask.argtypes = [S, C.c_int, C.c_int]
+    lib.mvd_set_halo_mask.restype = C.c_int
     lib.mvd_fill_halo.argtypes = [S, C.c_int, C.c_int, C.c_int]
     lib.mvd_fill_halo.restype = C.c_int
     lib.mvd_view_phase.argtypes = [S, C.c_int, C.c_int, c_double_p]
