@@ -169,6 +169,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+_T0 = time.perf_counter()
+
+
+def tlog(msg):
+    if os.environ.get("SPIM_BENCH_TRACE") and int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,8 +199,10 @@ def main():
         run_reference(args)
         return
 
+    tlog("start")
     import torch
     from spim_registration_b200 import build as b
+    tlog("torch imported")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,6 +217,7 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
+        tlog("process group up")
     if world != args.gpus:
         if rank == 0:
             sys.stderr.write(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE\n")
@@ -219,6 +231,7 @@ def main():
     coords = bricks.rank_coords(rank, grid)
     gshape = tuple(BRICK[d] * grid[d] for d in range(3))
     imgs, ws, psfs = make_inputs(BRICK, rank_seed=rank)
+    tlog("inputs generated")
     nvox_brick = int(np.prod(BRICK))
     nvox_global = nvox_brick * N
 
@@ -228,6 +241,7 @@ def main():
     pin_out = torch.empty(BRICK, dtype=torch.float32).pin_memory()
     h2d_bytes = sum(t.numel() * 4 for t in pin_img + pin_w) + sum(p.size * 4 for p in psfs)
     d2h_bytes = pin_out.numel() * 4
+    tlog("pinned")
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,13 +268,16 @@ def main():
     # ---------------- device-resident throughput -------------------------------------------------
     runner = new_runner()
     upload(runner)
+    tlog("uploaded")
     runner.init()
+    tlog("init done")
     info = runner.session.info()
     np_brick = int(info.np_voxels)
     stream = torch.cuda.ExternalStream(runner.session.stream(), device=torch.device("cuda", local))
     for _ in range(args.warmup):
         runner.run(1)
     barrier()
+    tlog("warmup done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -272,6 +289,7 @@ def main():
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    tlog("timed region done")
     clocks = sampler.stop() if rank == 0 else None
     value = nvox_global * VIEWS * args.steps / (ms * 1e-3)
     launches = 10 * VIEWS * args.steps * 1 + runner.extra_launches_per_iteration() * args.steps
@@ -310,6 +328,7 @@ def main():
                      "alg_bytes": 44 * np_brick, "per_kernel": per_kernel}
     runner.close()
     del runner
+    tlog("kernel timing done")
 
     # ---------------- end to end through the reference-facing call -------------------------------------
     barrier()
@@ -324,6 +343,7 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     r2.close()
     e2e_value = nvox_global * VIEWS * args.steps / t_e2e
+    tlog("e2e done")
 
     # ---------------- CPU baseline: the oracle on a bounded sample (rank 0, N = 1 only) --------------------
     cpu = None
@@ -362,9 +382,14 @@ def main():
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        tlog("exiting")
+        # hard exit: tearing down NCCL communicators that were captured into CUDA graphs can block for minutes
+        os._exit(0)
 
 
 if __name__ == "__main__":

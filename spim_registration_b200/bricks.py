@@ -273,5 +273,10 @@ class BrickRunner:
         return self.session.get_psi()
 
     def close(self):
+        # release the captured graph (it references NCCL work) before the session and the process group go away
+        if self._graph is not None:
+            import torch
+            torch.cuda.synchronize()
+            self._graph = None
         self._bufs = None
         self.session.close()

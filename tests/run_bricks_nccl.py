@@ -55,8 +55,8 @@ def main():
         print("BRICKS_NCCL_OK" if ok else "BRICKS_NCCL_FAIL")
     r.close()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
