@@ -106,6 +106,11 @@ int mvd_get_device_buffer(mvd_session* s, int which, void** dptr, int dims[3], i
  * reads the halo there (the caller refreshes it before every convolution) and applies the convolution's
  * own out-of-bounds rule on all other sides (volume faces).  Default: no neighbours. */
 int mvd_set_halo_mask(mvd_session* s, int lo_mask, int hi_mask);
+/* gather (pack) / scatter (unpack) up to 26 box-shaped pieces of buffer `which` to / from one flat DEVICE staging
+ * buffer in a single kernel launch.  regions: npieces x 6 ints (z0, y0, x0, nz, ny, nx) in array coordinates of
+ * the haloed buffer; pieces are laid out back to back in `flat` in the order given. */
+int mvd_halo_pack(mvd_session* s, int which, int npieces, const int* regions, void* flat);
+int mvd_halo_unpack(mvd_session* s, int which, int npieces, const int* regions, void* flat);
 /* fill the halo faces flagged in lo_mask / hi_mask (bit d = axis d of (z,y,x)) of buffer `which`
  * from the brick's own interior using the convolution's out-of-bounds rule (volume faces) */
 int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask);

@@ -171,6 +171,19 @@ class BrickRunner:
             if not empty:
                 plan.append((coords_rank(c, self.grid), tuple(send), tuple(recv)))
         self._xplan = plan
+        # flat staging buffers for the single-launch pack / unpack path
+        import torch
+        t = self._bufs[0][0]
+        box = lambda sl_: tuple(s_.start for s_ in sl_) + tuple(s_.stop - s_.start for s_ in sl_)
+        self._send_regions = [box(ssl) for _, ssl, _ in plan]
+        self._recv_regions = [box(rsl) for _, _, rsl in plan]
+        sizes_s = [int(np.prod(r[3:])) for r in self._send_regions]
+        sizes_r = [int(np.prod(r[3:])) for r in self._recv_regions]
+        self._send_flat = torch.empty(max(1, sum(sizes_s)), dtype=t.dtype, device=t.device)
+        self._recv_flat = torch.empty(max(1, sum(sizes_r)), dtype=t.dtype, device=t.device)
+        self._send_off = np.concatenate([[0], np.cumsum(sizes_s)]).astype(int)
+        self._recv_off = np.concatenate([[0], np.cumsum(sizes_r)]).astype(int)
+        self.use_pack = os.environ.get("SPIM_BRICK_PACK", "1") != "0"
         lo_mask = sum(1 << d for d in range(3) if self._neighbour(d, -1) is not None)
         hi_mask = sum(1 << d for d in range(3) if self._neighbour(d, +1) is not None)
         self.session.set_halo_mask(lo_mask, hi_mask)
@@ -181,6 +194,18 @@ class BrickRunner:
         import torch
         t, dims, origin = self._bufs[which]
         if not self._xplan:
+            return
+        if self.use_pack:
+            # one gather kernel, one NCCL batch on slices of the flat buffers, one scatter kernel
+            with self._stream_ctx():
+                self.session.halo_pack(which, self._send_regions, self._send_flat.data_ptr())
+                ops = []
+                for i, (peer, _, _) in enumerate(self._xplan):
+                    ops.append(self.dist.P2POp(self.dist.isend, self._send_flat[self._send_off[i]:self._send_off[i + 1]], peer))
+                    ops.append(self.dist.P2POp(self.dist.irecv, self._recv_flat[self._recv_off[i]:self._recv_off[i + 1]], peer))
+                for r in self.dist.batch_isend_irecv(ops):
+                    r.wait()
+                self.session.halo_pack(which, self._recv_regions, self._recv_flat.data_ptr(), unpack=True)
             return
         with self._stream_ctx():
             ops, recvs = [], []
@@ -264,7 +289,7 @@ class BrickRunner:
     def extra_launches_per_iteration(self) -> int:
         if not self.haloed:
             return 0
-        return 0     # halo refresh = NCCL send/recv + torch slab copies; no kernel of this library
+        return 4 * self.num_views if getattr(self, "use_pack", False) else 0    # pack + unpack per exchange
 
     def finish(self):
         self.session.finish()

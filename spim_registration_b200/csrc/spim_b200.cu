@@ -187,6 +187,32 @@ struct HaloFillK {
     }
 };
 
+// brick mode: gather / scatter up to 26 box-shaped pieces of a haloed buffer to / from one flat staging buffer
+constexpr int MAX_PIECES = 26;
+struct HaloPackK {
+    struct Params {
+        float* buf; float* flat; int dims[3]; int npieces; int unpack; int nblocks;
+        int lo[MAX_PIECES][3]; int ext[MAX_PIECES][3]; long long off[MAX_PIECES + 1];
+    };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        const long long total = p.off[p.npieces];
+        for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= total) continue;
+                int pc = 0;
+                while (pc + 1 < p.npieces && idx >= p.off[pc + 1]) ++pc;
+                long long r = idx - p.off[pc];
+                const int x = (int)(r % p.ext[pc][2]); r /= p.ext[pc][2];
+                const int y = (int)(r % p.ext[pc][1]);
+                const int z = (int)(r / p.ext[pc][1]);
+                const long long a = ((long long)(z + p.lo[pc][0]) * p.dims[1] + (y + p.lo[pc][1])) * p.dims[2] + x + p.lo[pc][2];
+                if (p.unpack) p.buf[a] = p.flat[idx]; else p.flat[idx] = p.buf[a];
+            }
+        }
+    }
+};
+
 inline int ew_blocks(long long n) {
     long long b = (n + kChunk - 1) / kChunk;
     const long long cap = 148LL * 16;
@@ -894,6 +920,48 @@ int mvd_set_halo_mask(mvd_session* s, int lo_mask, int hi_mask) {
     s->halo_lo_mask = lo_mask & 7;
     s->halo_hi_mask = hi_mask & 7;
     return 0;
+    SPIM_API_END
+}
+
+static int halo_pack_common(mvd_session* s, int which, int npieces, const int* regions, void* flat, int unpack) {
+    if (!s || !regions || !flat) return fail("mvd_halo_pack: null argument");
+    if (!s->prm.haloed || !s->d_psi) return fail("mvd_halo_pack: not a brick-mode session / not initialised");
+    if (npieces < 0 || npieces > MAX_PIECES) return fail("mvd_halo_pack: too many pieces");
+    if (npieces == 0) return 0;
+    rt::set_device(s->prm.device);
+    HaloPackK::Params p;
+    memset(&p, 0, sizeof(p));
+    p.buf = which == 0 ? s->d_psi : s->d_tmp;
+    p.flat = (float*)flat;
+    p.npieces = npieces; p.unpack = unpack;
+    for (int d = 0; d < 3; ++d) p.dims[d] = s->pdims[d];
+    long long off = 0;
+    for (int i = 0; i < npieces; ++i) {
+        p.off[i] = off;
+        long long n = 1;
+        for (int d = 0; d < 3; ++d) {
+            p.lo[i][d] = regions[i * 6 + d];
+            p.ext[i][d] = regions[i * 6 + 3 + d];
+            if (p.lo[i][d] < 0 || p.ext[i][d] < 1 || p.lo[i][d] + p.ext[i][d] > s->pdims[d]) return fail("mvd_halo_pack: region out of range");
+            n *= p.ext[i][d];
+        }
+        off += n;
+    }
+    p.off[npieces] = off;
+    p.nblocks = ew_blocks(off);
+    rt::launch<HaloPackK>(p, p.nblocks, kThreads, 0, s->stream);
+    return 0;
+}
+
+int mvd_halo_pack(mvd_session* s, int which, int npieces, const int* regions, void* flat) {
+    SPIM_API_BEGIN
+    return halo_pack_common(s, which, npieces, regions, flat, 0);
+    SPIM_API_END
+}
+
+int mvd_halo_unpack(mvd_session* s, int which, int npieces, const int* regions, void* flat) {
+    SPIM_API_BEGIN
+    return halo_pack_common(s, which, npieces, regions, flat, 1);
     SPIM_API_END
 }
 

@@ -172,6 +172,13 @@ class Session:
     def set_halo_mask(self, lo_mask: int, hi_mask: int):
         native.check(self.lib, self.lib.mvd_set_halo_mask(self._h, lo_mask, hi_mask), "mvd_set_halo_mask")
 
+    def halo_pack(self, which: int, regions, flat_ptr: int, unpack: bool = False):
+        """regions: sequence of (z0, y0, x0, nz, ny, nx); flat_ptr: device pointer of the staging buffer."""
+        n = len(regions)
+        arr = (C.c_int * (6 * max(n, 1)))(*[int(v) for r in regions for v in r])
+        fn = self.lib.mvd_halo_unpack if unpack else self.lib.mvd_halo_pack
+        native.check(self.lib, fn(self._h, which, n, arr, C.c_void_p(flat_ptr)), "mvd_halo_unpack" if unpack else "mvd_halo_pack")
+
     def fill_halo(self, which: int, lo_mask: int, hi_mask: int):
         native.check(self.lib, self.lib.mvd_fill_halo(self._h, which, lo_mask, hi_mask), "mvd_fill_halo")
 

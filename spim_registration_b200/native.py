@@ -70,7 +70,7 @@ LEGACY_SYMBOLS = (
 SESSION_SYMBOLS = (
     "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_init", "mvd_run",
     "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_get_stream", "mvd_set_timing",
-    "mvd_get_timing", "mvd_get_device_buffer", "mvd_set_halo_mask", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
+    "mvd_get_timing", "mvd_get_device_buffer", "mvd_set_halo_mask", "mvd_halo_pack", "mvd_halo_unpack", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
     "mvd_set_avg", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
 )
 
@@ -138,6 +138,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_get_device_buffer.restype = C.c_int
     lib.mvd_set_halo_mask.argtypes = [S, C.c_int, C.c_int]
     lib.mvd_set_halo_mask.restype = C.c_int
+    lib.mvd_halo_pack.argtypes = [S, C.c_int, C.c_int, c_int_p, C.c_void_p]
+    lib.mvd_halo_pack.restype = C.c_int
+    lib.mvd_halo_unpack.argtypes = [S, C.c_int, C.c_int, c_int_p, C.c_void_p]
+    lib.mvd_halo_unpack.restype = C.c_int
     lib.mvd_fill_halo.argtypes = [S, C.c_int, C.c_int, C.c_int]
     lib.mvd_fill_halo.restype = C.c_int
     lib.mvd_view_phase.argtypes = [S, C.c_int, C.c_int, c_double_p]

@@ -269,3 +269,63 @@ def test_full_size_view_step_spot_check_against_oracle(gpu):
         gs = tuple(slice(c, c + n) for c in (z0, y0, x0))
         per, l2 = O.parity_errors(psi[gs], ref.psi[rs])
         assert per <= P.TOL_PER_VOXEL and l2 <= P.TOL_L2, (interior, per, l2)
+
+
+# ---- brick mode on one GPU ---------------------------------------------------------------------------
+def test_brick_mode_without_neighbours_equals_plain_session(gpu):
+    """A haloed (brick-mode) session whose every face is a volume face must reproduce the plain session:
+    the loader applies the boundary rule itself on faces without a neighbour."""
+    from spim_registration_b200.deconvolution import Session
+    shape, V = (20, 26, 30), 2
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, 7)
+    plain, *_ = P.run_session(gpu, imgs, ws, psfs, 2, 2, 2)
+    with Session(shape, V, 2, generation=2, haloed=True, lib=gpu) as s:
+        for v in range(V):
+            s.set_view(v, imgs[v], ws[v], psfs[v])
+        s.init()
+        part = s.init_partials()
+        s.set_avg(part[0] / part[1], 1.0)
+        s.set_halo_mask(0, 0)
+        for _ in range(2):
+            for v in range(V):
+                s.view_phase(v, 0)
+                s.view_phase(v, 1)
+        s.finish()
+        psi = s.get_psi()
+    assert np.array_equal(plain, psi)
+
+
+def test_halo_pack_unpack_roundtrip(gpu):
+    import torch
+    from spim_registration_b200.deconvolution import Session
+    shape, V = (12, 14, 16), 1
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, 5)
+    with Session(shape, V, 3, generation=2, haloed=True, lib=gpu) as s:
+        s.set_view(0, imgs[0], ws[0], psfs[0])
+        s.init()
+        s.set_avg(0.5, 1.0)
+        ptr, dims, origin = s.device_buffer(0)
+
+        class _CAI:
+            pass
+        o = _CAI()
+        o.__cuda_array_interface__ = {"shape": tuple(dims), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        t = torch.as_tensor(o, device="cuda:0")
+        rng = torch.Generator(device="cuda:0").manual_seed(1)
+        t.copy_(torch.rand(tuple(dims), generator=rng, device="cuda:0"))
+        regions = [(2, 0, 3, 4, dims[1], 2), (0, 5, 0, dims[0], 3, dims[2]), (1, 1, 1, 1, 1, 1)]
+        n = sum(r[3] * r[4] * r[5] for r in regions)
+        flat = torch.zeros(n, device="cuda:0")
+        s.halo_pack(0, regions, flat.data_ptr())
+        s.sync()
+        want = torch.cat([t[r[0]:r[0] + r[3], r[1]:r[1] + r[4], r[2]:r[2] + r[5]].reshape(-1) for r in regions])
+        assert torch.equal(flat, want)
+        before = t.clone()
+        flat2 = torch.rand(n, device="cuda:0")
+        s.halo_pack(0, regions[:1], flat2.data_ptr(), unpack=True)
+        s.sync()
+        r = regions[0]
+        assert torch.equal(t[r[0]:r[0] + r[3], r[1]:r[1] + r[4], r[2]:r[2] + r[5]].reshape(-1), flat2[:r[3] * r[4] * r[5]])
+        mask = torch.ones_like(t, dtype=torch.bool)
+        mask[r[0]:r[0] + r[3], r[1]:r[1] + r[4], r[2]:r[2] + r[5]] = False
+        assert torch.equal(t[mask], before[mask])
