@@ -42,7 +42,10 @@ ITER_TYPE = 2                # EFFICIENT_BAYESIAN
 METRIC = "MV deconvolution voxel-view-iterations/s"
 UNIT = "voxel-view-iterations/s"
 KERNEL_NAMES = ["x_fwd_r2c", "y_fwd", "z_fwd_mul_inv", "y_inv", "x_inv_c2r_epilogue"]
-KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor * Np (DESIGN.md section 5)
+KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor * Np (DESIGN.md section 4)
+# the x-inverse launch also carries the fused pointwise traffic of SURVEY 8d (16 B per voxel-view-iteration):
+# ratio epilogue reads img (4 N), update epilogue reads weight + psi (8 N); their writes are the sweep's own write
+XINV_POINTWISE_BYTES_PER_VOXEL = 6     # average of the two launches of a view-step
 
 
 def peaks():
@@ -304,7 +307,7 @@ def main():
     for i, name in enumerate(KERNEL_NAMES):
         if kcnt[i] > 0:
             avg_ms = kms[i] / kcnt[i]
-            alg = KERNEL_ALG_FACTOR[i] * np_brick
+            alg = KERNEL_ALG_FACTOR[i] * np_brick + (XINV_POINTWISE_BYTES_PER_VOXEL * nvox_brick if i == 4 else 0)
             per_kernel[name] = {"avg_ms": avg_ms, "launches": int(kcnt[i]), "alg_bytes": alg,
                                 "gbs": alg / (avg_ms * 1e-3) / 1e9}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
@@ -325,7 +328,12 @@ def main():
         tot_ms = sum(per_kernel[k]["avg_ms"] for k in per_kernel)
         a2 = 44 * np_brick / (tot_ms * 1e-3) / 1e9
         conv_pass = {"achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "ms_per_conv": tot_ms,
-                     "alg_bytes": 44 * np_brick, "per_kernel": per_kernel}
+                     "alg_bytes": 44 * np_brick, "per_kernel": per_kernel,
+                     "note": "44*Np per FFT-convolution pass (SURVEY 8d), Np = prod(n + k - 1); sum of the five kernels' average durations"}
+        # whole view-step: two passes + 16 B/voxel pointwise = B_vvi * N
+        vs_bytes = 88 * np_brick + 16 * nvox_brick
+        a3 = vs_bytes / (2 * tot_ms * 1e-3) / 1e9
+        view_step = {"achieved": a3, "peak": peak, "unit": "GB/s", "frac": a3 / peak, "alg_bytes": vs_bytes}
     runner.close()
     del runner
     tlog("kernel timing done")
@@ -379,6 +387,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_conv_pass": conv_pass,
+            "roofline_view_step": view_step if dom else None,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
