@@ -48,6 +48,14 @@ KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor *
 XINV_POINTWISE_BYTES_PER_VOXEL = 6     # average of the two launches of a view-step
 
 
+def workload_string(n_gpus):
+    from spim_registration_b200 import bricks
+    grid = bricks.grid_for(n_gpus)
+    g = tuple(BRICK[d] * grid[d] for d in range(3))
+    return (f"{VIEWS}-view {g[2]}x{g[1]}x{g[0]} fp32 ({n_gpus} brick(s) of {BRICK[2]}x{BRICK[1]}x{BRICK[0]}), {PSF}^3 PSFs, "
+            "Efficient-Bayesian, lambda 0.006, gen-2 semantics; step = one iteration over all views"), grid
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,11 +168,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "7-view 512x512x256 fp32, 31^3 PSFs, Efficient-Bayesian, lambda 0.006; "
-                               "each step = ONE view-step (1/7 iteration) of that workload on the host CPU",
+        "config": {"workload": workload_string(args.gpus)[0],
+                   "reference_step": "each timed step of this arm is ONE view-step (1/%d of an iteration) of one "
+                                     "%dx%dx%d brick on the host CPU; value is normalised to voxel-view-iterations/s" % (
+                                         VIEWS, BRICK[2], BRICK[1], BRICK[0]),
                    "l2": "inputs (256 MiB per volume) larger than any cache"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} view-steps of the 512x512x256 workload, CPU restatement of the "
+                         "sample": f"{args.steps} view-steps of one {BRICK[2]}x{BRICK[1]}x{BRICK[0]} brick, CPU restatement of the "
                                    "reference (NumPy + SciPy pocketfft, workers = all cores); reference JVM unavailable"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -374,9 +384,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{VIEWS}-view {gshape[2]}x{gshape[1]}x{gshape[0]} fp32 "
-                                   f"({N} brick(s) of {BRICK[2]}x{BRICK[1]}x{BRICK[0]}), {PSF}^3 PSFs, "
-                                   "Efficient-Bayesian, lambda 0.006, gen-2 semantics; step = one iteration over all views",
+            "config": {"workload": workload_string(N)[0],
                        "fft_dims_zyx": list(info.fft_dims), "np_voxels_per_brick": np_brick,
                        "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), NCCL halo exchange" if N > 1 else "single GPU",
                        "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"},

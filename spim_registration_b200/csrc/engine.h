@@ -136,6 +136,7 @@ inline int env_int(const char* name, int dflt) {
 inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); return t; }
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
+inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
 inline int threads_colp() { static int t = env_int("SPIM_THREADS_COLP", 512); return t; }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct, 1 persistent double-buffered, 2 one-shot async tile
 
@@ -316,7 +317,15 @@ public:
             p.ntiles = (int)grid;
             p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
             rt::launch<ColPassP, 512>(p, p.nctas, threads_colp(), (p.kstage ? 4 : 2) * smem, st);
-        } else if (use_colp() == 2) {
+        } else if (use_colp() == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
+            // experimental TMA / mbarrier pipeline (not yet timed on hardware)
+            p.kstage = 0;
+            p.ntiles = (int)grid;
+            p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
+            int T = threads_colt();
+            if (T < 96) T = 96;
+            rt::launch<ColPassT, 512>(p, p.nctas, T, 3 * smem + 64, st);
+        } else if (use_colp() >= 2) {
             p.ntiles = -1;    // async mode flag
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;

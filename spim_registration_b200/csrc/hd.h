@@ -19,6 +19,12 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 #define SPIM_HD inline
 #define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)
 #define SPIM_BARRIER() ((void)0)
+// a thread group = the threads that cooperate on one tile (the whole CTA, or one consumer group of a
+// warp-specialised kernel); the emulator runs every group as a single serial thread
+struct TG { int tid, n, bar; };
+static inline TG tg_cta() { TG t; t.tid = 0; t.n = 1; t.bar = 0; return t; }
+static inline void tg_barrier(const TG&) {}
+#define SPIM_FOR_ITEMS_TG(tg, i, cnt) for (int i = (tg).tid; i < (int)(cnt); i += (tg).n)
 #define SPIM_NTHREADS 1
 #define SPIM_TID 0
 template <class T> static inline T spim_ldg(const T* p) { return *p; }
@@ -45,6 +51,13 @@ static inline float spim_fmaf_rn(float a, float b, float c) { return fmaf(a, b, 
 #define SPIM_HD __host__ __device__ __forceinline__
 #define SPIM_FOR_ITEMS(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)
 #define SPIM_BARRIER() __syncthreads()
+struct TG { int tid, n, bar; };   // thread index in the group, group size, named barrier id (0 = whole CTA)
+__device__ __forceinline__ TG tg_cta() { TG t; t.tid = (int)threadIdx.x; t.n = (int)blockDim.x; t.bar = 0; return t; }
+__device__ __forceinline__ void tg_barrier(const TG& tg) {
+    if (tg.bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(tg.bar), "r"(tg.n) : "memory");
+}
+#define SPIM_FOR_ITEMS_TG(tg, i, cnt) for (int i = (tg).tid; i < (int)(cnt); i += (tg).n)
 #define SPIM_NTHREADS ((int)blockDim.x)
 #define SPIM_TID ((int)threadIdx.x)
 template <class T> __device__ __forceinline__ T spim_ldg(const T* p) { return __ldg(p); }
@@ -70,6 +83,31 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- mbarrier + TMA bulk-copy helpers (sm_90+/sm_100a) ------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
+// TMA bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // explicitly un-fused fp32 ops: the reference's Java float arithmetic has no FMA contraction
 __device__ __forceinline__ float spim_fadd_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float spim_fsub_rn(float a, float b) { return __fsub_rn(a, b); }

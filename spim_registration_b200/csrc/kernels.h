@@ -125,7 +125,7 @@ SPIM_DEV void apply_twiddles1(float2 (&a)[R], const float2* tw) {
 SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
 
 template <int R, bool INV>
-SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
+SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     const int M = pl.M[s];
     const int L = M * R;
     const int nb = pl.n / R;
@@ -133,7 +133,7 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int
     const float2* twp = pl.tws + pl.tw_off[s];
     const long long gs4 = g.stride >> 1;
     const long long gstep = (long long)M * gs4;
-    SPIM_FOR_ITEMS(i, nb * TP) {
+    SPIM_FOR_ITEMS_TG(tg, i, nb * TP) {
         const int c2 = i & (TP - 1);
         const int m = i >> 3;
         const int blk = (M == 1) ? m : fastdiv(m, magic);
@@ -190,15 +190,15 @@ SPIM_DEV void stage_tile(const FftPlanDev& pl, int s, float4* tile, int swz, int
             }
         }
     }
-    SPIM_BARRIER();
+    tg_barrier(tg);
 }
 
 // last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
 template <int R>
-SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
+SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
     const int nb = pl.n / R;
     const long long gs4 = g.stride >> 1;
-    SPIM_FOR_ITEMS(i, nb * TP) {
+    SPIM_FOR_ITEMS_TG(tg, i, nb * TP) {
         const int c2 = i & (TP - 1);
         const int base = (i >> 3) * R;
         float2 a[R], b[R];
@@ -246,7 +246,7 @@ SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g,
             for (int q = 0; q < R; ++q) sp[q * TP] = pack4(a[q], b[q]);
         }
     }
-    SPIM_BARRIER();
+    tg_barrier(tg);
 }
 
 // radix dispatch.  SPIM_MAX_RADIX bounds the radices the planner may use (and therefore the code paths
@@ -266,11 +266,11 @@ SPIM_DEV void mid_tile(const FftPlanDev& pl, float4* tile, int src_g, int dst_g,
     }
 
 template <bool INV>
-SPIM_DEV void stage_dispatch(const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
-    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(pl, s, tile, swz, src_g, dst_g, g)))
+SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
+    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(tg, pl, s, tile, swz, src_g, dst_g, g)))
 }
-SPIM_DEV void mid_dispatch(const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
-    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(pl, tile, src_g, dst_g, g, kh, ks, ks4)))
+SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
+    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,13 +303,22 @@ SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_l
     float4* d = buf + row * TP + c2;
     const float4* g = gp + (long long)row * gs4 + c2;
     const long long gstep = (long long)rstep * gs4;
-    for (; row < row_hi; row += rstep, d += rstep * TP, g += gstep) cp_async16(d, g);
+    const int dstep = rstep * TP;
+    // four rows per trip: one bounds check and one pointer update per four 16-byte copies
+    for (; row + 3 * rstep < row_hi; row += 4 * rstep, d += 4 * dstep, g += 4 * gstep) {
+        cp_async16(d, g);
+        cp_async16(d + dstep, g + gstep);
+        cp_async16(d + 2 * dstep, g + 2 * gstep);
+        cp_async16(d + 3 * dstep, g + 3 * gstep);
+    }
+    for (; row < row_hi; row += rstep, d += dstep, g += gstep) cp_async16(d, g);
 #endif
 }
 
 struct ColPass {
     typedef ColPassParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
         const int o = bid / p.ntx;
         const int tx = bid - o * p.ntx;
@@ -348,13 +357,13 @@ struct ColPass {
             g.va = P; g.vb = P;
         }
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, sg && s == 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, sg && s == S - 1, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, sg && s == 0, 0, g);
-            mid_dispatch(pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
+            mid_dispatch(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
         }
     }
 };
@@ -394,6 +403,7 @@ struct ColPassP {
         cp_async_commit();
     }
     SPIM_DEV static void run(const Params& p, int bid, float2* smem2) {
+        const TG tg = tg_cta();
         const FftPlanDev& pl = p.plan;
         const int P = pl.n;
         const int S = pl.nstages;
@@ -419,17 +429,117 @@ struct ColPassP {
             g.stride = p.row_stride;
             g.va = P; g.vb = P; g.sa = p.sa;
             if (p.mode == COL_FWD) {
-                for (int s = 0; s < S; ++s) stage_dispatch<false>(pl, s, tile, 0, 0, s == S - 1, g);
+                for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g);
             } else if (p.mode == COL_INV) {
-                for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+                for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
             } else {
-                for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(pl, s, tile, 0, 0, 0, g);
-                if (p.kstage) mid_dispatch(pl, tile, 0, S == 1, g, nullptr, kbuf[cur], 0);
-                else mid_dispatch(pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
-                for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(pl, s, tile, 0, 0, s == 0, g);
+                for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, 0, g);
+                if (p.kstage) mid_dispatch(tg, pl, tile, 0, S == 1, g, nullptr, kbuf[cur], 0);
+                else mid_dispatch(tg, pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
+                for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
             }
             // every stage ends with a barrier, so buf[cur] is free for the loads issued next iteration
         }
+    }
+};
+
+// Persistent, warp-specialised variant with a TMA / mbarrier pipeline (EXPERIMENTAL, SPIM_COLP=3, not yet
+// timed on hardware): one CTA per SM; the last warp is the producer and streams whole tile rows into a ring
+// of NSLOT shared-memory tiles with cp.async.bulk (UBLKCP, completion counted on an mbarrier); two consumer
+// groups alternate over the tiles with their own named barriers, so one group's barrier / latency stalls are
+// filled by the other; results leave straight from the registers of the last stage.
+struct ColPassT {
+    typedef ColPassParams Params;
+    static constexpr int NSLOT = 3;
+    SPIM_DEV static void consume(const TG& tg, const Params& p, int t, float4* tile) {
+        const FftPlanDev& pl = p.plan;
+        const int P = pl.n, S = pl.nstages;
+        if (p.va < p.vb) {   // rows of the zero gap are never loaded
+            SPIM_FOR_ITEMS_TG(tg, i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tg_barrier(tg);
+        long long base;
+        ColPassP::tile_base(p, t, base);
+        GRows g;
+        g.p = p.data + base;
+        g.stride = p.row_stride;
+        g.va = P; g.vb = P; g.sa = p.sa;
+        if (p.mode == COL_FWD) {
+            for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g);
+        } else if (p.mode == COL_INV) {
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
+        } else {
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, 0, g);
+            mid_dispatch(tg, pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
+        }
+    }
+    SPIM_DEV static void run(const Params& p, int bid, float2* smem2) {
+        const int P = p.plan.n;
+        float4* smem = reinterpret_cast<float4*>(smem2);
+        const long long gs4 = p.row_stride >> 1;
+        const bool gap = p.va < p.vb;
+        const int nvalid = gap ? P - (p.vb - p.va) : P;
+#if defined(SPIM_HOST_EMU)
+        const TG tg = tg_cta();
+        for (int t = bid; t < p.ntiles; t += p.nctas) {
+            long long base;
+            ColPassP::tile_base(p, t, base);
+            const float4* gp = reinterpret_cast<const float4*>(p.data + base);
+            for (int r = 0; r < nvalid; ++r) {
+                const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
+                memcpy(smem + row * TP, gp + (long long)row * gs4, TP * sizeof(float4));
+            }
+            consume(tg, p, t, smem);
+        }
+#else
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NSLOT * P * TP);
+        uint64_t* empty = full + NSLOT;
+        const int tid = threadIdx.x;
+        const int nthr = blockDim.x;
+        const int gsize = ((nthr - 32) / 64) * 32;      // two consumer groups of whole warps
+        const int ntl = (p.ntiles - bid + p.nctas - 1) / p.nctas;
+        if (tid == 0) {
+            for (int s = 0; s < NSLOT; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid >= 2 * gsize) {
+            if (tid >= 2 * gsize + 32) return;          // spare threads of a partial warp layout
+            // ---- producer warp -------------------------------------------------------------------------
+            const int lane = tid & 31;
+            for (int i = 0; i < ntl; ++i) {
+                const int slot = i % NSLOT, use = i / NSLOT;
+                if (use > 0) mbar_wait(empty + slot, (unsigned)((use - 1) & 1));
+                const int t = bid + i * p.nctas;
+                long long base;
+                ColPassP::tile_base(p, t, base);
+                const float4* gp = reinterpret_cast<const float4*>(p.data + base);
+                float4* dst = smem + (size_t)slot * P * TP;
+                if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(nvalid * TP * sizeof(float4)));
+                __syncwarp();
+                for (int r = lane; r < nvalid; r += 32) {
+                    const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
+                    bulk_g2s(dst + row * TP, gp + (long long)row * gs4, TP * sizeof(float4), full + slot);
+                }
+            }
+        } else {
+            // ---- two consumer groups, alternating tiles -------------------------------------------------
+            const int group = tid / gsize;
+            TG tg;
+            tg.tid = tid - group * gsize; tg.n = gsize; tg.bar = 1 + group;
+            for (int i = group; i < ntl; i += 2) {
+                const int slot = i % NSLOT, use = i / NSLOT;
+                mbar_wait(full + slot, (unsigned)(use & 1));
+                float4* tile = smem + (size_t)slot * P * TP;
+                consume(tg, p, bid + i * p.nctas, tile);
+                // generic-proxy accesses to this slot are done; order them before the next async-proxy refill
+                fence_proxy_async();
+                tg_barrier(tg);
+                if (tg.tid == 0) mbar_arrive(empty + slot);
+            }
+        }
+#endif
     }
 };
 
@@ -535,6 +645,7 @@ SPIM_DEV void split_inv(float2 A, float2 B, float2 w, float2& zk, float2& zm) {
 struct XFwd {
     typedef XFwdParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
         const FftPlanDev& pl = p.plan;
         const int N2 = pl.n;
@@ -571,7 +682,7 @@ struct XFwd {
         SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR>(p, tile, srcoff)))
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
-        for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(pl, s, tile, 1, 0, 0, g);
+        for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
         // split step on line pairs (factor 1/2 folded into the kernel scale)
         const int nk = p.nk;
         SPIM_FOR_ITEMS(i, nk * TP) {
@@ -798,6 +909,7 @@ template <int EPI, bool EXACT>
 struct XInvT {
     typedef XInvParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
         const FftPlanDev& pl = p.plan;
         const int N2 = pl.n;
@@ -856,7 +968,7 @@ struct XInvT {
         SPIM_BARRIER();
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
-        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(pl, s, tile, 1, 0, 0, g);
+        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
         if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, EXACT, true>(p, tile2, auxoff, dstoff, acc))) }
