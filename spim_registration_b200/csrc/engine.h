@@ -137,8 +137,7 @@ inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); re
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
 inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
-inline int threads_colp() { static int t = env_int("SPIM_THREADS_COLP", 512); return t; }
-inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct, 1 persistent double-buffered, 2 one-shot async tile
+inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
 
@@ -310,15 +309,9 @@ public:
         const long long grid = (long long)p.ntx * outer_count;
         const size_t smem = (size_t)Pa * TC * sizeof(float2);
         if (timer) timer->begin(id, st);
-        // persistent double-buffered variant when two (or, with the kernel spectrum staged, four) tiles fit
         const size_t lim = rt::max_smem();
-        if (use_colp() == 1 && 2 * smem <= lim && grid <= 0x7fffffff) {
-            p.kstage = (mode == COL_MID && 4 * smem <= lim) ? 1 : 0;
-            p.ntiles = (int)grid;
-            p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
-            rt::launch<ColPassP, 512>(p, p.nctas, threads_colp(), (p.kstage ? 4 : 2) * smem, st);
-        } else if (use_colp() == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
-            // experimental TMA / mbarrier pipeline (not yet timed on hardware)
+        if (use_colp() == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
+            // experimental TMA / mbarrier pipeline: correct, but slower than the default in round 1 (see kernels.h)
             p.kstage = 0;
             p.ntiles = (int)grid;
             p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());

@@ -286,8 +286,8 @@ struct ColPassParams {
     int outer_split, outer_shift;  // outer = o < split ? o : o + shift  (skips the zero gap)
     int va, vb, sa;
     int mode;
-    int ntiles, nctas;         // ColPassP (persistent): tiles in total / CTAs launched
-    int kstage;                // ColPassP, COL_MID: kernel-spectrum tile staged in shared memory too
+    int ntiles, nctas;         // ColPassT (persistent): tiles in total / CTAs launched; ntiles < 0 selects the async mode of ColPass
+    int kstage;                // COL_MID: kernel-spectrum tile staged in shared memory too
 };
 
 // asynchronous copy of tile rows [row_lo, row_hi) (16 float2 = 8 x 16 B each) from global to shared memory.
@@ -368,83 +368,17 @@ struct ColPass {
     }
 };
 
-// Persistent, double-buffered variant: each CTA walks tiles bid, bid+nctas, ...; while the FFT stages of
-// tile t run out of one shared-memory buffer, the rows of tile t+1 stream into the other one with
-// cp.async (LDGSTS), so the global-memory latency is off the critical path.  Results leave straight from
-// the registers of the last stage.
-struct ColPassP {
-    typedef ColPassParams Params;
-    SPIM_DEV static void tile_base(const Params& p, int t, long long& base) {
-        const int o = t / p.ntx;
-        const int tx = t - o * p.ntx;
-        const int outer = o < p.outer_split ? o : o + p.outer_shift;
-        base = (long long)outer * p.outer_stride + (long long)tx * TC;
-    }
-    SPIM_DEV static void issue(const Params& p, int t, float4* buf, float4* kbuf) {
-        long long base;
-        tile_base(p, t, base);
-        const int P = p.plan.n;
-        const long long gs4 = p.row_stride >> 1;
-        const bool gap = p.va < p.vb;
-        const int nvalid = gap ? P - (p.vb - p.va) : P;
-        const float4* gp = reinterpret_cast<const float4*>(p.data + base);
-        SPIM_FOR_ITEMS(i, nvalid * TP) {
-            const int r = i >> 3, c2 = i & (TP - 1);
-            const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
-            cp_async16(buf + row * TP + c2, gp + (long long)row * gs4 + c2);
-        }
-        if (p.mode == COL_MID && p.kstage) {
-            const float4* kp = reinterpret_cast<const float4*>(p.khat + base);
-            SPIM_FOR_ITEMS(i, P * TP) {
-                const int r = i >> 3, c2 = i & (TP - 1);
-                cp_async16(kbuf + i, kp + (long long)r * gs4 + c2);
-            }
-        }
-        cp_async_commit();
-    }
-    SPIM_DEV static void run(const Params& p, int bid, float2* smem2) {
-        const TG tg = tg_cta();
-        const FftPlanDev& pl = p.plan;
-        const int P = pl.n;
-        const int S = pl.nstages;
-        float4* smem = reinterpret_cast<float4*>(smem2);
-        float4* buf[2] = {smem, smem + (size_t)P * TP};
-        float4* kbuf[2] = {smem + 2 * (size_t)P * TP, smem + 3 * (size_t)P * TP};
-        int t = bid;
-        if (t >= p.ntiles) return;
-        issue(p, t, buf[0], kbuf[0]);
-        for (int cur = 0; t < p.ntiles; t += p.nctas, cur ^= 1) {
-            const int tn = t + p.nctas;
-            if (tn < p.ntiles) { issue(p, tn, buf[cur ^ 1], kbuf[cur ^ 1]); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            float4* tile = buf[cur];
-            if (p.va < p.vb) {   // rows of the zero gap are not loaded
-                SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            SPIM_BARRIER();
-            long long base;
-            tile_base(p, t, base);
-            GRows g;
-            g.p = p.data + base;
-            g.stride = p.row_stride;
-            g.va = P; g.vb = P; g.sa = p.sa;
-            if (p.mode == COL_FWD) {
-                for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g);
-            } else if (p.mode == COL_INV) {
-                for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
-            } else {
-                for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, 0, g);
-                if (p.kstage) mid_dispatch(tg, pl, tile, 0, S == 1, g, nullptr, kbuf[cur], 0);
-                else mid_dispatch(tg, pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
-                for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
-            }
-            // every stage ends with a barrier, so buf[cur] is free for the loads issued next iteration
-        }
-    }
-};
+// tile index -> offset of its first element (x tiles fastest, outer index mapped over the zero gap)
+SPIM_DEV void col_tile_base(const ColPassParams& p, int t, long long& base) {
+    const int o = t / p.ntx;
+    const int tx = t - o * p.ntx;
+    const int outer = o < p.outer_split ? o : o + p.outer_shift;
+    base = (long long)outer * p.outer_stride + (long long)tx * TC;
+}
 
-// Persistent, warp-specialised variant with a TMA / mbarrier pipeline (EXPERIMENTAL, SPIM_COLP=3, not yet
-// timed on hardware): one CTA per SM; the last warp is the producer and streams whole tile rows into a ring
+// Persistent, warp-specialised variant with a TMA / mbarrier pipeline (EXPERIMENTAL, SPIM_COLP=3): correct on
+// B200 (parity tests pass) but 3.7x slower than ColPass in round 1 -- 560 separate 128-byte bulk copies per
+// tile saturate the TMA unit; the next step is 2-D tensor-map boxes (one request per 256 rows).  One CTA per SM; the last warp is the producer and streams whole tile rows into a ring
 // of NSLOT shared-memory tiles with cp.async.bulk (UBLKCP, completion counted on an mbarrier); two consumer
 // groups alternate over the tiles with their own named barriers, so one group's barrier / latency stalls are
 // filled by the other; results leave straight from the registers of the last stage.
@@ -459,7 +393,7 @@ struct ColPassT {
         }
         tg_barrier(tg);
         long long base;
-        ColPassP::tile_base(p, t, base);
+        col_tile_base(p, t, base);
         GRows g;
         g.p = p.data + base;
         g.stride = p.row_stride;
@@ -484,7 +418,7 @@ struct ColPassT {
         const TG tg = tg_cta();
         for (int t = bid; t < p.ntiles; t += p.nctas) {
             long long base;
-            ColPassP::tile_base(p, t, base);
+            col_tile_base(p, t, base);
             const float4* gp = reinterpret_cast<const float4*>(p.data + base);
             for (int r = 0; r < nvalid; ++r) {
                 const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
@@ -513,7 +447,7 @@ struct ColPassT {
                 if (use > 0) mbar_wait(empty + slot, (unsigned)((use - 1) & 1));
                 const int t = bid + i * p.nctas;
                 long long base;
-                ColPassP::tile_base(p, t, base);
+                col_tile_base(p, t, base);
                 const float4* gp = reinterpret_cast<const float4*>(p.data + base);
                 float4* dst = smem + (size_t)slot * P * TP;
                 if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(nvalid * TP * sizeof(float4)));

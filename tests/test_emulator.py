@@ -86,3 +86,110 @@ def test_error_paths(emu_lib):
             s.run(1)
         with pytest.raises(ValueError):
             s.set_view(1, np.ones((4, 4, 5), np.float32), None, np.ones((3, 3, 3), np.float32))
+
+
+# ---- edge cases and error behaviour (host logic, no GPU) -------------------------------------------------
+def test_degenerate_and_ragged_shapes(emu_lib):
+    # 2-D data (one plane), one-voxel-thick axes, kernels with unit axes, tiny images
+    for shape, kshape in [((1, 1, 8), (1, 1, 3)), ((1, 9, 1), (1, 3, 1)), ((2, 2, 2), (1, 1, 1)), ((1, 1, 2), (1, 1, 1)),
+                          ((3, 1, 5), (3, 1, 3)), ((2, 3, 4), (2, 3, 4))]:
+        for ext in (0, 1, 2, 3, 4):
+            P.conv_case(emu_lib, shape, kshape, ext)
+
+
+def test_single_view_and_many_views(emu_lib):
+    P.decon_case(emu_lib, (8, 9, 10), 1, 3, O.EFFICIENT_BAYESIAN, 2, 2)      # V = 1: every type degenerates to INDEPENDENT
+    P.decon_case(emu_lib, (6, 7, 8), 9, 3, O.OPTIMIZATION_II, 2, 1)           # K1^9 by repeated fp32 multiplication
+
+
+def test_views_without_any_data_and_psi_nan_rule(emu_lib):
+    """all-zero images: gen-2 average is NaN -> 0.5 (MVDeconvolution.java:138-142) and psi is masked to 0."""
+    from spim_registration_b200.deconvolution import Session
+    shape = (6, 6, 6)
+    z = np.zeros(shape, np.float32)
+    k = np.ones((3, 3, 3), np.float32)
+    with Session(shape, 2, 2, generation=2, lib=emu_lib) as s:
+        s.set_view(0, z, None, k)
+        s.set_view(1, z, None, k)
+        s.init()
+        assert s.info().avg == 0.5
+        s.run(1)
+        s.finish()
+        assert np.all(s.get_psi() == 0)
+
+
+def test_limits_and_argument_validation(emu_lib):
+    import ctypes
+    from spim_registration_b200 import native
+    from spim_registration_b200.deconvolution import Session
+    with pytest.raises(native.NativeError, match="num_views"):
+        Session((4, 4, 4), 65, 2, lib=emu_lib)                       # MAX_VIEWS = 64
+    with pytest.raises(native.NativeError, match="generation"):
+        Session((4, 4, 4), 1, 2, generation=3, lib=emu_lib)
+    with pytest.raises(native.NativeError, match="dims"):
+        Session((0, 4, 4), 1, 2, lib=emu_lib)
+    # an FFT axis that does not fit one shared-memory tile is refused with a message, not mis-computed
+    with Session((1, 1, 3000), 1, 3, lib=emu_lib) as s:
+        s.set_view(0, np.ones((1, 1, 3000), np.float32), None, np.ones((1, 1, 3), np.float32))
+        s.init()                                                     # x axis: Px/2 ~ 1512 rows of 128 B -> fits in 227 KB
+    with Session((1, 2000, 4), 1, 3, lib=emu_lib) as s:
+        s.set_view(0, np.ones((1, 2000, 4), np.float32), None, np.ones((1, 3, 1), np.float32))
+        with pytest.raises(native.NativeError, match="too long"):
+            s.init()
+    # struct_size guards the ABI
+    p = native.MvdParams()
+    emu_lib.mvd_params_default(ctypes.byref(p))
+    p.struct_size = 4
+    h = ctypes.c_void_p()
+    assert emu_lib.mvd_session_create(ctypes.byref(p), ctypes.byref(h)) != 0
+    assert b"struct_size" in emu_lib.mvd_last_error()
+    # brick-only entry points refuse plain sessions
+    with Session((4, 4, 4), 1, 3, lib=emu_lib) as s:
+        s.set_view(0, np.ones((4, 4, 4), np.float32), None, np.ones((3, 3, 3), np.float32))
+        s.init()
+        with pytest.raises(native.NativeError, match="brick"):
+            s.set_halo_mask(1, 1)
+        with pytest.raises(native.NativeError):
+            s.view_phase(5, 0)
+
+
+def test_legacy_entry_argument_checks(emu_lib):
+    from spim_registration_b200 import native
+    im = np.ones((4, 4, 4), np.float32)
+    k = np.ones((3, 3, 3), np.float32)
+    emu_lib.convolution3DfftCUDAInPlace(im.ctypes.data_as(native.c_float_p), native.int3((4, 4, 0)),
+                                        k.ctypes.data_as(native.c_float_p), native.int3((3, 3, 3)), 0)
+    assert np.all(im == 1) and b"dims" in emu_lib.spim_fftconv_last_error()     # void entry: buffer untouched + message
+
+
+def test_block_mirror_classes_match_oracle():
+    """Block / BlockGeneratorFixedSizePrecise (host logic) against the oracle's restatement."""
+    from spim_registration_b200 import BlockGeneratorFixedSizePrecise
+    from spim_registration_b200.blocks import divide_into_blocks
+    img_xyz, blk_xyz, k_xyz = (23, 17, 20), (16, 11, 12), (7, 5, 5)
+    blocks = BlockGeneratorFixedSizePrecise(blk_xyz).divideIntoBlocks(img_xyz, k_xyz)
+    ref = O.divide_into_blocks(img_xyz[::-1], blk_xyz[::-1], k_xyz[::-1])
+    assert len(blocks) == len(ref)
+    key = lambda t: tuple(t)
+    assert sorted(key(b.getOffset()[::-1]) for b in blocks) == sorted(key(r.offset) for r in ref)
+    assert sorted(key(b.getEffectiveSize()[::-1]) for b in blocks) == sorted(key(r.effective_size) for r in ref)
+    assert BlockGeneratorFixedSizePrecise((4, 4, 4)).divideIntoBlocks(img_xyz, k_xyz) is None        # gen-2: too small -> null
+    assert divide_into_blocks(img_xyz, (4, 4, 4), k_xyz, double_too_small=True)[0].blockSize == (8, 8, 8)   # gen-1 doubles
+    rng = np.random.default_rng(0)
+    src = rng.random(img_xyz[::-1], dtype=np.float32)
+    out = np.zeros_like(src)
+    buf = np.empty(blk_xyz[::-1], np.float32)
+    for b in blocks:                       # copy (mirror extension) + paste of the effective region = identity
+        b.copyBlock(src, buf, 2)
+        b.pasteBlock(out, buf)
+    assert np.array_equal(out, src)
+
+
+def test_device_query_mirrors_without_gpu(cuda_lib):
+    from spim_registration_b200 import CUDATools, NativeLibraryTools, native
+    c = native.CUDAFourierConvolution()
+    if c.getNumDevicesCUDA() <= 0:
+        assert CUDATools.queryCUDADetails(c) is None                  # -1 / 0 devices -> null like the reference
+    lib = NativeLibraryTools.loadNativeLibrary()
+    assert lib is not None and callable(lib.convolution3DfftCUDAInPlace)
+    assert NativeLibraryTools.loadNativeLibrary(directory="/nonexistent") is None
