@@ -192,3 +192,39 @@ def test_fp32_mode_tracks_fp64_truth():
     r64 = O.deconvolve(imgs, ws, psfs, O.DeconParams(num_iterations=5, dtype=np.float64))
     per, l2 = O.parity_errors(r32.psi, r64.psi)
     assert per < 1e-3 and l2 < 1e-4
+
+
+@pytest.mark.parametrize("kshape", [(3, 3, 3), (5, 3, 7), (4, 2, 6)])
+def test_convolution_against_independent_library(kshape):
+    """The oracle's convolution definition (kernel origin at dim//2, out-of-bounds rules) against
+    scipy.ndimage.convolve, an independent implementation: ndimage 'mirror' = mirror-single, 'reflect' =
+    mirror-double, 'wrap' = periodic, 'constant' = constant value; ndimage.convolve with origin 0 places the
+    kernel origin at dim//2 for odd and even sizes alike, which is the reference's convention."""
+    import scipy.ndimage as ndi
+    img = _rand((9, 8, 11))
+    k = _rand(kshape)
+    origin = 0
+    for ext, mode, cval in [(O.EXT_MIRROR_SINGLE, "mirror", 0.0), (O.EXT_MIRROR_DOUBLE, "reflect", 0.0),
+                            (O.EXT_PERIODIC, "wrap", 0.0), (O.EXT_CONSTANT, "constant", 1.0), (O.EXT_ZERO, "constant", 0.0)]:
+        want = ndi.convolve(img, k, mode=mode, cval=cval, origin=origin)
+        got = O.convolve(img, k, ext, value=cval, dtype=np.float64)
+        assert np.abs(got - want).max() < 1e-12, (ext, kshape)
+
+
+def test_richardson_lucy_against_independent_formula():
+    """One gen-1 view-step with w = 1, lambda = 0 written out with scipy.ndimage only."""
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(3)
+    img = rng.random((8, 9, 10)) + 0.1
+    psf = rng.random((3, 3, 3))
+    k1 = psf / psf.sum()
+    psi0 = np.full(img.shape, 0.7)
+    blur = ndi.convolve(psi0, k1, mode="mirror")
+    want = np.maximum(1e-4, psi0 * ndi.convolve(img / blur, k1[::-1, ::-1, ::-1], mode="mirror"))
+    p = O.DeconParams(iteration_type=O.INDEPENDENT, num_iterations=1, lam=0.0, gen=O.GEN1, dtype=np.float64,
+                      psi_init=psi0)
+    k1f = O.norm_image(psf).astype(np.float64)        # the oracle normalises in fp64 and stores fp32
+    blur = ndi.convolve(psi0, k1f, mode="mirror")
+    want = np.maximum(1e-4, psi0 * ndi.convolve(img / blur, k1f[::-1, ::-1, ::-1], mode="mirror"))
+    got = O.deconvolve([img], [np.ones(img.shape, np.float32)], [psf], p).psi
+    assert np.abs(got - want).max() < 1e-10
