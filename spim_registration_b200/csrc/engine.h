@@ -317,6 +317,29 @@ public:
             p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
             int T = threads_colt();
             if (T < 96) T = 96;
+            // tensor-map producer (SPIM_TMAP=1): one request per box of box_rows rows instead of one per row
+            static int want_tmap = env_int("SPIM_TMAP", 1);
+            p.use_tmap = 0;
+            if (want_tmap) {
+                int br = 0;
+                for (int d = std::min(Pa, 256); d >= 1; --d) if (Pa % d == 0) { br = d; break; }
+                const unsigned long long fl = 2ull * pitch;                      // floats per row
+                bool ok = br >= 8 && Pa / br <= 32;
+                if (ok && axis == 1) {
+                    const unsigned long long dims[2] = {fl, (unsigned long long)P[1] * P[0]};
+                    const unsigned long long str[1] = {fl * 4};
+                    const unsigned int box[2] = {2 * TC, (unsigned)br};
+                    ok = rt::encode_tensor_map(&p.tmap, data, 2, dims, str, box);
+                    p.tmap_rank = 2;
+                } else if (ok) {
+                    const unsigned long long dims[3] = {fl, (unsigned long long)P[1], (unsigned long long)P[0]};
+                    const unsigned long long str[2] = {fl * 4, fl * 4 * P[1]};
+                    const unsigned int box[3] = {2 * TC, 1, (unsigned)br};
+                    ok = rt::encode_tensor_map(&p.tmap, data, 3, dims, str, box);
+                    p.tmap_rank = 3;
+                }
+                if (ok) { p.use_tmap = 1; p.box_rows = br; }
+            }
             rt::launch<ColPassT, 512>(p, p.nctas, T, 3 * smem + 64, st);
         } else if (use_colp() >= 2) {
             p.ntiles = -1;    // async mode flag

@@ -21,6 +21,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 #define SPIM_BARRIER() ((void)0)
 // a thread group = the threads that cooperate on one tile (the whole CTA, or one consumer group of a
 // warp-specialised kernel); the emulator runs every group as a single serial thread
+struct alignas(64) SpimTensorMap { unsigned long long opaque[16]; };   // CUtensorMap stand-in (unused by the emulator)
 struct TG { int tid, n, bar; };
 static inline TG tg_cta() { TG t; t.tid = 0; t.n = 1; t.bar = 0; return t; }
 static inline void tg_barrier(const TG&) {}
@@ -46,6 +47,8 @@ static inline float spim_fmaf_rn(float a, float b, float c) { return fmaf(a, b, 
 #else
 
 #include <cuda_runtime.h>
+#include <cuda.h>
+typedef CUtensorMap SpimTensorMap;
 #define SPIM_DEV __device__ __forceinline__
 #define SPIM_NOINLINE_DEV __device__ __noinline__
 #define SPIM_HD __host__ __device__ __forceinline__
@@ -106,6 +109,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { whil
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA tensor copies global -> shared (UTMALDG): one request moves a whole [rows][128 B] box
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const SpimTensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const SpimTensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // explicitly un-fused fp32 ops: the reference's Java float arithmetic has no FMA contraction

@@ -288,6 +288,10 @@ struct ColPassParams {
     int mode;
     int ntiles, nctas;         // ColPassT (persistent): tiles in total / CTAs launched; ntiles < 0 selects the async mode of ColPass
     int kstage;                // COL_MID: kernel-spectrum tile staged in shared memory too
+    // ColPassT with tensor maps (use_tmap): y pass = 2-D map {2*pitch floats, Py*Pz rows}, box {32, box_rows};
+    // z pass = 3-D map {2*pitch, Py, Pz}, box {32, 1, box_rows}; box_rows divides the FFT length
+    int use_tmap, box_rows, tmap_rank;
+    SpimTensorMap tmap;
 };
 
 // asynchronous copy of tile rows [row_lo, row_hi) (16 float2 = 8 x 16 B each) from global to shared memory.
@@ -450,11 +454,26 @@ struct ColPassT {
                 col_tile_base(p, t, base);
                 const float4* gp = reinterpret_cast<const float4*>(p.data + base);
                 float4* dst = smem + (size_t)slot * P * TP;
-                if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(nvalid * TP * sizeof(float4)));
-                __syncwarp();
-                for (int r = lane; r < nvalid; r += 32) {
-                    const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
-                    bulk_g2s(dst + row * TP, gp + (long long)row * gs4, TP * sizeof(float4), full + slot);
+                if (p.use_tmap) {
+                    // whole tile (gap rows included: they are zeroed by the consumers after arrival) in P / box_rows requests
+                    const int o = t / p.ntx;
+                    const int tx = t - o * p.ntx;
+                    const int outer = o < p.outer_split ? o : o + p.outer_shift;
+                    const int nbox = P / p.box_rows;
+                    if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(P * TP * sizeof(float4)));
+                    __syncwarp();
+                    if (lane < nbox) {
+                        float4* d = dst + (size_t)lane * p.box_rows * TP;
+                        if (p.tmap_rank == 2) tma_load_2d(d, &p.tmap, tx * 2 * TC, outer * P + lane * p.box_rows, full + slot);
+                        else tma_load_3d(d, &p.tmap, tx * 2 * TC, outer, lane * p.box_rows, full + slot);
+                    }
+                } else {
+                    if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(nvalid * TP * sizeof(float4)));
+                    __syncwarp();
+                    for (int r = lane; r < nvalid; r += 32) {
+                        const int row = (gap && r >= p.va) ? r + (p.vb - p.va) : r;
+                        bulk_g2s(dst + row * TP, gp + (long long)row * gs4, TP * sizeof(float4), full + slot);
+                    }
                 }
             }
         } else {

@@ -37,6 +37,8 @@ inline void launch(const typename Body::Params& p, long long grid, int /*block*/
     for (long long b = 0; b < grid; ++b) Body::run(p, (int)b, reinterpret_cast<float2*>(buf.data()));
 }
 
+inline bool encode_tensor_map(SpimTensorMap*, void*, int, const unsigned long long*, const unsigned long long*, const unsigned int*) { return false; }
+
 struct KernelTimer {
     void enable(bool) {}
     void begin(int, Stream) {}
@@ -87,7 +89,7 @@ inline int sm_count() {
 
 template <class Body, int MAXT>
 __global__ void __launch_bounds__(MAXT) kernel_entry(const __grid_constant__ typename Body::Params p) {
-    extern __shared__ __align__(16) unsigned char spim_smem[];
+    extern __shared__ __align__(1024) unsigned char spim_smem[];
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
 
@@ -104,6 +106,29 @@ inline void launch(const typename Body::Params& p, long long grid, int block, si
     if (block > MAXT) block = MAXT;
     kernel_entry<Body, MAXT><<<(unsigned)grid, block, smem, s>>>(p);
     SPIM_CUDA_CHECK(cudaGetLastError());
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+inline bool encode_tensor_map(SpimTensorMap* out, void* base, int rank, const unsigned long long* dims,
+                              const unsigned long long* strides_bytes /* rank-1 */, const unsigned int* box) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (EncodeFn)ptr;
+    }
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // optional per-kernel-class timing with CUDA events on the launching stream
