@@ -187,9 +187,53 @@ template <int R, bool INV> struct DftComposite {
     }
 };
 
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+constexpr int cmodinv(int a, int m) {      // a^-1 mod m (m small)
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
+    return 1;
+}
+// coprime factors for the prime-factor (Good-Thomas) butterfly, 0 if the radix has none
+constexpr int pfa_factor(int r) {
+    if (r == 6) return 2;
+    if (r == 10) return 2;
+    if (r == 12) return 4;
+    if (r == 14) return 2;
+    if (r == 15) return 3;
+    return 0;
+}
+
+// composite radix with coprime factors R = R1*R2: Good-Thomas index maps make the two small DFTs
+// independent -- no internal twiddle multiplications, the permutations are register renames.
+//   input  n = (R2*n1 + R1*n2) mod R,  output k = (k1*R2*(R2^-1 mod R1) + k2*R1*(R1^-1 mod R2)) mod R
+template <int R, bool INV> struct DftPFA {
+    SPIM_HD static void run(float2 (&a)[R]) {
+        constexpr int R1 = pfa_factor(R);
+        constexpr int R2 = R / R1;
+        static_assert(cgcd(R1, R2) == 1, "PFA needs coprime factors");
+        constexpr int E1 = R2 * cmodinv(R2 % R1, R1);   // == 1 mod R1, == 0 mod R2
+        constexpr int E2 = R1 * cmodinv(R1 % R2, R2);   // == 0 mod R1, == 1 mod R2
+        float2 y[R];
+        static_for<R2>([&](auto n2i) {
+            constexpr int n2 = decltype(n2i)::value;
+            float2 t[R1];
+            static_for<R1>([&](auto n1i) { constexpr int n1 = decltype(n1i)::value; t[n1] = a[(R2 * n1 + R1 * n2) % R]; });
+            dft<R1, INV>(t);
+            static_for<R1>([&](auto k1i) { constexpr int k1 = decltype(k1i)::value; y[k1 * R2 + n2] = t[k1]; });
+        });
+        static_for<R1>([&](auto k1i) {
+            constexpr int k1 = decltype(k1i)::value;
+            float2 u[R2];
+            static_for<R2>([&](auto n2i) { constexpr int n2 = decltype(n2i)::value; u[n2] = y[k1 * R2 + n2]; });
+            dft<R2, INV>(u);
+            static_for<R2>([&](auto k2i) { constexpr int k2 = decltype(k2i)::value; a[(k1 * E1 + k2 * E2) % R] = u[k2]; });
+        });
+    }
+};
+
 template <int R, bool INV> struct Dft {
     SPIM_HD static void run(float2 (&a)[R]) {
         if constexpr (is_prime(R)) DftPrime<R, INV>::run(a);
+        else if constexpr (pfa_factor(R) != 0) DftPFA<R, INV>::run(a);
         else DftComposite<R, INV>::run(a);
     }
 };
