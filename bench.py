@@ -39,8 +39,8 @@ VIEWS = 7
 PSF = 31
 LAMBDA = 0.006
 ITER_TYPE = 2                # EFFICIENT_BAYESIAN
-METRIC = "MV deconvolution voxel-view-iterations/s"
-UNIT = "voxel-view-iterations/s"
+METRIC = "MV deconvolution voxel-view-iters/s"      # BASELINE.json: "MV deconvolution voxel-view-iters/s at 1/2/4/8 B200"
+UNIT = "voxel-view-iters/s"
 KERNEL_NAMES = ["x_fwd_r2c", "y_fwd", "z_fwd_mul_inv", "y_inv", "x_inv_c2r_epilogue"]
 KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor * Np
 # the x-inverse launch also carries the fused pointwise traffic of SURVEY 8d (16 B per voxel-view-iteration):
