@@ -184,6 +184,46 @@ class BrickRunner:
         self._send_off = np.concatenate([[0], np.cumsum(sizes_s)]).astype(int)
         self._recv_off = np.concatenate([[0], np.cumsum(sizes_r)]).astype(int)
         self.use_pack = os.environ.get("SPIM_BRICK_PACK", "1") != "0"
+        if self.use_pack and plan and self.dist is not None:
+            self._verify_pack_path()
+
+    def _verify_pack_path(self):
+        """One-time self-check: the single-launch pack / unpack exchange must reproduce the halo the plain
+        slab-copy exchange produces, bit for bit, on every rank -- otherwise all ranks fall back together."""
+        import torch
+        t = self._bufs[1][0]                      # the ratio buffer is scratch at this point
+        keep = t.clone()
+        g = torch.Generator(device=t.device).manual_seed(1234 + self.rank)
+        t.copy_(torch.rand(t.shape, generator=g, device=t.device, dtype=t.dtype))
+        filled = t.clone()
+        ok = True
+        try:
+            self.use_pack = False
+            self.exchange(1)
+            self._sync_stream()
+            want = t.clone()
+            t.copy_(filled)
+            self.use_pack = True
+            self.exchange(1)
+            self._sync_stream()
+            ok = bool(torch.equal(t, want))
+        except Exception as e:                    # argument / launch errors surface before any NCCL call is posted
+            ok = False
+            if self.rank == 0:
+                print(f"[bricks] pack path unavailable ({type(e).__name__}: {e})", flush=True)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=t.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        self.use_pack = bool(int(flag.item()))
+        if not self.use_pack and self.rank == 0:
+            print("[bricks] halo exchange: using slab copies (pack-path self-check failed)", flush=True)
+        t.copy_(keep)
+        self._sync_stream()
+
+    def _sync_stream(self):
+        self.session.sync()
+        if not self.cpu:
+            import torch
+            torch.cuda.synchronize()
         lo_mask = sum(1 << d for d in range(3) if self._neighbour(d, -1) is not None)
         hi_mask = sum(1 << d for d in range(3) if self._neighbour(d, +1) is not None)
         self.session.set_halo_mask(lo_mask, hi_mask)
