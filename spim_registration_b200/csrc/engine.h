@@ -137,6 +137,8 @@ inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); re
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
 inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
+// SPIM_REGCAP=1 (experiment): run the column pass from an instantiation capped at 85 registers (3 x 256 threads per SM)
+inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
@@ -345,7 +347,8 @@ public:
             p.ntiles = -1;    // async mode flag
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
-            rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            if (use_regcap()) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            else rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
         } else {
             rt::launch<ColPass>(p, grid, threads_col(), smem, st);
         }

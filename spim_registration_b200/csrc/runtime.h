@@ -31,7 +31,7 @@ inline void stream_sync(Stream) {}
 inline size_t max_smem() { return 227 * 1024; }
 inline int sm_count() { return 148; }
 
-template <class Body, int MAXT = 256>
+template <class Body, int MAXT = 256, int MINB = 1>
 inline void launch(const typename Body::Params& p, long long grid, int /*block*/, size_t smem, Stream) {
     std::vector<double> buf((smem + 7) / 8 + 1);
     for (long long b = 0; b < grid; ++b) Body::run(p, (int)b, reinterpret_cast<float2*>(buf.data()));
@@ -87,24 +87,25 @@ inline int sm_count() {
     return v;
 }
 
-template <class Body, int MAXT>
-__global__ void __launch_bounds__(MAXT) kernel_entry(const __grid_constant__ typename Body::Params p) {
+// MINB > 1 asks ptxas to fit MINB blocks of MAXT threads per SM (caps the registers per thread)
+template <class Body, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) kernel_entry(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
 
-template <class Body, int MAXT = 256>
+template <class Body, int MAXT = 256, int MINB = 1>
 inline void launch(const typename Body::Params& p, long long grid, int block, size_t smem, Stream s) {
     if (grid <= 0) return;
     static thread_local size_t configured[64] = {0};   // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && smem > configured[dev]) {
-        SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
     if (block > MAXT) block = MAXT;
-    kernel_entry<Body, MAXT><<<(unsigned)grid, block, smem, s>>>(p);
+    kernel_entry<Body, MAXT, MINB><<<(unsigned)grid, block, smem, s>>>(p);
     SPIM_CUDA_CHECK(cudaGetLastError());
 }
 
