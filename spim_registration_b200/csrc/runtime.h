@@ -87,9 +87,14 @@ inline int sm_count() {
     return v;
 }
 
-// MINB > 1 asks ptxas to fit MINB blocks of MAXT threads per SM (caps the registers per thread)
+template <class Body, int MAXT>
+__global__ void __launch_bounds__(MAXT) kernel_entry(const __grid_constant__ typename Body::Params p) {
+    extern __shared__ __align__(1024) unsigned char spim_smem[];
+    Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
+}
+// experiment hook: MINB blocks of MAXT threads per SM must fit (caps the registers per thread)
 template <class Body, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) kernel_entry(const __grid_constant__ typename Body::Params p) {
+__global__ void __launch_bounds__(MAXT, MINB) kernel_entry_capped(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
@@ -100,12 +105,20 @@ inline void launch(const typename Body::Params& p, long long grid, int block, si
     static thread_local size_t configured[64] = {0};   // per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 64 && smem > configured[dev]) {
-        SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = smem;
-    }
     if (block > MAXT) block = MAXT;
-    kernel_entry<Body, MAXT, MINB><<<(unsigned)grid, block, smem, s>>>(p);
+    if constexpr (MINB > 1) {
+        if (dev < 64 && smem > configured[dev]) {
+            SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry_capped<Body, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = smem;
+        }
+        kernel_entry_capped<Body, MAXT, MINB><<<(unsigned)grid, block, smem, s>>>(p);
+    } else {
+        if (dev < 64 && smem > configured[dev]) {
+            SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = smem;
+        }
+        kernel_entry<Body, MAXT><<<(unsigned)grid, block, smem, s>>>(p);
+    }
     SPIM_CUDA_CHECK(cudaGetLastError());
 }
 
