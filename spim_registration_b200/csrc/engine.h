@@ -139,7 +139,7 @@ inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); re
 inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
 // SPIM_REGCAP=1 (experiment): run the column pass from an instantiation capped at 85 registers (3 x 256 threads per SM)
 inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
-inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline
+inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
 
@@ -343,6 +343,9 @@ public:
                 if (ok) { p.use_tmap = 1; p.box_rows = br; }
             }
             rt::launch<ColPassT, 512>(p, p.nctas, T, 3 * smem + 64, st);
+        } else if (use_colp() == 4) {
+            // experimental warp-private-column variant: 4 warps per tile, no CTA barriers between stages
+            rt::launch<ColPassW>(p, grid, 128, smem, st);
         } else if (use_colp() >= 2) {
             p.ntiles = -1;    // async mode flag
             static int ks = env_int("SPIM_KSTAGE", 0);

@@ -26,6 +26,7 @@ struct TG { int tid, n, bar; };
 static inline TG tg_cta() { TG t; t.tid = 0; t.n = 1; t.bar = 0; return t; }
 static inline void tg_barrier(const TG&) {}
 #define SPIM_FOR_ITEMS_TG(tg, i, cnt) for (int i = (tg).tid; i < (int)(cnt); i += (tg).n)
+static inline void spim_syncwarp() {}
 #define SPIM_NTHREADS 1
 #define SPIM_TID 0
 template <class T> static inline T spim_ldg(const T* p) { return *p; }
@@ -61,6 +62,7 @@ __device__ __forceinline__ void tg_barrier(const TG& tg) {
     else asm volatile("bar.sync %0, %1;" ::"r"(tg.bar), "r"(tg.n) : "memory");
 }
 #define SPIM_FOR_ITEMS_TG(tg, i, cnt) for (int i = (tg).tid; i < (int)(cnt); i += (tg).n)
+__device__ __forceinline__ void spim_syncwarp() { __syncwarp(); }
 #define SPIM_NTHREADS ((int)blockDim.x)
 #define SPIM_TID ((int)threadIdx.x)
 template <class T> __device__ __forceinline__ T spim_ldg(const T* p) { return __ldg(p); }

@@ -497,6 +497,174 @@ struct ColPassT {
 };
 
 // ---------------------------------------------------------------------------------------------
+// ColPassW (EXPERIMENTAL, SPIM_COLP=4, not yet timed on hardware): warp-private columns.
+// The 16 columns of a tile are dealt out to the 4 warps of the CTA, two column pairs each.  A column's FFT
+// only ever touches that column, so after the cooperative tile load (one CTA barrier) every warp runs all its
+// stages with warp-level synchronisation only: no CTA barriers between stages, and the warps of an SM drift
+// out of phase instead of stalling together.  Rows are stored rotated (pair c2 of row r sits in 16-byte slot
+// (c2 + 2 r) & 7) so that the 8 lanes of a quarter warp -- 4 consecutive rows x 2 pairs -- hit 8 different slots.
+// ---------------------------------------------------------------------------------------------
+constexpr int WP = 2;                       // column pairs per warp
+SPIM_HD int wslot(int c2, int row) { return (c2 + WP * row) & (TP - 1); }
+
+template <int R, bool INV>
+SPIM_DEV void stage_tile_w(int lane, int nlanes, int c0, const FftPlanDev& pl, int s, float4* tile, int dst_g, const GRows& g) {
+    const int M = pl.M[s];
+    const int L = M * R;
+    const int nb = pl.n / R;
+    const uint32_t magic = pl.magicM[s];
+    const float2* twp = pl.tws + pl.tw_off[s];
+    const long long gs4 = g.stride >> 1;
+    const long long gstep = (long long)M * gs4;
+    for (int i = lane; i < nb * WP; i += nlanes) {
+        const int c2 = c0 + (i & (WP - 1));
+        const int m = i >> 1;
+        const int blk = (M == 1) ? m : fastdiv(m, magic);
+        const int j = m - blk * M;
+        const int base = blk * L + j;
+        float2 a[R], b[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int row = base + q * M;
+            const float4 v = tile[row * TP + wslot(c2, row)];
+            a[q] = lo2(v); b[q] = hi2(v);
+        }
+        if (!INV) {
+            dft<R, false>(a);
+            dft<R, false>(b);
+            if (M > 1) apply_twiddles2<R, false>(a, b, twp + j * (R - 1));
+        } else {
+            if (M > 1) apply_twiddles2<R, true>(a, b, twp + j * (R - 1));
+            dft<R, true>(a);
+            dft<R, true>(b);
+        }
+        if (dst_g) {
+            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                if (row < g.sa) stg_stream(gp + q * gstep, pack4(a[q], b[q]));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q * M;
+                tile[row * TP + wslot(c2, row)] = pack4(a[q], b[q]);
+            }
+        }
+    }
+    spim_syncwarp();
+}
+
+template <int R>
+SPIM_DEV void mid_tile_w(int lane, int nlanes, int c0, const FftPlanDev& pl, float4* tile, int dst_g, const GRows& g, const float2* kh) {
+    const int nb = pl.n / R;
+    const long long gs4 = g.stride >> 1;
+    for (int i = lane; i < nb * WP; i += nlanes) {
+        const int c2 = c0 + (i & (WP - 1));
+        const int base = (i >> 1) * R;
+        float2 a[R], b[R];
+        float4 kv[R];
+        const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * gs4 + c2;
+#pragma unroll
+        for (int q = 0; q < R; ++q) kv[q] = ldg_stream(kp + q * gs4);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int row = base + q;
+            const float4 v = tile[row * TP + wslot(c2, row)];
+            a[q] = lo2(v); b[q] = hi2(v);
+        }
+        dft<R, false>(a);
+        dft<R, false>(b);
+#pragma unroll
+        for (int q = 0; q < R; ++q) { a[q] = cmul(a[q], lo2(kv[q])); b[q] = cmul(b[q], hi2(kv[q])); }
+        dft<R, true>(a);
+        dft<R, true>(b);
+        if (dst_g) {
+            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q;
+                if (row < g.sa) stg_stream(gp + q * gs4, pack4(a[q], b[q]));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = base + q;
+                tile[row * TP + wslot(c2, row)] = pack4(a[q], b[q]);
+            }
+        }
+    }
+    spim_syncwarp();
+}
+
+template <bool INV>
+SPIM_DEV void stage_dispatch_w(int lane, int nlanes, int c0, const FftPlanDev& pl, int s, float4* tile, int dst_g, const GRows& g) {
+    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile_w<RR, INV>(lane, nlanes, c0, pl, s, tile, dst_g, g)))
+}
+SPIM_DEV void mid_dispatch_w(int lane, int nlanes, int c0, const FftPlanDev& pl, float4* tile, int dst_g, const GRows& g, const float2* kh) {
+    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile_w<RR>(lane, nlanes, c0, pl, tile, dst_g, g, kh)))
+}
+
+// cooperative async load of tile rows into the rotated layout
+SPIM_DEV void async_rows_w(float4* buf, const float4* gp, long long gs4, int row_lo, int row_hi) {
+#if defined(SPIM_HOST_EMU)
+    for (int row = row_lo; row < row_hi; ++row)
+        for (int c2 = 0; c2 < TP; ++c2) cp_async16(buf + row * TP + wslot(c2, row), gp + (long long)row * gs4 + c2);
+#else
+    const int c2 = threadIdx.x & (TP - 1);
+    const int rstep = blockDim.x >> 3;
+    for (int row = row_lo + (threadIdx.x >> 3); row < row_hi; row += rstep)
+        cp_async16(buf + row * TP + wslot(c2, row), gp + (long long)row * gs4 + c2);
+#endif
+}
+
+struct ColPassW {
+    typedef ColPassParams Params;
+    SPIM_DEV static void warp_work(const Params& p, int lane, int nlanes, int c0, float4* tile, const GRows& g, long long base) {
+        const FftPlanDev& pl = p.plan;
+        const int S = pl.nstages;
+        if (p.mode == COL_FWD) {
+            for (int s = 0; s < S; ++s) stage_dispatch_w<false>(lane, nlanes, c0, pl, s, tile, s == S - 1, g);
+        } else if (p.mode == COL_INV) {
+            for (int s = S - 1; s >= 0; --s) stage_dispatch_w<true>(lane, nlanes, c0, pl, s, tile, s == 0, g);
+        } else {
+            for (int s = 0; s < S - 1; ++s) stage_dispatch_w<false>(lane, nlanes, c0, pl, s, tile, 0, g);
+            mid_dispatch_w(lane, nlanes, c0, pl, tile, S == 1, g, p.khat + base);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch_w<true>(lane, nlanes, c0, pl, s, tile, s == 0, g);
+        }
+    }
+    SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
+        float4* tile = reinterpret_cast<float4*>(tile2);
+        const int P = p.plan.n;
+        long long base;
+        col_tile_base(p, bid, base);
+        GRows g;
+        g.p = p.data + base;
+        g.stride = p.row_stride;
+        g.va = P; g.vb = P; g.sa = p.sa;
+        const long long gs4 = p.row_stride >> 1;
+        const float4* gp = reinterpret_cast<const float4*>(g.p);
+        if (p.va < p.vb) {
+            async_rows_w(tile, gp, gs4, 0, p.va);
+            async_rows_w(tile, gp, gs4, p.vb, P);
+            SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            async_rows_w(tile, gp, gs4, 0, P);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        SPIM_BARRIER();          // the only CTA-wide barrier of the tile
+#if defined(SPIM_HOST_EMU)
+        for (int w = 0; w < TP / WP; ++w) warp_work(p, 0, 1, w * WP, tile, g, base);
+#else
+        const int warp = threadIdx.x >> 5;
+        if (warp < TP / WP) warp_work(p, threadIdx.x & 31, 32, warp * WP, tile, g, base);
+#endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // XFwd: real lines -> half spectrum (R2C via one complex FFT of length Px/2 + split step)
 // Tile = [Px/2 rows][16 lines]; line pair bp of row r lives in float4 slot (bp + r) & 7.
 // ---------------------------------------------------------------------------------------------
