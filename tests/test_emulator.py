@@ -193,3 +193,29 @@ def test_device_query_mirrors_without_gpu(cuda_lib):
     lib = NativeLibraryTools.loadNativeLibrary()
     assert lib is not None and callable(lib.convolution3DfftCUDAInPlace)
     assert NativeLibraryTools.loadNativeLibrary(directory="/nonexistent") is None
+
+
+# ---- randomized sweeps (fixed seeds): ragged shapes, kernels larger than the image, every extension rule ------
+def test_randomized_convolutions(emu_lib):
+    from spim_registration_b200 import native
+    rng = np.random.default_rng(12345)
+    for _ in range(120):
+        shape = tuple(int(rng.integers(1, 24)) for _ in range(3))
+        ks = tuple(int(rng.integers(1, 10)) for _ in range(3))
+        ext = int(rng.integers(0, 5))
+        P.conv_case(emu_lib, shape, ks, ext, seed=int(rng.integers(0, 1 << 30)))
+        if all(k <= s for k, s in zip(ks, shape)):
+            P.legacy_case(emu_lib, shape, ks, seed=int(rng.integers(0, 1 << 30)))
+
+
+def test_randomized_deconvolutions(emu_lib):
+    rng = np.random.default_rng(777)
+    for _ in range(12):
+        shape = tuple(int(rng.integers(5, 16)) for _ in range(3))
+        V = int(rng.integers(1, 5))
+        ks = int(rng.choice([3, 5, 7]))
+        typ = int(rng.integers(0, 4))
+        gen = int(rng.integers(1, 3))
+        P.decon_case(emu_lib, shape, V, ks, typ, gen, int(rng.integers(1, 4)), lam=float(rng.choice([0.0, 0.006, 0.06])),
+                     weight_mode=str(rng.choice(["normalized", "blending", "ones"])), use_weights=bool(rng.integers(0, 2)),
+                     osem_index=int(rng.integers(0, 3)) if gen == 1 else 0, seed=int(rng.integers(0, 1000)))
