@@ -329,3 +329,28 @@ def test_halo_pack_unpack_roundtrip(gpu):
         mask = torch.ones_like(t, dtype=torch.bool)
         mask[r[0]:r[0] + r[3], r[1]:r[1] + r[4], r[2]:r[2] + r[5]] = False
         assert torch.equal(t[mask], before[mask])
+
+
+# ---- randomized sweeps on the GPU (same seeds as the emulator tests) ------------------------------------------
+def test_randomized_convolutions(gpu):
+    rng = np.random.default_rng(12345)
+    for _ in range(120):
+        shape = tuple(int(rng.integers(1, 24)) for _ in range(3))
+        ks = tuple(int(rng.integers(1, 10)) for _ in range(3))
+        ext = int(rng.integers(0, 5))
+        P.conv_case(gpu, shape, ks, ext, seed=int(rng.integers(0, 1 << 30)))
+        if all(k <= s for k, s in zip(ks, shape)):
+            P.legacy_case(gpu, shape, ks, seed=int(rng.integers(0, 1 << 30)))
+
+
+def test_randomized_deconvolutions(gpu):
+    rng = np.random.default_rng(777)
+    for _ in range(12):
+        shape = tuple(int(rng.integers(5, 16)) for _ in range(3))
+        V = int(rng.integers(1, 5))
+        ks = int(rng.choice([3, 5, 7]))
+        typ = int(rng.integers(0, 4))
+        gen = int(rng.integers(1, 3))
+        P.decon_case(gpu, shape, V, ks, typ, gen, int(rng.integers(1, 4)), lam=float(rng.choice([0.0, 0.006, 0.06])),
+                     weight_mode=str(rng.choice(["normalized", "blending", "ones"])), use_weights=bool(rng.integers(0, 2)),
+                     osem_index=int(rng.integers(0, 3)) if gen == 1 else 0, seed=int(rng.integers(0, 1000)))
