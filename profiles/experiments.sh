@@ -1,0 +1,31 @@
+#!/bin/bash
+# A/B matrix of the kernel variants that are in tree behind environment switches (run on the GPU box):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/experiments.sh > gpurun_out/experiments.txt 2>&1'
+# Every line: the switch setting, whole-iteration throughput and the per-kernel CUDA-event averages of bench.py.
+# A variant is only worth adopting if the parity subset below passes with it.
+set -u
+summ='import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=d["roofline_conv_pass"]
+print("  value %.4g  conv %.3f ms  frac %.3f " % (d["value"], c["ms_per_conv"], c["frac"]), {k: round(v["avg_ms"], 3) for k, v in c["per_kernel"].items()})'
+run() {   # run "<env assignments>"
+    echo "== $1"
+    env $1 timeout 60 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "$summ" || echo "  FAILED"
+}
+check() { # parity subset under a variant
+    echo "== parity under: $1"
+    env $1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -k "conv_all_extensions or golden or radix_path or config1 or randomized" 2>&1 | tail -1
+}
+run "SPIM_COLP=2"                                   # default: one-shot cp.async tile staging
+run "SPIM_COLP=2 SPIM_REGCAP=1 SPIM_THREADS_COL=256" # 80 registers, 24 resident warps
+run "SPIM_COLP=2 SPIM_THREADS_COL=160"
+run "SPIM_COLP=3"                                   # TMA tensor-map pipeline, 2 consumer groups
+run "SPIM_COLP=3 SPIM_THREADS_COLT=352"
+run "SPIM_COLP=3 SPIM_TMAP=0"                       # per-row bulk copies (known slow)
+run "SPIM_COLP=4"                                   # warp-private columns
+run "SPIM_COLP=2 SPIM_KSTAGE=1"
+run "SPIM_THREADS_XFWD=128"
+run "SPIM_THREADS_XFWD=256"
+run "SPIM_THREADS_XINV=192"
+check "SPIM_COLP=3"
+check "SPIM_COLP=4"
+check "SPIM_COLP=2 SPIM_REGCAP=1 SPIM_THREADS_COL=256"
