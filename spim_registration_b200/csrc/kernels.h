@@ -120,11 +120,32 @@ SPIM_DEV void apply_twiddles1(float2 (&a)[R], const float2* tw) {
     }
 }
 
+// twiddles of one butterfly, fetched into registers at the very start of the item so that their L1 / L2
+// latency overlaps the shared-memory loads and the butterfly instead of being exposed right before use
+template <int R>
+SPIM_DEV void load_twiddles(float2 (&w)[R], const float2* tw) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) w[p] = spim_ldg(tw + (p - 1));
+}
+template <int R, bool INV>
+SPIM_DEV void mul_twiddles2(float2 (&a)[R], float2 (&b)[R], const float2 (&w)[R]) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) {
+        a[p] = INV ? cmulc(a[p], w[p]) : cmul(a[p], w[p]);
+        b[p] = INV ? cmulc(b[p], w[p]) : cmul(b[p], w[p]);
+    }
+}
+template <int R, bool INV>
+SPIM_DEV void mul_twiddles1(float2 (&a)[R], const float2 (&w)[R]) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) a[p] = INV ? cmulc(a[p], w[p]) : cmul(a[p], w[p]);
+}
+
 // physical float4 slot of column pair c2 in row `row` (x kernels rotate the pairs so that the
 // transposing first / last phases are conflict-free)
 SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
 
-template <int R, bool INV>
+template <int R, bool INV, bool TW>
 SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     const int M = pl.M[s];
     const int L = M * R;
@@ -139,7 +160,8 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
         const int blk = (M == 1) ? m : fastdiv(m, magic);
         const int j = m - blk * M;
         const int base = blk * L + j;
-        float2 a[R], b[R];
+        float2 a[R], b[R], w[R];
+        if (TW) load_twiddles<R>(w, twp + j * (R - 1));
         if (src_g) {
             const float4* gp = reinterpret_cast<const float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
@@ -165,9 +187,9 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
         if (!INV) {
             dft<R, false>(a);
             dft<R, false>(b);
-            if (M > 1) apply_twiddles2<R, false>(a, b, twp + j * (R - 1));
+            if (TW) mul_twiddles2<R, false>(a, b, w);
         } else {
-            if (M > 1) apply_twiddles2<R, true>(a, b, twp + j * (R - 1));
+            if (TW) mul_twiddles2<R, true>(a, b, w);
             dft<R, true>(a);
             dft<R, true>(b);
         }
@@ -267,7 +289,8 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
 
 template <bool INV>
 SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
-    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV>(tg, pl, s, tile, swz, src_g, dst_g, g)))
+    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, true>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+    else { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, false>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
 }
 SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
     SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
@@ -723,7 +746,8 @@ SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* sr
         const int bp = (M == 1) ? i : fastdiv(i, p.magic_m0);
         const int m = i - bp * M;
         const long long so0 = srcoff[2 * bp], so1 = srcoff[2 * bp + 1];
-        float2 a[R], b[R];
+        float2 a[R], b[R], w[R];
+        if (M > 1) load_twiddles<R>(w, twp + m * (R - 1));
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             a[q] = xfwd_pair(p, so0, m + q * M);
@@ -731,7 +755,7 @@ SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* sr
         }
         dft<R, false>(a);
         dft<R, false>(b);
-        if (M > 1) apply_twiddles2<R, false>(a, b, twp + m * (R - 1));
+        if (M > 1) mul_twiddles2<R, false>(a, b, w);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
@@ -974,13 +998,14 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
         const long long d_o = dstoff[b];
         if (d_o < 0) continue;
         const long long a_o = auxoff[b];
-        float2 x1[R], x2[R];
+        float2 x1[R], x2[R], w[R];
+        if (M > 1) load_twiddles<R>(w, twp + m * (R - 1));
 #pragma unroll
         for (int q = 0; q < R; ++q) epi_fetch<EPI, VEC>(p, a_o, d_o, m + q * M, x1[q], x2[q]);
         float2 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = tile2[xelem(b, m + q * M)];
-        if (M > 1) apply_twiddles1<R, true>(a, twp + m * (R - 1));
+        if (M > 1) mul_twiddles1<R, true>(a, w);
         dft<R, true>(a);
         float csum = 0.f, cmax = 0.f;
 #pragma unroll
