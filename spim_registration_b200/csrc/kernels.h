@@ -828,29 +828,49 @@ struct XFwd {
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
         for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
-        // split step on line pairs (factor 1/2 folded into the kernel scale)
+        // split step on line pairs (factor 1/2 folded into the kernel scale).  Two items per trip: the dependent
+        // chain pos[] -> shared-memory row -> arithmetic of one item overlaps the other's
         const int nk = p.nk;
-        SPIM_FOR_ITEMS(i, nk * TP) {
-            const int bp = fastdiv(i, p.magic_nk);
-            const int k = i - bp * nk;
-            const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
-            if (d0 < 0 && d1 < 0) continue;
-            const int km = N2 - k;
-            const int rk = spim_ldg(p.pos + k);
-            const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
-            const float4 zk = tile[rk * TP + ((bp + rk) & (TP - 1))];
-            const float4 zm = tile[rm * TP + ((bp + rm) & (TP - 1))];
-            const float2 w = spim_ldg(p.wx + k);
-            float2 xk, xm;
-            if (d0 >= 0) {
-                split_fwd(lo2(zk), lo2(zm), w, xk, xm);
-                p.spec[d0 + k] = xk;
-                if (km != k) p.spec[d0 + km] = xm;
+        const int total = nk * TP;
+        for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
+            int bpv[2], kv[2], rk[2], rm[2];
+            float2 wv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * SPIM_NTHREADS;
+                bpv[u] = -1; kv[u] = 0; rk[u] = 0; rm[u] = 0; wv[u] = make_float2(1.f, 0.f);
+                if (i < total) {
+                    const int bp = fastdiv(i, p.magic_nk);
+                    const int k = i - bp * nk;
+                    bpv[u] = bp; kv[u] = k;
+                    rk[u] = spim_ldg(p.pos + k);
+                    rm[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
+                    wv[u] = spim_ldg(p.wx + k);
+                }
             }
-            if (d1 >= 0) {
-                split_fwd(hi2(zk), hi2(zm), w, xk, xm);
-                p.spec[d1 + k] = xk;
-                if (km != k) p.spec[d1 + km] = xm;
+            float4 zkv[2], zmv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int bp = bpv[u] < 0 ? 0 : bpv[u];
+                zkv[u] = tile[rk[u] * TP + ((bp + rk[u]) & (TP - 1))];
+                zmv[u] = tile[rm[u] * TP + ((bp + rm[u]) & (TP - 1))];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (bpv[u] < 0) continue;
+                const int bp = bpv[u], k = kv[u], km = N2 - k;
+                const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
+                float2 xk, xm;
+                if (d0 >= 0) {
+                    split_fwd(lo2(zkv[u]), lo2(zmv[u]), wv[u], xk, xm);
+                    p.spec[d0 + k] = xk;
+                    if (km != k) p.spec[d0 + km] = xm;
+                }
+                if (d1 >= 0) {
+                    split_fwd(hi2(zkv[u]), hi2(zmv[u]), wv[u], xk, xm);
+                    p.spec[d1 + k] = xk;
+                    if (km != k) p.spec[d1 + km] = xm;
+                }
             }
         }
         // zero the pad columns [N2+1, pitch)
