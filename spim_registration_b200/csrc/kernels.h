@@ -1099,13 +1099,14 @@ struct XInvT {
         const int nk = p.nk;
         const int total = nk * TP;
         for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
-            float2 A0[2], B0[2], A1[2], B1[2];
-            int bpv[2], kk[2];
+            float2 A0[2], B0[2], A1[2], B1[2], wv[2];
+            int bpv[2], kk[2], rkv[2], rmv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = i0 + u * SPIM_NTHREADS;
                 A0[u] = B0[u] = A1[u] = B1[u] = make_float2(0.f, 0.f);
-                bpv[u] = -1; kk[u] = 0;
+                wv[u] = make_float2(1.f, 0.f);
+                bpv[u] = -1; kk[u] = 0; rkv[u] = 0; rmv[u] = 0;
                 if (i < total) {
                     const int bp = fastdiv(i, p.magic_nk);
                     const int k = i - bp * nk;
@@ -1113,20 +1114,23 @@ struct XInvT {
                     const long long s0 = srcoff[2 * bp], s1 = srcoff[2 * bp + 1];
                     if (s0 >= 0) { A0[u] = ldg_stream(p.spec + s0 + k); B0[u] = ldg_stream(p.spec + s0 + (N2 - k)); }
                     if (s1 >= 0) { A1[u] = ldg_stream(p.spec + s1 + k); B1[u] = ldg_stream(p.spec + s1 + (N2 - k)); }
+                    // table lookups issued together with the spectrum loads, not right before their use
+                    wv[u] = spim_ldg(p.wx + k);
+                    rkv[u] = spim_ldg(p.pos + k);
+                    rmv[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
                 }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (bpv[u] < 0) continue;
                 const int bp = bpv[u], k = kk[u], km = N2 - k;
-                const float2 w = spim_ldg(p.wx + k);
                 float2 zk0, zm0, zk1, zm1;
-                split_inv(A0[u], B0[u], w, zk0, zm0);
-                split_inv(A1[u], B1[u], w, zk1, zm1);
-                const int rk = spim_ldg(p.pos + k);
+                split_inv(A0[u], B0[u], wv[u], zk0, zm0);
+                split_inv(A1[u], B1[u], wv[u], zk1, zm1);
+                const int rk = rkv[u];
                 tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
                 if (k != 0 && km != k) {
-                    const int rm = spim_ldg(p.pos + km);
+                    const int rm = rmv[u];
                     tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
                 }
             }
