@@ -351,6 +351,10 @@ public:
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
             if (use_regcap()) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            else if (smem <= 40 * 1024 && threads_col() <= 128 && !p.kstage)
+                // small tiles (z pass of the 512x512x256 brick: 36 KB): registers, not shared memory, limit the resident
+                // blocks -- keep 5 blocks of 128 threads per SM (<= 102 registers) as in the measured round-1 binary
+                rt::launch<ColPass, 128, 5>(p, grid, threads_col(), smem, st);
             else rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
         } else {
             rt::launch<ColPass>(p, grid, threads_col(), smem, st);
