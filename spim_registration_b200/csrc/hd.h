@@ -44,6 +44,12 @@ static inline float spim_fmul_rn(float a, float b) { volatile float r = a * b; r
 static inline float spim_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float spim_fsqrt_rn(float a) { volatile float r = sqrtf(a); return r; }
 static inline float spim_fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+// un-fused fp64 ops (the Java double arithmetic of the fusion pre-step has no FMA contraction)
+static inline double spim_dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double spim_dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double spim_dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double spim_ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline float spim_d2f_rn(double a) { volatile float r = (float)a; return r; }
 
 #else
 
@@ -129,5 +135,11 @@ __device__ __forceinline__ float spim_fmul_rn(float a, float b) { return __fmul_
 __device__ __forceinline__ float spim_fdiv_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float spim_fsqrt_rn(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ float spim_fmaf_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// un-fused fp64 ops (the Java double arithmetic of the fusion pre-step has no FMA contraction)
+__device__ __forceinline__ double spim_dadd_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double spim_dsub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double spim_dmul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double spim_ddiv_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float spim_d2f_rn(double a) { return __double2float_rn(a); }
 
 #endif

@@ -39,7 +39,10 @@ struct ScaleClampK {   // adjustOSEMspeedup: w <- min(1, w * (float)osem)
         for (long long base = (long long)bid * kChunk; base < p.n; base += (long long)p.nblocks * kChunk) {
             SPIM_FOR_ITEMS(i, kChunk) {
                 const long long idx = base + i;
-                if (idx < p.n) p.p[idx] = fminf(1.f, spim_fmul_rn(p.p[idx], p.f));
+                if (idx < p.n) {
+                    const float x = spim_fmul_rn(p.p[idx], p.f);
+                    p.p[idx] = (x < 1.f || x != x) ? x : 1.f;     // Math.min(1, x): NaN stays NaN (fminf would drop it)
+                }
             }
         }
     }
@@ -221,6 +224,8 @@ inline int ew_blocks(long long n) {
 
 }  // namespace spim
 
+#include "fusion.h"
+
 // ================================================================================================
 // error plumbing
 // ================================================================================================
@@ -383,6 +388,15 @@ struct mvd_session {
     double t_ms[8] = {0};
     long long t_cnt[8] = {0};
     std::vector<std::unique_ptr<ConvWorkspace>> small;   // PSF-sized plans for kernel building
+    // fusion pre-step (include/spim_fusion.h)
+    float* d_stack = nullptr;  // raw stack of the view being transformed
+    size_t stack_cap = 0;
+    int stack_dims[3] = {0, 0, 0};
+    double* d_lut = nullptr;   // blending cosine table
+    float* d_sumw = nullptr;   // virtual weights: sum image of WeightNormalizer.ComputeSumImage
+    bool virtual_weights = false, wn_valid = false;
+    int wn_min = 0;
+    double wn_avg = 0.0;
 
     int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
     int conv2_ext() const { return prm.conv2_ext >= 0 ? prm.conv2_ext : (prm.generation == 2 ? EXT_CONSTANT : EXT_MIRROR_SINGLE); }
@@ -487,7 +501,18 @@ struct mvd_session {
 
     void apply_avg(double avg_, double osem_) {
         avg = avg_; osem = osem_;
-        if (osem != 1.0) {
+        if (virtual_weights && d_sumw) {
+            // NormalizingRandomAccess.get(): w <- (float)min(1, (w / sumWeights) * osem), materialised once
+            WeightNormParams p;
+            memset(&p, 0, sizeof(p));
+            p.v.nviews = prm.num_views;
+            for (int v = 0; v < prm.num_views; ++v) p.v.w[v] = d_w[v];
+            p.n = N; p.mode = 2; p.sumw = d_sumw; p.osem = osem; p.nportions = 0; p.nblocks = ew_blocks(N);
+            rt::launch<WeightNormK>(p, p.nblocks, kThreads, 16, stream);
+            rt::stream_sync(stream);
+            rt::dfree(d_sumw); d_sumw = nullptr; dev_bytes -= (long long)N * (long long)sizeof(float);
+            virtual_weights = false;
+        } else if (osem != 1.0) {
             for (int v = 0; v < prm.num_views; ++v) {
                 if (!d_w[v]) {   // constant-1 weight: min(1, 1*osem) = 1 for osem >= 1; materialise otherwise
                     if (osem >= 1.0) continue;
@@ -600,6 +625,7 @@ void mvd_session_destroy(mvd_session* s) {
         for (auto p : s->d_kh2) rt::dfree(p);
         rt::dfree(s->d_psi); rt::dfree(s->d_tmp);
         rt::dfree(s->d_stat_sum); rt::dfree(s->d_stat_max);
+        rt::dfree(s->d_stack); rt::dfree(s->d_lut); rt::dfree(s->d_sumw);
         if (s->plan_ok) s->plan.destroy();
         rt::stream_destroy(s->stream);
     } catch (...) {}
@@ -680,6 +706,11 @@ int mvd_init(mvd_session* s) {
     if (s->prm.generation == 1) {
         if (s->prm.osem_index == 1) osem = std::max(1.0, (double)mn);
         else if (s->prm.osem_index == 2) osem = std::max(1.0, av);
+    } else if (s->wn_valid) {
+        // ProcessForDeconvolution.java:346-358: overlap statistics of the WeightNormalizer, each max(1, .)
+        s->min_overlap = s->wn_min; s->avg_overlap = s->wn_avg;
+        if (s->prm.osem_index == 1) osem = (double)std::max(1, s->wn_min);
+        else if (s->prm.osem_index == 2) osem = std::max(1.0, s->wn_avg);
     }
     s->apply_avg(avg, osem);
     return 0;
@@ -1091,3 +1122,5 @@ float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim
 }
 
 }  // extern "C"
+
+#include "fusion_api.h"

@@ -74,6 +74,26 @@ SESSION_SYMBOLS = (
     "mvd_set_avg", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
 )
 
+#: include/spim_fusion.h
+FUSION_SYMBOLS = (
+    "mvd_load_stack", "mvd_transform_view", "mvd_set_psf", "mvd_normalize_weights", "mvd_get_view", "mvd_extract_psf",
+    "mvd_transform_psf_size", "mvd_transform_psf", "mvd_blending_lookup",
+)
+
+
+class MvdTransform(C.Structure):
+    """``mvd_transform`` of include/spim_fusion.h."""
+    _fields_ = [
+        ("struct_size", C.c_int),
+        ("inverse", C.c_double * 12),
+        ("offset", C.c_longlong * 3),
+        ("want_image", C.c_int),
+        ("want_weight", C.c_int),
+        ("border", C.c_float * 3),
+        ("range", C.c_float * 3),
+        ("reserved", C.c_int * 8),
+    ]
+
 
 def default_library_path() -> str:
     env = os.environ.get("SPIM_B200_LIBRARY")
@@ -158,6 +178,26 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_last_error.restype = C.c_char_p
     lib.mvd_version.argtypes = []
     lib.mvd_version.restype = C.c_char_p
+
+    T = C.POINTER(MvdTransform)
+    lib.mvd_load_stack.argtypes = [S, C.c_void_p, c_int_p, C.c_int]
+    lib.mvd_load_stack.restype = C.c_int
+    lib.mvd_transform_view.argtypes = [S, C.c_int, T]
+    lib.mvd_transform_view.restype = C.c_int
+    lib.mvd_set_psf.argtypes = [S, C.c_int, C.c_void_p, c_int_p]
+    lib.mvd_set_psf.restype = C.c_int
+    lib.mvd_normalize_weights.argtypes = [S, C.c_int, C.c_int, c_int_p, c_double_p]
+    lib.mvd_normalize_weights.restype = C.c_int
+    lib.mvd_get_view.argtypes = [S, C.c_int, C.c_int, C.c_void_p]
+    lib.mvd_get_view.restype = C.c_int
+    lib.mvd_extract_psf.argtypes = [S, C.c_int, c_double_p, c_int_p, C.c_int, C.c_void_p]
+    lib.mvd_extract_psf.restype = C.c_int
+    lib.mvd_transform_psf_size.argtypes = [c_int_p, c_double_p, c_int_p, c_double_p]
+    lib.mvd_transform_psf_size.restype = C.c_int
+    lib.mvd_transform_psf.argtypes = [C.c_void_p, c_int_p, c_double_p, c_double_p, C.c_void_p, c_int_p, C.c_int]
+    lib.mvd_transform_psf.restype = C.c_int
+    lib.mvd_blending_lookup.argtypes = [c_double_p]
+    lib.mvd_blending_lookup.restype = C.c_int
 
 
 _LIB_CACHE = {}
