@@ -74,6 +74,12 @@ void mvd_session_destroy(mvd_session* s);
 int mvd_set_view(mvd_session* s, int view, const float* img, const float* weight,
                  const float* psf, const int psf_dims[3]);
 
+/* The same for volumes handed over in cells (imglib2 CellImg) or larger than Java's 2^31-element arrays:
+ * upload the box [lo, lo + ext) (z, y, x) of the view's image (which = 0) or weight (which = 1) from a tightly
+ * packed host buffer.  The first call for a buffer creates it zero-filled; the PSF is set with mvd_set_psf
+ * (spim_fusion.h) or a previous mvd_set_view. */
+int mvd_upload_region(mvd_session* s, int view, int which, const float* data, const int lo[3], const int ext[3]);
+
 /* views.init(iterationType) + psi initialisation + OSEM clamp
  * (BayesMVDeconvolution.java:91-117, MVDeconvolution.java:114-148). */
 int mvd_init(mvd_session* s);

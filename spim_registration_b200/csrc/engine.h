@@ -135,6 +135,14 @@ inline int env_int(const char* name, int dflt) {
 }
 inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); return t; }
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
+// Column tiles larger than a third of the shared memory leave room for only two / one block per SM: scale the block
+// so that ~384 threads stay resident (2 x 192, 1 x 384).  SPIM_THREADS_COL, when set, wins.
+inline int threads_col_for(size_t smem_bytes, size_t smem_limit) {
+    static int user = env_int("SPIM_THREADS_COL", 0);
+    if (user > 0) return user;
+    const size_t blocks = smem_limit / (smem_bytes + 1024);   // 1 KB per block is reserved by the driver
+    return blocks >= 3 ? 128 : (blocks == 2 ? 192 : 384);
+}
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
 inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
 // SPIM_REGCAP=1 (experiment): run the column pass from an instantiation capped at 85 registers (3 x 256 threads per SM)
@@ -355,7 +363,12 @@ public:
                 // small tiles (z pass of the 512x512x256 brick: 36 KB): registers, not shared memory, limit the resident
                 // blocks -- keep 5 blocks of 128 threads per SM (<= 102 registers) as in the measured round-1 binary
                 rt::launch<ColPass, 128, 5>(p, grid, threads_col(), smem, st);
-            else rt::launch<ColPass>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            else {
+                const size_t sm = (p.kstage ? 2 : 1) * smem;
+                const int T = threads_col_for(sm, lim);
+                if (T > 256) rt::launch<ColPass, 384>(p, grid, T, sm, st);     // one 1080-row tile per SM
+                else rt::launch<ColPass>(p, grid, T, sm, st);
+            }
         } else {
             rt::launch<ColPass>(p, grid, threads_col(), smem, st);
         }

@@ -25,6 +25,13 @@ inline void h2d(void* d, const void* h, size_t n, Stream) { memcpy(d, h, n); }
 inline void d2h(void* h, const void* d, size_t n, Stream) { memcpy(h, d, n); }
 inline void d2d(void* d, const void* s, size_t n, Stream) { memmove(d, s, n); }
 inline void dzero(void* d, size_t n, Stream) { memset(d, 0, n); }
+// copy a host box [ext] (tightly packed floats) into a device volume [ddims] at offset lo; all triples are (z, y, x)
+inline void h2d_box(float* d, const int ddims[3], const int lo[3], const float* h, const int ext[3], Stream) {
+    for (int z = 0; z < ext[0]; ++z)
+        for (int y = 0; y < ext[1]; ++y)
+            memcpy(d + ((size_t)(z + lo[0]) * ddims[1] + (y + lo[1])) * ddims[2] + lo[2],
+                   h + ((size_t)z * ext[1] + y) * ext[2], (size_t)ext[2] * sizeof(float));
+}
 inline Stream stream_create() { return 0; }
 inline void stream_destroy(Stream) {}
 inline void stream_sync(Stream) {}
@@ -71,6 +78,17 @@ inline void h2d(void* d, const void* h, size_t n, Stream s) { SPIM_CUDA_CHECK(cu
 inline void d2h(void* h, const void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 inline void d2d(void* d, const void* s_, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
 inline void dzero(void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemsetAsync(d, 0, n, s)); }
+// copy a host box [ext] (tightly packed floats) into a device volume [ddims] at offset lo; all triples are (z, y, x)
+inline void h2d_box(float* d, const int ddims[3], const int lo[3], const float* h, const int ext[3], Stream s) {
+    cudaMemcpy3DParms q;
+    memset(&q, 0, sizeof(q));
+    q.srcPtr = make_cudaPitchedPtr(const_cast<float*>(h), (size_t)ext[2] * sizeof(float), (size_t)ext[2], (size_t)ext[1]);
+    q.dstPtr = make_cudaPitchedPtr(d, (size_t)ddims[2] * sizeof(float), (size_t)ddims[2], (size_t)ddims[1]);
+    q.dstPos = make_cudaPos((size_t)lo[2] * sizeof(float), (size_t)lo[1], (size_t)lo[0]);
+    q.extent = make_cudaExtent((size_t)ext[2] * sizeof(float), (size_t)ext[1], (size_t)ext[0]);
+    q.kind = cudaMemcpyHostToDevice;
+    SPIM_CUDA_CHECK(cudaMemcpy3DAsync(&q, s));
+}
 inline Stream stream_create() { Stream s; SPIM_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
 inline void stream_destroy(Stream s) { cudaStreamDestroy(s); }
 inline void stream_sync(Stream s) { SPIM_CUDA_CHECK(cudaStreamSynchronize(s)); }

@@ -656,6 +656,27 @@ int mvd_set_view(mvd_session* s, int v, const float* img, const float* weight, c
     SPIM_API_END
 }
 
+int mvd_upload_region(mvd_session* s, int view, int which, const float* data, const int lo[3], const int ext[3]) {
+    SPIM_API_BEGIN
+    if (!s || !data || !lo || !ext) return fail("mvd_upload_region: null argument");
+    if (view < 0 || view >= s->prm.num_views) return fail("mvd_upload_region: view index out of range");
+    if (which != 0 && which != 1) return fail("mvd_upload_region: which must be 0 (image) or 1 (weight)");
+    for (int d = 0; d < 3; ++d)
+        if (lo[d] < 0 || ext[d] < 1 || (long long)lo[d] + ext[d] > s->n[d]) return fail("mvd_upload_region: region out of range");
+    rt::set_device(s->prm.device);
+    float*& dst = which == 0 ? s->d_img[view] : s->d_w[view];
+    if (!dst) {
+        // a freshly created buffer starts as "no data" (image 0) / "no contribution" (weight 0)
+        dst = (float*)s->dalloc((size_t)s->N * sizeof(float));
+        rt::dzero(dst, (size_t)s->N * sizeof(float), s->stream);
+    }
+    rt::h2d_box(dst, s->n, lo, data, ext, s->stream);
+    rt::stream_sync(s->stream);
+    s->inited = false;
+    return 0;
+    SPIM_API_END
+}
+
 static int session_prepare(mvd_session* s) {
     const int V = s->prm.num_views;
     for (int v = 0; v < V; ++v) if (!s->d_img[v] || s->psf[v].v.empty()) return fail("mvd_init: view " + std::to_string(v) + " not set");

@@ -103,6 +103,12 @@ class Session:
                                                      C.c_void_p(weight_ptr) if weight_ptr else None,
                                                      k.ctypes.data, native.int3(k.shape)), "mvd_set_view")
 
+    def upload_region(self, v: int, which: int, data: np.ndarray, lo: Sequence[int]):
+        """Upload one cell ``data`` ([z, y, x]) of the view's image (which = 0) / weight (which = 1) at offset ``lo``."""
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        native.check(self.lib, self.lib.mvd_upload_region(self._h, int(v), int(which), a.ctypes.data, native.int3(lo),
+                                                          native.int3(a.shape)), "mvd_upload_region")
+
     def init(self):
         native.check(self.lib, self.lib.mvd_init(self._h), "mvd_init")
 

@@ -4,6 +4,7 @@ the oracle on the same seeded inputs."""
 import os
 
 import numpy as np
+import pytest
 
 from oracle import mvdecon_oracle as O
 from spim_registration_b200 import native, synthetic
@@ -130,3 +131,27 @@ def golden_conv_case(lib):
     lib.convolution3DfftCUDAInPlace(got.ctypes.data_as(native.c_float_p), native.int3(got.shape),
                                     k.ctypes.data_as(native.c_float_p), native.int3(k.shape), 0)
     assert np.abs(got - d["circular"]).max() / np.abs(d["circular"]).max() < TOL_CONV
+
+
+def cells_case(lib, shape=(10, 12, 14), cell=(4, 5, 6), V=2, ks=3):
+    """Views handed over cell by cell (mvd_upload_region, the CellImg / > 2^31-element path) give bit-identical
+    device buffers -- and therefore a bit-identical deconvolution -- to whole-array uploads."""
+    from spim_registration_b200 import fusion
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, ks, kind="beads")
+    whole, *_ = run_session(lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 2)
+    with Session(shape, V, O.EFFICIENT_BAYESIAN, generation=2, lib=lib) as s:
+        for v in range(V):
+            for z in range(0, shape[0], cell[0]):
+                for y in range(0, shape[1], cell[1]):
+                    for x in range(0, shape[2], cell[2]):
+                        sl = (slice(z, z + cell[0]), slice(y, y + cell[1]), slice(x, x + cell[2]))
+                        s.upload_region(v, 0, imgs[v][sl], (z, y, x))
+                        s.upload_region(v, 1, ws[v][sl], (z, y, x))
+            fusion.set_psf(s, v, psfs[v])
+            assert np.array_equal(fusion.get_view(s, v, 0), imgs[v]) and np.array_equal(fusion.get_view(s, v, 1), ws[v])
+        with pytest.raises(native.NativeError, match="out of range"):
+            s.upload_region(0, 0, np.zeros((2, 2, 2), np.float32), (shape[0] - 1, 0, 0))
+        s.init()
+        s.run(2)
+        s.finish()
+        assert np.array_equal(s.get_psi(), whole)

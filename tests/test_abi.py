@@ -24,10 +24,11 @@ def test_headers_and_binding_agree():
     session = declared_symbols("spim_mvdecon.h")
     assert sorted(native.LEGACY_SYMBOLS) == legacy
     assert sorted(native.SESSION_SYMBOLS) == session
+    assert sorted(native.FUSION_SYMBOLS) == declared_symbols("spim_fusion.h")
 
 
 def test_library_exports_every_declared_symbol(cuda_lib):
-    for name in declared_symbols("spim_fftconv.h") + declared_symbols("spim_mvdecon.h"):
+    for name in declared_symbols("spim_fftconv.h") + declared_symbols("spim_mvdecon.h") + declared_symbols("spim_fusion.h"):
         assert hasattr(cuda_lib, name), name
 
 
@@ -93,3 +94,23 @@ def test_params_default_values(cuda_lib):
     assert p.struct_size == ctypes.sizeof(native.MvdParams)
     assert p.generation == 2 and p.iteration_type == 2 and abs(p.lambda_ - 0.006) < 1e-12
     assert abs(p.min_value - 1e-4) < 1e-10 and p.conv1_ext == -1 and p.conv2_ext == -1
+
+
+def test_host_only_fusion_helpers_work_without_gpu(cuda_lib):
+    # geometry of ExtractPSF.transformPSF and the blending table are host logic: no device needed
+    lut = (ctypes.c_double * 1001)()
+    assert cuda_lib.mvd_blending_lookup(lut) == 0 and lut[0] == 0.0 and abs(lut[1000] - 1.0) < 1e-12
+    od, off = (ctypes.c_int * 3)(), (ctypes.c_double * 3)()
+    scal = (ctypes.c_double * 12)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 2.5, 0)
+    assert cuda_lib.mvd_transform_psf_size(native.int3((5, 7, 9)), scal, od, off) == 0
+    assert tuple(od) == (11, 7, 9) and tuple(off) == (0.0, 0.0, 0.0)
+
+
+def test_fusion_compute_fails_loudly_without_gpu(cuda_lib):
+    if cuda_lib.getNumDevicesCUDA() > 0:
+        pytest.skip("a GPU is present")
+    psf = np.ones((3, 3, 3), np.float32)
+    ident = (ctypes.c_double * 12)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0)
+    out = np.zeros((3, 3, 3), np.float32)
+    rc = cuda_lib.mvd_transform_psf(psf.ctypes.data, native.int3((3, 3, 3)), ident, ident, out.ctypes.data, native.int3((3, 3, 3)), 0)
+    assert rc != 0 and b"no CUDA device" in cuda_lib.mvd_last_error()

@@ -66,6 +66,10 @@ def test_gen1_osem_from_overlap(emu_lib):
     P.decon_case(emu_lib, (10, 12, 14), 3, 3, O.OPTIMIZATION_II, 1, 2, osem=2.0, osem_index=0)
 
 
+def test_views_uploaded_in_cells(emu_lib):
+    P.cells_case(emu_lib)
+
+
 def test_exact_tikhonov_switch(emu_lib):
     P.exact_tikhonov_case(emu_lib)
 
