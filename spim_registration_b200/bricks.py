@@ -183,6 +183,10 @@ class BrickRunner:
         self._recv_flat = torch.empty(max(1, sum(sizes_r)), dtype=t.dtype, device=t.device)
         self._send_off = np.concatenate([[0], np.cumsum(sizes_s)]).astype(int)
         self._recv_off = np.concatenate([[0], np.cumsum(sizes_r)]).astype(int)
+        # sides with a neighbour read the exchanged halo; all other sides (volume faces) use the out-of-bounds rule
+        lo_mask = sum(1 << d for d in range(3) if self._neighbour(d, -1) is not None)
+        hi_mask = sum(1 << d for d in range(3) if self._neighbour(d, +1) is not None)
+        self.session.set_halo_mask(lo_mask, hi_mask)
         self.use_pack = os.environ.get("SPIM_BRICK_PACK", "1") != "0"
         if self.use_pack and plan and self.dist is not None:
             self._verify_pack_path()
@@ -224,9 +228,6 @@ class BrickRunner:
         if not self.cpu:
             import torch
             torch.cuda.synchronize()
-        lo_mask = sum(1 << d for d in range(3) if self._neighbour(d, -1) is not None)
-        hi_mask = sum(1 << d for d in range(3) if self._neighbour(d, +1) is not None)
-        self.session.set_halo_mask(lo_mask, hi_mask)
 
     def exchange(self, which: int):
         """Refresh the halo of buffer ``which`` (0 = psi, 1 = ratio) from all neighbours in ONE batch of

@@ -19,8 +19,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, brick, V, ks, typ, gen, iters, emu_path, outdir):
+def _worker(rank, world, port, brick, V, ks, typ, gen, iters, emu_path, outdir, pack="1"):
     sys.path.insert(0, ROOT)
+    os.environ["SPIM_BRICK_PACK"] = pack
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch
@@ -49,8 +50,8 @@ def _worker(rank, world, port, brick, V, ks, typ, gen, iters, emu_path, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,gen,typ", [(2, 2, 2), (4, 2, 0), (8, 1, 1)])
-def test_bricks_match_whole_volume_oracle(tmp_path, world, gen, typ):
+@pytest.mark.parametrize("world,gen,typ,pack", [(2, 2, 2, "1"), (4, 2, 0, "1"), (8, 1, 1, "1"), (2, 2, 2, "0"), (4, 1, 3, "0")])
+def test_bricks_match_whole_volume_oracle(tmp_path, world, gen, typ, pack):
     import torch.multiprocessing as mp
     import __graft_entry__ as g
     from oracle import mvdecon_oracle as O
@@ -58,7 +59,8 @@ def test_bricks_match_whole_volume_oracle(tmp_path, world, gen, typ):
     emu = g.build_emulator()
     brick, V, ks, iters = (8, 9, 10), 2, 5, 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, brick, V, ks, typ, gen, iters, emu, str(tmp_path)), nprocs=world, join=True)
+    # pack = "0": the slab-copy exchange (the fallback of the single-launch pack / unpack path) must be just as correct
+    mp.spawn(_worker, args=(world, port, brick, V, ks, typ, gen, iters, emu, str(tmp_path), pack), nprocs=world, join=True)
     grid = bricks.grid_for(world)
     gshape = tuple(brick[d] * grid[d] for d in range(3))
     _, imgs, ws, psfs = synthetic.make_dataset(gshape, V, ks, kind="beads", seed=3)
