@@ -134,6 +134,38 @@ class BrickRunner:
         self._plan_exchange()
 
     # ------------------------------------------------------------------------------------------
+    def fuse_stacks(self, stacks, transforms, bb_min, blending_border, blending_range, virtual: bool = True,
+                    psfs=None, normalize_stacks: bool = True):
+        """Device-side fusion pre-step for this rank's brick (spim_fusion.h; ProcessForDeconvolution.java:180-366):
+        every rank loads the raw stacks and resamples them into ITS brick of the bounding box -- the brick origin is
+        simply added to the bounding-box offset, the per-voxel arithmetic is position-independent -- then the weights are
+        normalised voxel-locally.  Returns the global (min, avg) number of overlapping views: counts are all-reduced, so
+        avg is the reference's value for a single portion (Threads.numThreads() * 2 == 1)."""
+        from . import fusion
+        s = self.session
+        n = s.dims
+        origin_xyz = [self.coords[2] * n[2], self.coords[1] * n[1], self.coords[0] * n[0]]
+        off = [int(bb_min[d]) + origin_xyz[d] for d in range(3)]
+        for v in range(self.num_views):
+            st = np.ascontiguousarray(stacks[v], dtype=np.float32)
+            fusion.load_stack(s, st, normalize=normalize_stacks)
+            bl = fusion.Blending(st.shape[::-1], blending_border, blending_range)
+            fusion.transform_view(s, v, transforms[v], off, bl)
+            if psfs is not None:
+                fusion.set_psf(s, v, psfs[v])
+        fusion.load_stack(s, None)
+        mn, avg = fusion.normalize_weights(s, virtual=virtual, num_portions=1)
+        if self.dist is not None and self.world > 1:
+            import torch
+            dev = "cpu" if self.cpu else torch.device("cuda", self.device)
+            nvox = float(np.prod(n))
+            t = torch.tensor([avg * nvox, nvox], dtype=torch.float64, device=dev)      # avg * nvox = exact integer count
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            m = torch.tensor([float(mn)], dtype=torch.float64, device=dev)
+            self.dist.all_reduce(m, op=self.dist.ReduceOp.MIN)
+            mn, avg = int(m.item()), float(t[0].item() / t[1].item())
+        return mn, avg
+
     def _neighbour(self, axis: int, step: int) -> Optional[int]:
         c = list(self.coords)
         c[axis] += step
@@ -202,11 +234,15 @@ class BrickRunner:
         filled = t.clone()
         ok = True
         try:
+            # torch fills the buffer on ITS current stream; the exchange runs on the session's (non-blocking) stream:
+            # synchronise the device between the two, or the exchange may pack the buffer before it is filled
+            self._sync_stream()
             self.use_pack = False
             self.exchange(1)
             self._sync_stream()
             want = t.clone()
             t.copy_(filled)
+            self._sync_stream()
             self.use_pack = True
             self.exchange(1)
             self._sync_stream()

@@ -92,3 +92,62 @@ def test_grid_and_rank_mapping():
             assert bricks.coords_rank(c, g) == r
             seen.add(c)
         assert len(seen) == w
+
+
+def _fusion_worker(rank, world, port, brick, V, emu_path, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spim_registration_b200 import native, synthetic, bricks
+    import fusion_cases as FC
+    lib = native.load_library(emu_path)
+    grid = bricks.grid_for(world)
+    gshape = tuple(brick[d] * grid[d] for d in range(3))
+    stacks, models = FC.make_view_set(V, (8, 18, 22), gshape, seed=5)
+    psfs = synthetic.make_psfs(V, 3)
+    r = bricks.BrickRunner(brick, V, 3, generation=2, lam=0.006, rank=rank, world=world, grid=grid, dist=dist, lib=lib, cpu=True)
+    mn, avg = r.fuse_stacks(stacks, models, (-1, 0, 1), (1, 1, 0), (4, 4, 2), virtual=True, psfs=psfs)
+    r.init()
+    r.run(2, stats=True)
+    r.finish()
+    c = bricks.rank_coords(rank, grid)
+    sl = tuple(slice(c[d] * brick[d], (c[d] + 1) * brick[d]) for d in range(3))
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), psi=r.get_psi(), sl=np.array([[x.start, x.stop] for x in sl]), mn=mn, avg=avg)
+    r.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bricks_fuse_raw_stacks_then_deconvolve(tmp_path):
+    """Raw stacks -> per-brick device-side transformation + weights -> brick deconvolution (world 4) equals the
+    single-volume pipeline of the oracle."""
+    import torch.multiprocessing as mp
+    import __graft_entry__ as g
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fusion_cases as FC
+    from oracle import fusion_oracle as F
+    from oracle import mvdecon_oracle as O
+    from spim_registration_b200 import synthetic, bricks
+    emu = g.build_emulator()
+    world, brick, V = 4, (12, 8, 10), 2
+    mp.spawn(_fusion_worker, args=(world, _free_port(), brick, V, emu, str(tmp_path)), nprocs=world, join=True)
+    grid = bricks.grid_for(world)
+    gshape = tuple(brick[d] * grid[d] for d in range(3))
+    stacks, models = FC.make_view_set(V, (8, 18, 22), gshape, seed=5)
+    imgs, ws = FC.oracle_views(stacks, models, gshape, (-1, 0, 1), (1, 1, 0), (4, 4, 2))
+    sumw, mn, avg = F.weight_normalizer_virtual(ws, 1)
+    wv = [F.normalizing_access(w, sumw, 1.0) for w in ws]
+    psfs = synthetic.make_psfs(V, 3)
+    ref = O.deconvolve(imgs, wv, psfs, O.DeconParams(iteration_type=3, num_iterations=2, lam=0.006, gen=2))
+    psi = np.zeros(gshape, np.float32)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        psi[tuple(slice(a, b) for a, b in d["sl"])] = d["psi"]
+        assert int(d["mn"]) == mn and abs(float(d["avg"]) - avg) < 1e-12
+    per, l2 = O.parity_errors(psi, ref.psi)
+    assert per <= 1e-3 and l2 <= 1e-4, (per, l2)
