@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -205,6 +206,24 @@ class ExtractPSF:
         native.check(lib, lib.mvd_transform_psf(a.ctypes.data, native.int3(a.shape), m, _dbl12(model.inverse().getRowPackedCopy()),
                                                 out.ctypes.data, od, device), "mvd_transform_psf")
         return out
+
+    @classmethod
+    def loadAndTransformPSFs(cls, filenames: Dict[object, str], viewIds: Sequence[object],
+                             models: Optional[Dict[object, AffineTransform3D]] = None, lib: Optional[C.CDLL] = None,
+                             device: int = 0) -> "ExtractPSF":
+        """ExtractPSF.java:541-598: one TIFF per view (``filenames[viewId]``), transformed with the view's model when
+        ``models`` is given, used as it is otherwise."""
+        from .export import read_tiff_stack
+        e = cls(lib=lib, device=device)
+        for vd in viewIds:
+            if vd not in filenames or not os.path.exists(filenames[vd]):
+                raise RuntimeError(f"Could not load '{filenames.get(vd)}' (should be a TIFF file).")
+            psfImage = read_tiff_stack(filenames[vd])
+            psf = cls.transformPSF(psfImage, models[vd], lib=e.lib, device=device) if models is not None else psfImage.copy()
+            e.viewIds.append(vd)
+            e.pointSpreadFunctions[vd] = psf
+            e.originalPSFs[vd] = psfImage
+        return e
 
     @staticmethod
     def makeSameSize(img: np.ndarray, sizeIn: Sequence[int]) -> np.ndarray:
