@@ -21,11 +21,18 @@ run "SPIM_COLP=2 SPIM_THREADS_COL=160"
 run "SPIM_COLP=3"                                   # TMA tensor-map pipeline, 2 consumer groups
 run "SPIM_COLP=3 SPIM_THREADS_COLT=352"
 run "SPIM_COLP=3 SPIM_TMAP=0"                       # per-row bulk copies (known slow)
+run "SPIM_COLP=2 SPIM_COLP_Y=3"                     # hybrid: TMA pipeline for the 72 KB y tiles, default for the z pass
+run "SPIM_COLP=2 SPIM_COLP_Y=3 SPIM_THREADS_COLT=352"
 run "SPIM_COLP=4"                                   # warp-private columns
+run "SPIM_COLP=2 SPIM_COLP_Z=4"                     # warp-private columns for the small z tiles only
 run "SPIM_COLP=2 SPIM_KSTAGE=1"
 run "SPIM_THREADS_XFWD=128"
 run "SPIM_THREADS_XFWD=256"
 run "SPIM_THREADS_XINV=192"
 check "SPIM_COLP=3"
+check "SPIM_COLP=2 SPIM_COLP_Y=3"
 check "SPIM_COLP=4"
 check "SPIM_COLP=2 SPIM_REGCAP=1 SPIM_THREADS_COL=256"
+# fusion pre-step (round-2 first run on hardware): parity, then one ncu pass over its kernels
+echo "== fusion pre-step GPU tests"
+timeout 600 python -m pytest tests/test_zz_gpu_fusion.py -x -q 2>&1 | tail -3

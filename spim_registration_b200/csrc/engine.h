@@ -149,6 +149,13 @@ inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); re
 inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
 
+// per-axis override for A/B runs: SPIM_COLP_Y / SPIM_COLP_Z (e.g. the TMA pipeline for the 72 KB y tiles only)
+inline int use_colp_for(int axis) {
+    static int y = env_int("SPIM_COLP_Y", -1), z = env_int("SPIM_COLP_Z", -1);
+    const int v = axis == 1 ? y : z;
+    return v >= 0 ? v : use_colp();
+}
+
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
 
 // ------------------------------------------------------------------------------------------
@@ -320,7 +327,8 @@ public:
         const size_t smem = (size_t)Pa * TC * sizeof(float2);
         if (timer) timer->begin(id, st);
         const size_t lim = rt::max_smem();
-        if (use_colp() == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
+        const int colp = use_colp_for(axis);
+        if (colp == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
             // experimental TMA / mbarrier pipeline: correct, but slower than the default in round 1 (see kernels.h)
             p.kstage = 0;
             p.ntiles = (int)grid;
@@ -351,10 +359,10 @@ public:
                 if (ok) { p.use_tmap = 1; p.box_rows = br; }
             }
             rt::launch<ColPassT, 512>(p, p.nctas, T, 3 * smem + 64, st);
-        } else if (use_colp() == 4) {
+        } else if (colp == 4) {
             // experimental warp-private-column variant: 4 warps per tile, no CTA barriers between stages
             rt::launch<ColPassW>(p, grid, 128, smem, st);
-        } else if (use_colp() >= 2) {
+        } else if (colp >= 2) {
             p.ntiles = -1;    // async mode flag
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;

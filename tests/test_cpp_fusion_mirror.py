@@ -1,6 +1,6 @@
 """The header-only C++ host layer of the fusion pre-step (include/spim_fusion.hpp: AffineTransform3D, ExtractPSF,
 ProcessForDeconvolution) compiled with g++ and run against the kernel emulator (CPU) -- and against the CUDA library on
-a GPU box -- then recomputed with the oracle: transformed image / weights / PSFs bit-exact, psi at the parity bar."""
+a GPU box (test_zz_gpu_fusion.py) -- then recomputed with the oracle: transformed image / weights / PSFs bit-exact, psi at the parity bar."""
 import os
 import subprocess
 
@@ -71,9 +71,3 @@ def check(lib_path, tmp_path):
 def test_cpp_fusion_mirror_on_emulator(tmp_path):
     import __graft_entry__ as g
     check(g.build_emulator(), tmp_path)
-
-
-@pytest.mark.gpu
-def test_cpp_fusion_mirror_on_gpu(gpu, tmp_path):
-    from spim_registration_b200 import native
-    check(native.default_library_path(), tmp_path)

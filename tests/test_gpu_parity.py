@@ -117,11 +117,6 @@ def test_gen1_osem_variants(gpu):
     P.decon_case(gpu, (24, 28, 32), 3, 5, O.EFFICIENT_BAYESIAN, 1, 2, osem=2.0, osem_index=0)
 
 
-def test_views_uploaded_in_cells(gpu):
-    P.cells_case(gpu)
-    P.cells_case(gpu, shape=(40, 50, 60), cell=(16, 32, 24), V=3, ks=7)
-
-
 def test_exact_tikhonov_switch(gpu):
     P.exact_tikhonov_case(gpu, (30, 34, 38))
 

@@ -1,10 +1,14 @@
 """GPU parity tests of the fusion pre-step: the CUDA kernels of csrc/fusion.h through
 the C-ABI of include/spim_fusion.h against oracle/fusion_oracle.py -- bit-exact (the Java arithmetic is reproduced
-operation by operation, no FMA contraction).  Run on the B200 box with  python -m pytest tests -m gpu."""
+operation by operation, no FMA contraction).  Run on the B200 box with  python -m pytest tests -m gpu.
+
+The file name sorts last on purpose: these rows were written after the round's GPU budget was spent, so under `pytest -x`
+the hot-path parity tests (test_gpu_parity.py), which have run on hardware, are reported before anything here can stop the run."""
 import numpy as np
 import pytest
 
 import fusion_cases as FC
+import parity_cases as P
 from oracle import fusion_oracle as F
 from oracle import mvdecon_oracle as O
 from spim_registration_b200 import fusion
@@ -65,3 +69,14 @@ def test_psf_extraction_and_transform(gpu):
 def test_full_size_identity_properties(gpu):
     """C2-sized view (512 x 512 x 256): size-independent properties instead of an oracle run."""
     FC.identity_properties_case(gpu, (256, 512, 512))
+
+
+def test_views_uploaded_in_cells(gpu):
+    P.cells_case(gpu)
+    P.cells_case(gpu, shape=(40, 50, 60), cell=(16, 32, 24), V=3, ks=7)
+
+
+def test_cpp_fusion_mirror_on_gpu(gpu, tmp_path):
+    from spim_registration_b200 import native
+    from test_cpp_fusion_mirror import check
+    check(native.default_library_path(), tmp_path)
