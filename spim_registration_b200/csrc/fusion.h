@@ -8,10 +8,12 @@
 //   MinMaxK / NormalizeK   loader normalisation (spim/fiji/spimdata/imgloaders/AbstractImgLoader.java:164-184)
 // FD/ = spim/process/fusion/deconvolution/, FW/ = spim/process/fusion/weights/ under /root/reference/src/main/java/.
 //
-// All of it is streaming work bound by HBM (one coalesced write per output voxel; the gathers of the tri-linear
-// taps walk a straight line through the source stack and are served by L2).  The Java arithmetic is reproduced
-// operation by operation: double position math and interpolation weights, every tap rounded to float, float
-// accumulation in the interpolator's Gray-code order, no FMA contraction anywhere.
+// Streaming work: one coalesced write per output voxel, the gathers of the tri-linear taps walk a straight line
+// through the source stack and are served by L2.  The Java arithmetic is reproduced operation by operation (double
+// position math and interpolation weights, every tap rounded to float, float accumulation in the interpolator's
+// Gray-code order, no FMA contraction anywhere), which makes ResampleK bound by fp64 / integer issue (~100 un-fused
+// double operations per voxel) rather than by its ~10 bytes per voxel of HBM traffic; WeightNormK and the loader
+// normalisation are plain HBM-bound passes.
 // Included by spim_b200.cu after its element-wise helpers (atomic_* / warp_* shims, kChunk, ew_blocks).
 #pragma once
 
@@ -122,6 +124,29 @@ SPIM_DEV float blend_weight(const BlendDesc& b, float t0, float t1, float t2) {
     return md;
 }
 
+// (x, y, z) of a linear voxel index without a 64-bit division per voxel: the items a thread visits inside one chunk
+// are `step` apart, so the coordinates are decomposed once per chunk and then advanced with carries.
+struct VoxelWalker {
+    int x, y, z, nx, ny;
+    SPIM_DEV void start(long long idx, int nx_, int ny_) {
+        nx = nx_; ny = ny_;
+        x = (int)(idx % nx);
+        const long long r = idx / nx;
+        y = (int)(r % ny);
+        z = (int)(r / ny);
+    }
+    SPIM_DEV void advance(int step) {
+        x += step;
+        while (x >= nx) { x -= nx; ++y; }
+        while (y >= ny) { y -= ny; ++z; }
+    }
+};
+#if defined(SPIM_HOST_EMU)
+#define SPIM_ITEM_STEP 1
+#else
+#define SPIM_ITEM_STEP ((int)blockDim.x)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // ResampleK: one output voxel per item, x fastest (coalesced stores).
 //   pos_mode 0  TransformInput arithmetic: s = (float)voxel + (float)offset, t = (float)(inverse * s)
@@ -147,13 +172,13 @@ struct ResampleK {
     SPIM_DEV static void run(const Params& p, int bid, float2*) {
         const long long total = (long long)p.on[0] * p.on[1] * p.on[2];
         for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            VoxelWalker w;
+            w.start(base + SPIM_TID, p.on[2], p.on[1]);
             SPIM_FOR_ITEMS(i, kChunk) {
                 const long long idx = base + i;
+                const int x = w.x, y = w.y, z = w.z;
+                w.advance(SPIM_ITEM_STEP);
                 if (idx >= total) continue;
-                const int x = (int)(idx % p.on[2]);
-                const long long r = idx / p.on[2];
-                const int y = (int)(r % p.on[1]);
-                const int z = (int)(r / p.on[1]);
                 double t0, t1, t2;
                 if (p.pos_mode == 0) {
                     const float s0 = spim_fadd_rn((float)x, (float)p.off[0]);
@@ -201,13 +226,13 @@ struct ExtractPsfK {
     SPIM_DEV static void run(const Params& p, int bid, float2*) {
         const long long total = (long long)p.size[0] * p.size[1] * p.size[2];
         for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            VoxelWalker w;
+            w.start(base + SPIM_TID, p.size[2], p.size[1]);
             SPIM_FOR_ITEMS(i, kChunk) {
                 const long long idx = base + i;
+                const int x = w.x, y = w.y, z = w.z;
+                w.advance(SPIM_ITEM_STEP);
                 if (idx >= total) continue;
-                const int x = (int)(idx % p.size[2]);
-                const long long r = idx / p.size[2];
-                const int y = (int)(r % p.size[1]);
-                const int z = (int)(r / p.size[1]);
                 const double dx = (double)(x - p.size[2] / 2), dy = (double)(y - p.size[1] / 2), dz = (double)(z - p.size[0] / 2);
                 float acc = 0.f;
                 for (int b = 0; b < p.n_beads; ++b) {
