@@ -48,7 +48,11 @@ typedef struct mvd_params {
     int exact_tikhonov;    /* 0 (default): Tikhonov step in the algebraically identical, cancellation-free fp32 form
                               2v/(1+sqrt(1+2*lambda*v)) (<= 2 ulp from the reference's fp64 expression);
                               1: evaluate (sqrt(1+2*lambda*v)-1)/lambda in fp64 exactly like the Java code */
-    int reserved[7];
+    int fast_epilogue;     /* 0 (default): IEEE fp32 division / square root in the fused ratio and update epilogues;
+                              1: branch-free refinement of the hardware approximations -- the same correctly rounded values
+                              for operands in the normal range, NaN instead of 0 / infinity for zero, denormal or infinite
+                              operands (csrc/fast_math.h) */
+    int reserved[6];
 } mvd_params;
 
 typedef struct mvd_info {

@@ -34,13 +34,14 @@ public interface MVDeconSession extends Library
 		public int device;
 		public int haloed;
 		public int exact_tikhonov;
-		public int[] reserved = new int[ 7 ];
+		public int fast_epilogue;
+		public int[] reserved = new int[ 6 ];
 
 		@Override
 		protected List< String > getFieldOrder()
 		{
 			return Arrays.asList( "struct_size", "dims", "num_views", "iteration_type", "generation", "lambda", "min_value",
-					"osem_speedup", "osem_index", "conv1_ext", "conv2_ext", "device", "haloed", "exact_tikhonov", "reserved" );
+					"osem_speedup", "osem_index", "conv1_ext", "conv2_ext", "device", "haloed", "exact_tikhonov", "fast_epilogue", "reserved" );
 		}
 	}
 

@@ -26,9 +26,12 @@ run "SPIM_COLP=2 SPIM_COLP_Y=3 SPIM_THREADS_COLT=352"
 run "SPIM_COLP=4"                                   # warp-private columns
 run "SPIM_COLP=2 SPIM_COLP_Z=4"                     # warp-private columns for the small z tiles only
 run "SPIM_COLP=2 SPIM_KSTAGE=1"
+run "SPIM_FAST_EPI=1"                               # branch-free MUFU-seeded division / sqrt in the ratio / update epilogues
+run "SPIM_FAST_EPI=1 SPIM_COLP_Y=3"
 run "SPIM_THREADS_XFWD=128"
 run "SPIM_THREADS_XFWD=256"
 run "SPIM_THREADS_XINV=192"
+check "SPIM_FAST_EPI=1"
 check "SPIM_COLP=3"
 check "SPIM_COLP=2 SPIM_COLP_Y=3"
 check "SPIM_COLP=4"

@@ -182,6 +182,7 @@ struct EpiDesc {            // what XInv does with the result
     float min_value = 1e-4f;
     int gen2_quotient = 1;
     int exact_tikhonov = 0;
+    int fast_epilogue = 0;
     double* stat_sum = nullptr;
     unsigned int* stat_max = nullptr;
 };
@@ -400,6 +401,8 @@ public:
         p.lambda = e.lambda; p.min_value = e.min_value; p.gen2_quotient = e.gen2_quotient;
         p.two_lambda = (float)(2.0 * e.lambda);
         p.exact_tikhonov = e.exact_tikhonov;
+        static int fast_env = env_int("SPIM_FAST_EPI", 0);       // A/B switch for the benchmarks
+        p.fast_epilogue = (e.fast_epilogue || fast_env) ? 1 : 0;
         p.stat_sum = e.stat_sum; p.stat_max = e.stat_max;
         auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
         p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);
@@ -407,10 +410,21 @@ public:
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
         if (timer) timer->begin(K_XINV, st);
         const int T = threads_xinv();
-        if (e.epi == EPI_STORE) rt::launch<XInvT<EPI_STORE, false>>(p, grid, T, smem, st);
-        else if (e.epi == EPI_RATIO) rt::launch<XInvT<EPI_RATIO, false>>(p, grid, T, smem, st);
-        else if (e.exact_tikhonov) rt::launch<XInvT<EPI_UPDATE, true>>(p, grid, T, smem, st);
-        else rt::launch<XInvT<EPI_UPDATE, false>>(p, grid, T, smem, st);
+        // 36 KB tiles: six 128-thread blocks fit per SM as long as the ratio kernel stays within 85 registers
+        const bool cap6 = T <= 128 && smem <= 37 * 1024;
+        if (e.epi == EPI_STORE) rt::launch<XInvT<EPI_STORE, MATH_IEEE>>(p, grid, T, smem, st);
+        else if (e.epi == EPI_RATIO) {
+            if (p.fast_epilogue) {
+                if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_FAST>, 128, 6>(p, grid, T, smem, st);
+                else rt::launch<XInvT<EPI_RATIO, MATH_FAST>>(p, grid, T, smem, st);
+            } else {
+                if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_IEEE>, 128, 6>(p, grid, T, smem, st);
+                else rt::launch<XInvT<EPI_RATIO, MATH_IEEE>>(p, grid, T, smem, st);
+            }
+        }
+        else if (e.exact_tikhonov) rt::launch<XInvT<EPI_UPDATE, MATH_EXACT64>>(p, grid, T, smem, st);
+        else if (p.fast_epilogue) rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
+        else rt::launch<XInvT<EPI_UPDATE, MATH_IEEE>>(p, grid, T, smem, st);
         if (timer) timer->end(K_XINV, st);
     }
 

@@ -50,6 +50,11 @@ static inline double spim_dsub_rn(double a, double b) { volatile double r = a - 
 static inline double spim_dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double spim_ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float spim_d2f_rn(double a) { volatile float r = (float)a; return r; }
+// seeds of the fast epilogue (csrc/fast_math.h): the emulator uses correctly rounded values, the GPU MUFU approximations
+static inline float spim_rcp_seed(float b) { volatile float r = 1.0f / b; return r; }
+static inline float spim_rsqrt_seed(float x) { volatile float r = (float)(1.0 / sqrt((double)x)); return r; }
+#define SPIM_FM_HD static inline
+#define SPIM_FM_MUL(a, b) spim_fmul_rn(a, b)
 
 #else
 
@@ -141,5 +146,10 @@ __device__ __forceinline__ double spim_dsub_rn(double a, double b) { return __ds
 __device__ __forceinline__ double spim_dmul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double spim_ddiv_rn(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ float spim_d2f_rn(double a) { return __double2float_rn(a); }
+// seeds of the fast epilogue (csrc/fast_math.h): MUFU.RCP (<= 1 ulp) and MUFU.RSQ (<= 2 ulp)
+__device__ __forceinline__ float spim_rcp_seed(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float spim_rsqrt_seed(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define SPIM_FM_HD __device__ __forceinline__
+#define SPIM_FM_MUL(a, b) __fmul_rn(a, b)
 
 #endif

@@ -26,6 +26,7 @@
 // same source runs under the CPU emulator used by the unit tests (see hd.h).
 #pragma once
 #include "fft_math.h"
+#include "fast_math.h"
 
 namespace spim {
 
@@ -911,6 +912,7 @@ struct XInvParams {
     float min_value;
     int gen2_quotient;         // 1: q = img > 0 ? img / blur : 1 ; 0: q = img / blur
     int exact_tikhonov;        // 1: evaluate (sqrt(1+2 lambda v)-1)/lambda in fp64 exactly like the Java code
+    int fast_epilogue;         // 1: MATH_FAST division / square root in the ratio and update epilogues
     double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
     unsigned int* stat_max;    // max |change| as float bits
     int vec_ok;                // float2 accesses to dst / img / weight allowed and nx even
@@ -933,31 +935,41 @@ SPIM_DEV float tikhonov_fp64(float value, double lambda) {
 // next psi value, computeNextValue FD/MVDeconvolution.java:692-724 (= D2/BayesMVDeconvolution.java:452-476).
 // Default: the algebraically identical cancellation-free fp32 form 2v / (1 + sqrt(1 + 2 lambda v))
 // (<= 2 ulp from the fp64 expression for lambda >= 0.006 on v in [1e-5, 10]); EXACT selects the fp64 path.
-template <bool EXACT>
-SPIM_DEV float next_value(const XInvParams& p, float last, float integral) {
-    const float value = spim_fmul_rn(last, integral);
-    float adj;
-    if (value > 0.f) {
-        if (p.lambda > 0.0) {
-            if (EXACT) adj = tikhonov_fp64(value, p.lambda);
-            else adj = spim_fdiv_rn(value + value, 1.f + spim_fsqrt_rn(spim_fmaf_rn(p.two_lambda, value, 1.f)));
-        } else {
-            adj = value;
-        }
-    } else {
-        adj = p.min_value;
-    }
-    return fmaxf(p.min_value, adj);       // fmaxf returns the non-NaN operand: NaN -> minValue
+// Written with selects instead of branches (the Tikhonov value is computed unconditionally and discarded where the
+// reference does not use it): the result is the same for every input, NaN included, and the fused epilogue stays
+// straight-line code.  `lam_pos` = (lambda > 0), hoisted by the caller.
+// MATH: 0 = IEEE fp32 division / square root intrinsics (default), 1 = the reference's fp64 Tikhonov expression,
+//       2 = fast epilogue: branch-free refinement of the hardware approximations (fast_math.h; identical results for
+//           operands in the normal range)
+enum { MATH_IEEE = 0, MATH_EXACT64 = 1, MATH_FAST = 2 };
+template <int MATH> SPIM_DEV float epi_div(float a, float b) {
+    return MATH == MATH_FAST ? spim_div_from_seed(a, b, spim_rcp_seed(b)) : spim_fdiv_rn(a, b);
+}
+template <int MATH> SPIM_DEV float epi_sqrt(float x) {
+    return MATH == MATH_FAST ? spim_sqrt_from_seed(x, spim_rsqrt_seed(x)) : spim_fsqrt_rn(x);
 }
 
-template <int EPI, bool EXACT>
-SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, float& csum, float& cmax) {
-    if (EPI == EPI_RATIO) {            // x1 = observed image value
-        if (p.gen2_quotient) return x1 > 0.f ? spim_fdiv_rn(x1, v) : 1.f;
-        return spim_fdiv_rn(x1, v);
+template <int MATH>
+SPIM_DEV float next_value(const XInvParams& p, bool lam_pos, float last, float integral) {
+    const float value = spim_fmul_rn(last, integral);
+    float tik;
+    if (MATH == MATH_EXACT64) tik = (value > 0.f && lam_pos) ? tikhonov_fp64(value, p.lambda) : value;
+    else tik = epi_div<MATH>(value + value, 1.f + epi_sqrt<MATH>(spim_fmaf_rn(p.two_lambda, value, 1.f)));
+    float adj = lam_pos ? tik : value;
+    adj = (value > 0.f) ? adj : p.min_value;      // value NaN -> minValue, like the reference's else branch
+    return fmaxf(p.min_value, adj);               // fmaxf returns the non-NaN operand: NaN -> minValue
+}
+
+struct EpiFlags { bool lam_pos, gen2q, has_w; };
+
+template <int EPI, int MATH>
+SPIM_DEV float epi_one(const XInvParams& p, const EpiFlags& f, float v, float x1, float x2, float& csum, float& cmax) {
+    if (EPI == EPI_RATIO) {            // x1 = observed image value; gen-2: q = img > 0 ? img / blur : 1
+        const float q = epi_div<MATH>(x1, v);
+        return (f.gen2q && !(x1 > 0.f)) ? 1.f : q;
     }
     if (EPI == EPI_UPDATE) {           // x1 = psi (last), x2 = weight
-        const float next = next_value<EXACT>(p, x1, v);
+        const float next = next_value<MATH>(p, f.lam_pos, x1, v);
         const float nw = spim_fadd_rn(x1, spim_fmul_rn(spim_fsub_rn(next, x1), x2));
         const float ch = fabsf(spim_fsub_rn(nw, x1));
         csum += ch;
@@ -968,50 +980,39 @@ SPIM_DEV float epi_one(const XInvParams& p, float v, float x1, float x2, float& 
 }
 
 // epilogue inputs for output samples x = 2n, 2n+1 of one line, fetched BEFORE the butterfly so that the
-// global-memory latency overlaps the shared-memory stage
-template <int EPI, bool VEC>
-SPIM_DEV void epi_fetch(const XInvParams& p, long long aux0, long long dst0, int n, float2& x1, float2& x2) {
+// global-memory latency overlaps the shared-memory stage (scalar path: odd nx / unaligned buffers)
+template <int EPI>
+SPIM_DEV void epi_fetch_scalar(const XInvParams& p, long long aux0, long long dst0, int n, float2& x1, float2& x2) {
     const int u0 = 2 * n;
     x1 = make_float2(0.f, 0.f);
     x2 = make_float2(p.const_weight, p.const_weight);
     if (EPI == EPI_STORE || u0 >= p.nx) return;
     const long long ai = aux0 + u0, di = dst0 + u0;
-    if (VEC) {
-        if (EPI == EPI_RATIO) x1 = ldg_stream(reinterpret_cast<const float2*>(p.img + ai));
-        else {
-            if (p.weight) x2 = ldg_stream(reinterpret_cast<const float2*>(p.weight + ai));
-            x1 = *reinterpret_cast<const float2*>(p.dst + di);
-        }
-    } else {
-        const bool two = (u0 + 1 < p.nx);
-        if (EPI == EPI_RATIO) { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
-        else {
-            if (p.weight) { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
-            x1.x = p.dst[di]; if (two) x1.y = p.dst[di + 1];
-        }
+    const bool two = (u0 + 1 < p.nx);
+    if (EPI == EPI_RATIO) { x1.x = spim_ldg(p.img + ai); if (two) x1.y = spim_ldg(p.img + ai + 1); }
+    else {
+        if (p.weight) { x2.x = spim_ldg(p.weight + ai); if (two) x2.y = spim_ldg(p.weight + ai + 1); }
+        x1.x = p.dst[di]; if (two) x1.y = p.dst[di + 1];
     }
 }
 
-template <int EPI, bool EXACT, bool VEC>
-SPIM_DEV void epi_store(const XInvParams& p, long long dst0, int n, float2 v, float2 x1, float2 x2, float& csum, float& cmax) {
+template <int EPI, int MATH>
+SPIM_DEV void epi_store_scalar(const XInvParams& p, const EpiFlags& f, long long dst0, int n, float2 v, float2 x1, float2 x2,
+                               float& csum, float& cmax) {
     const int u0 = 2 * n;
     if (u0 >= p.nx) return;
     const long long di = dst0 + u0;
-    const float r0 = epi_one<EPI, EXACT>(p, v.x, x1.x, x2.x, csum, cmax);
-    if (VEC) {
-        const float r1 = epi_one<EPI, EXACT>(p, v.y, x1.y, x2.y, csum, cmax);
-        *reinterpret_cast<float2*>(p.dst + di) = make_float2(r0, r1);
-    } else {
-        p.dst[di] = r0;
-        if (u0 + 1 < p.nx) p.dst[di + 1] = epi_one<EPI, EXACT>(p, v.y, x1.y, x2.y, csum, cmax);
-    }
+    p.dst[di] = epi_one<EPI, MATH>(p, f, v.x, x1.x, x2.x, csum, cmax);
+    if (u0 + 1 < p.nx) p.dst[di + 1] = epi_one<EPI, MATH>(p, f, v.y, x1.y, x2.y, csum, cmax);
 }
 
-template <int R, int EPI, bool EXACT, bool VEC>
+template <int R, int EPI, int MATH, bool VEC>
 SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
     const float2* twp = pl.tws + pl.tw_off[0];
+    EpiFlags f;
+    f.lam_pos = p.lambda > 0.0; f.gen2q = p.gen2_quotient != 0; f.has_w = p.weight != nullptr;
     SPIM_FOR_ITEMS(i, M * TC) {
         const int b = (M == 1) ? i : fastdiv(i, p.magic_m0);
         const int m = i - b * M;
@@ -1020,16 +1021,53 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
         const long long a_o = auxoff[b];
         float2 x1[R], x2[R], w[R];
         if (M > 1) load_twiddles<R>(w, twp + m * (R - 1));
+        if (VEC) {
+            // 8-byte accesses (nx even, aligned buffers): one base pointer per array and item, predicated accesses per row
+            // pair instead of early exits, the weight's null check once per item
+            const float2* in1 = reinterpret_cast<const float2*>(EPI == EPI_RATIO ? p.img + a_o : p.dst + d_o);
+            const float2* in2 = reinterpret_cast<const float2*>(p.weight + a_o);
+            const int nh = p.nx >> 1;
 #pragma unroll
-        for (int q = 0; q < R; ++q) epi_fetch<EPI, VEC>(p, a_o, d_o, m + q * M, x1[q], x2[q]);
+            for (int q = 0; q < R; ++q) {
+                const int n = m + q * M;
+                x1[q] = make_float2(0.f, 0.f);
+                x2[q] = make_float2(p.const_weight, p.const_weight);
+                if (EPI != EPI_STORE && n < nh) x1[q] = (EPI == EPI_RATIO) ? ldg_stream(in1 + n) : in1[n];
+            }
+            if (EPI == EPI_UPDATE && f.has_w) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) { const int n = m + q * M; if (n < nh) x2[q] = ldg_stream(in2 + n); }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) epi_fetch_scalar<EPI>(p, a_o, d_o, m + q * M, x1[q], x2[q]);
+        }
         float2 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = tile2[xelem(b, m + q * M)];
         if (M > 1) mul_twiddles1<R, true>(a, w);
         dft<R, true>(a);
         float csum = 0.f, cmax = 0.f;
+        if (VEC) {
+            float2* out = reinterpret_cast<float2*>(p.dst + d_o);
+            const int nh = p.nx >> 1;
 #pragma unroll
-        for (int q = 0; q < R; ++q) epi_store<EPI, EXACT, VEC>(p, d_o, m + q * M, a[q], x1[q], x2[q], csum, cmax);
+            for (int q = 0; q < R; ++q) {
+                const int n = m + q * M;
+                // rows beyond the image take part in the arithmetic with benign inputs and are simply not stored / counted
+                float s0 = 0.f, s1 = 0.f, mx = 0.f;
+                const float r0 = epi_one<EPI, MATH>(p, f, a[q].x, x1[q].x, x2[q].x, s0, mx);
+                const float r1 = epi_one<EPI, MATH>(p, f, a[q].y, x1[q].y, x2[q].y, s1, mx);
+                if (n < nh) {
+                    out[n] = make_float2(r0, r1);
+                    csum += s0; csum += s1;
+                    cmax = fmaxf(cmax, mx);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) epi_store_scalar<EPI, MATH>(p, f, d_o, m + q * M, a[q], x1[q], x2[q], csum, cmax);
+        }
         if (EPI == EPI_UPDATE) { acc.sum += (double)csum; acc.mx = fmaxf(acc.mx, cmax); }
     }
 }
@@ -1071,7 +1109,7 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
 #endif
 }
 
-template <int EPI, bool EXACT>
+template <int EPI, int MATH>
 struct XInvT {
     typedef XInvParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
@@ -1141,8 +1179,8 @@ struct XInvT {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, EXACT, true>(p, tile2, auxoff, dstoff, acc))) }
-        else { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, EXACT, false>(p, tile2, auxoff, dstoff, acc))) }
+        if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        else { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }
 };

@@ -539,12 +539,12 @@ struct mvd_session {
         e.min_value = prm.min_value;
         if (ph == 0) {
             src.p = d_psi; src.ext = conv1_ext(); src.ext_value = 0.f;
-            e.epi = EPI_RATIO; e.dst = d_tmp; e.img = d_img[v]; e.gen2_quotient = (prm.generation == 2);
+            e.epi = EPI_RATIO; e.dst = d_tmp; e.img = d_img[v]; e.gen2_quotient = (prm.generation == 2); e.fast_epilogue = prm.fast_epilogue;
             plan.convolve(src, d_kh1[v], e, stream);
         } else {
             src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = 1.f;
             e.epi = EPI_UPDATE; e.dst = d_psi; e.weight = d_w[v]; e.const_weight = 1.f;
-            e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max; e.exact_tikhonov = prm.exact_tikhonov;
+            e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max; e.exact_tikhonov = prm.exact_tikhonov; e.fast_epilogue = prm.fast_epilogue;
             plan.convolve(src, d_kh2[v], e, stream);
         }
     }

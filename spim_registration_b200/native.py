@@ -41,7 +41,8 @@ class MvdParams(C.Structure):
         ("device", C.c_int),
         ("haloed", C.c_int),
         ("exact_tikhonov", C.c_int),
-        ("reserved", C.c_int * 7),
+        ("fast_epilogue", C.c_int),
+        ("reserved", C.c_int * 6),
     ]
 
 

@@ -155,3 +155,21 @@ def cells_case(lib, shape=(10, 12, 14), cell=(4, 5, 6), V=2, ks=3):
         s.run(2)
         s.finish()
         assert np.array_equal(s.get_psi(), whole)
+
+
+def fast_epilogue_case(lib, shape=(14, 16, 18), bit_identical=False):
+    """fast_epilogue = 1 (branch-free division / square root, csrc/fast_math.h): for operands in the normal range the values
+    are the correctly rounded ones, so the deconvolution must agree with the IEEE epilogue to rounding noise and meet the
+    same parity bar; under the emulator (correctly rounded seeds) it is bit-identical."""
+    for gen, typ, lam in ((2, O.EFFICIENT_BAYESIAN, 0.006), (1, O.OPTIMIZATION_I, 0.06), (2, O.INDEPENDENT, 0.0)):
+        _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 5, kind="beads")
+        ref = O.deconvolve(imgs, ws, psfs, O.DeconParams(iteration_type=typ, num_iterations=3, lam=lam, gen=gen))
+        a, *_ = run_session(lib, imgs, ws, psfs, typ, gen, 3, lam=lam, fast_epilogue=True)
+        b, *_ = run_session(lib, imgs, ws, psfs, typ, gen, 3, lam=lam, fast_epilogue=False)
+        per, l2 = O.parity_errors(a, ref.psi)
+        assert per <= TOL_PER_VOXEL and l2 <= TOL_L2, (gen, typ, per, l2)
+        if bit_identical:
+            assert np.array_equal(a, b)
+        else:
+            per, l2 = O.parity_errors(a, b)
+            assert per <= 2e-5 and l2 <= 2e-6, (gen, typ, per, l2)

@@ -70,6 +70,10 @@ def test_views_uploaded_in_cells(emu_lib):
     P.cells_case(emu_lib)
 
 
+def test_fast_epilogue_switch(emu_lib):
+    P.fast_epilogue_case(emu_lib, bit_identical=True)
+
+
 def test_exact_tikhonov_switch(emu_lib):
     P.exact_tikhonov_case(emu_lib)
 

@@ -80,3 +80,9 @@ def test_cpp_fusion_mirror_on_gpu(gpu, tmp_path):
     from spim_registration_b200 import native
     from test_cpp_fusion_mirror import check
     check(native.default_library_path(), tmp_path)
+
+
+def test_fast_epilogue_switch(gpu):
+    """opt-in MUFU-seeded division / square root in the fused epilogues (mvd_params.fast_epilogue)"""
+    P.fast_epilogue_case(gpu)
+    P.fast_epilogue_case(gpu, shape=(40, 48, 56))
