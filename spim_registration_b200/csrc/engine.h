@@ -303,7 +303,9 @@ public:
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         if (timer) timer->begin(K_XFWD, st);
-        rt::launch<XFwd>(p, grid, threads_xfwd(), smem, st);
+        // four 192-thread blocks per SM (the measured round-1 configuration) need <= 85 registers
+        if (threads_xfwd() <= 192) rt::launch<XFwd, 192, 4>(p, grid, threads_xfwd(), smem, st);
+        else rt::launch<XFwd>(p, grid, threads_xfwd(), smem, st);
         if (timer) timer->end(K_XFWD, st);
     }
 

@@ -728,35 +728,48 @@ SPIM_DEV float xfwd_val(const XFwdParams& p, long long so, int u) {
     return (p.ext == EXT_CONSTANT) ? p.ext_value : 0.f;
 }
 
-SPIM_DEV float2 xfwd_pair(const XFwdParams& p, long long so, int n) {
-    const int u0 = 2 * n;
-    if (so >= 0 && u0 + 1 < p.nx) {   // interior fast path
-        const float* q = p.src + so + p.ox + u0;
-        if (p.src_vec_ok) return ldg_stream(reinterpret_cast<const float2*>(q));
-        return make_float2(spim_ldg(q), spim_ldg(q + 1));
-    }
-    return make_float2(xfwd_val(p, so, u0), xfwd_val(p, so, u0 + 1));
+// everything that is not an interior pair of two real lines: halo, gap, constant or invalid lines, the last odd sample.
+// Kept out of line (one call site per row, both lines of the pair) so that the first stage's inner loop is just the
+// interior loads.
+SPIM_NOINLINE_DEV float4 xfwd_pair_slow(const XFwdParams& p, long long so0, long long so1, int n) {
+    return make_float4(xfwd_val(p, so0, 2 * n), xfwd_val(p, so0, 2 * n + 1), xfwd_val(p, so1, 2 * n), xfwd_val(p, so1, 2 * n + 1));
 }
 
-template <int R>
+template <int R, bool VEC>
 SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* srcoff) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
     const float2* twp = pl.tws + pl.tw_off[0];
+    const int nh = p.nx >> 1;                      // pairs (2n, 2n+1) that lie entirely inside the image: n < nx / 2
     SPIM_FOR_ITEMS(i, M * TP) {
         const int bp = (M == 1) ? i : fastdiv(i, p.magic_m0);
         const int m = i - bp * M;
         const long long so0 = srcoff[2 * bp], so1 = srcoff[2 * bp + 1];
-        float2 a[R], b[R], w[R];
-        if (M > 1) load_twiddles<R>(w, twp + m * (R - 1));
+        // x = 0 of the two lines (only dereferenced when both are real lines: so >= 0)
+        const float* l0 = p.src + (so0 + p.ox);
+        const float* l1 = p.src + (so1 + p.ox);
+        const bool real2 = (so0 >= 0) && (so1 >= 0);
+        float2 a[R], b[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            a[q] = xfwd_pair(p, so0, m + q * M);
-            b[q] = xfwd_pair(p, so1, m + q * M);
+            const int n = m + q * M;
+            if (real2 && n < nh) {
+                if (VEC) {
+                    a[q] = ldg_stream(reinterpret_cast<const float2*>(l0) + n);
+                    b[q] = ldg_stream(reinterpret_cast<const float2*>(l1) + n);
+                } else {
+                    a[q] = make_float2(spim_ldg(l0 + 2 * n), spim_ldg(l0 + 2 * n + 1));
+                    b[q] = make_float2(spim_ldg(l1 + 2 * n), spim_ldg(l1 + 2 * n + 1));
+                }
+            } else {
+                const float4 v = xfwd_pair_slow(p, so0, so1, n);
+                a[q] = lo2(v); b[q] = hi2(v);
+            }
         }
         dft<R, false>(a);
         dft<R, false>(b);
-        if (M > 1) mul_twiddles2<R, false>(a, b, w);
+        // twiddles are fetched on use here: holding them across the loads and the butterfly costs the fourth resident block
+        if (M > 1) apply_twiddles2<R, false>(a, b, twp + m * (R - 1));
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
@@ -825,7 +838,8 @@ struct XFwd {
             dstoff[b] = d_o;
         }
         SPIM_BARRIER();
-        SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR>(p, tile, srcoff)))
+        if (p.src_vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR, true>(p, tile, srcoff))) }
+        else { SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR, false>(p, tile, srcoff))) }
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
         for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
