@@ -801,6 +801,55 @@ SPIM_DEV void split_inv(float2 A, float2 B, float2 w, float2& zk, float2& zm) {
     zm = make_float2(s.x + t.y, -s.y + t.x);
 }
 
+// forward split step of one tile: half spectrum of 16 real lines from the 8 complex transforms of their pairs
+SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2) {
+    // split step on line pairs (factor 1/2 folded into the kernel scale).  Two items per trip: the dependent
+    // chain pos[] -> shared-memory row -> arithmetic of one item overlaps the other's
+    const int nk = p.nk;
+    const int total = nk * TP;
+    for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
+        int bpv[2], kv[2], rk[2], rm[2];
+        float2 wv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * SPIM_NTHREADS;
+            bpv[u] = -1; kv[u] = 0; rk[u] = 0; rm[u] = 0; wv[u] = make_float2(1.f, 0.f);
+            if (i < total) {
+                const int bp = fastdiv(i, p.magic_nk);
+                const int k = i - bp * nk;
+                bpv[u] = bp; kv[u] = k;
+                rk[u] = spim_ldg(p.pos + k);
+                rm[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
+                wv[u] = spim_ldg(p.wx + k);
+            }
+        }
+        float4 zkv[2], zmv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int bp = bpv[u] < 0 ? 0 : bpv[u];
+            zkv[u] = tile[rk[u] * TP + ((bp + rk[u]) & (TP - 1))];
+            zmv[u] = tile[rm[u] * TP + ((bp + rm[u]) & (TP - 1))];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (bpv[u] < 0) continue;
+            const int bp = bpv[u], k = kv[u], km = N2 - k;
+            const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
+            float2 xk, xm;
+            if (d0 >= 0) {
+                split_fwd(lo2(zkv[u]), lo2(zmv[u]), wv[u], xk, xm);
+                p.spec[d0 + k] = xk;
+                if (km != k) p.spec[d0 + km] = xm;
+            }
+            if (d1 >= 0) {
+                split_fwd(hi2(zkv[u]), hi2(zmv[u]), wv[u], xk, xm);
+                p.spec[d1 + k] = xk;
+                if (km != k) p.spec[d1 + km] = xm;
+            }
+        }
+    }
+}
+
 struct XFwd {
     typedef XFwdParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
@@ -843,51 +892,7 @@ struct XFwd {
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
         for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
-        // split step on line pairs (factor 1/2 folded into the kernel scale).  Two items per trip: the dependent
-        // chain pos[] -> shared-memory row -> arithmetic of one item overlaps the other's
-        const int nk = p.nk;
-        const int total = nk * TP;
-        for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
-            int bpv[2], kv[2], rk[2], rm[2];
-            float2 wv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = i0 + u * SPIM_NTHREADS;
-                bpv[u] = -1; kv[u] = 0; rk[u] = 0; rm[u] = 0; wv[u] = make_float2(1.f, 0.f);
-                if (i < total) {
-                    const int bp = fastdiv(i, p.magic_nk);
-                    const int k = i - bp * nk;
-                    bpv[u] = bp; kv[u] = k;
-                    rk[u] = spim_ldg(p.pos + k);
-                    rm[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
-                    wv[u] = spim_ldg(p.wx + k);
-                }
-            }
-            float4 zkv[2], zmv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int bp = bpv[u] < 0 ? 0 : bpv[u];
-                zkv[u] = tile[rk[u] * TP + ((bp + rk[u]) & (TP - 1))];
-                zmv[u] = tile[rm[u] * TP + ((bp + rm[u]) & (TP - 1))];
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (bpv[u] < 0) continue;
-                const int bp = bpv[u], k = kv[u], km = N2 - k;
-                const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
-                float2 xk, xm;
-                if (d0 >= 0) {
-                    split_fwd(lo2(zkv[u]), lo2(zmv[u]), wv[u], xk, xm);
-                    p.spec[d0 + k] = xk;
-                    if (km != k) p.spec[d0 + km] = xm;
-                }
-                if (d1 >= 0) {
-                    split_fwd(hi2(zkv[u]), hi2(zmv[u]), wv[u], xk, xm);
-                    p.spec[d1 + k] = xk;
-                    if (km != k) p.spec[d1 + km] = xm;
-                }
-            }
-        }
+        xfwd_split(p, tile, dstoff, N2);
         // zero the pad columns [N2+1, pitch)
         const int npad = p.pitch - (N2 + 1);
         SPIM_FOR_ITEMS(i, npad * TC) {
