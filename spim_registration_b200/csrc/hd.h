@@ -33,6 +33,7 @@ template <class T> static inline T spim_ldg(const T* p) { return *p; }
 static inline float4 ldg_stream(const float4* p) { return *p; }
 static inline float2 ldg_stream(const float2* p) { return *p; }
 static inline void stg_stream(float4* p, float4 v) { *p = v; }
+static inline void stg_stream_if(float4* p, float4 v, bool ok) { if (ok) *p = v; }
 static inline uint32_t spim_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 // cp.async (LDGSTS) shims: the emulator copies immediately
 static inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
@@ -90,6 +91,12 @@ __device__ __forceinline__ float2 ldg_stream(const float2* p) {
 }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// the same store under a predicate that lives inside the instruction (@p st...) instead of a branch around it:
+// rows beyond the kept range are skipped without reconvergence scaffolding
+__device__ __forceinline__ void stg_stream_if(float4* p, float4 v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok) : "memory");
 }
 __device__ __forceinline__ uint32_t spim_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 // asynchronous 16-byte global -> shared copies (LDGSTS), grouped and awaited per thread

@@ -195,11 +195,12 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
             dft<R, true>(b);
         }
         if (dst_g) {
+            // predicated streaming stores, the row pointer advanced by one 64-bit add per row
             float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                const int row = base + q * M;
-                if (row < g.sa) stg_stream(gp + q * gstep, pack4(a[q], b[q]));
+                stg_stream_if(gp, pack4(a[q], b[q]), base + q * M < g.sa);
+                gp += gstep;
             }
         } else if (!swz) {
             float4* sp = tile + base * TP + c2;
@@ -260,8 +261,8 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
             float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                const int row = base + q;
-                if (row < g.sa) stg_stream(gp + q * gs4, pack4(a[q], b[q]));
+                stg_stream_if(gp, pack4(a[q], b[q]), base + q < g.sa);
+                gp += gs4;
             }
         } else {
             float4* sp = tile + base * TP + c2;
