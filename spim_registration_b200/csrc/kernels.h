@@ -802,50 +802,39 @@ SPIM_DEV void split_inv(float2 A, float2 B, float2 w, float2& zk, float2& zm) {
     zm = make_float2(s.x + t.y, -s.y + t.x);
 }
 
-// forward split step of one tile: half spectrum of 16 real lines from the 8 complex transforms of their pairs
+// forward split step of one tile: half spectrum of 16 real lines from the 8 complex transforms of their pairs (factor
+// 1/2 folded into the kernel scale).  One item = one frequency pair (k, N2 - k) of FOUR line pairs, see xinv_presplit.
 SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2) {
-    // split step on line pairs (factor 1/2 folded into the kernel scale).  Two items per trip: the dependent
-    // chain pos[] -> shared-memory row -> arithmetic of one item overlaps the other's
     const int nk = p.nk;
-    const int total = nk * TP;
-    for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
-        int bpv[2], kv[2], rk[2], rm[2];
-        float2 wv[2];
+    SPIM_FOR_ITEMS(i, nk * (TP / 4)) {
+        const int h = fastdiv(i, p.magic_nk);
+        const int k = i - h * nk;
+        const int km = N2 - k;
+        const float2 w = spim_ldg(p.wx + k);
+        const int rk = spim_ldg(p.pos + k);
+        const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
+        const bool two = km != k;
+        float4 zk[4], zm[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = i0 + u * SPIM_NTHREADS;
-            bpv[u] = -1; kv[u] = 0; rk[u] = 0; rm[u] = 0; wv[u] = make_float2(1.f, 0.f);
-            if (i < total) {
-                const int bp = fastdiv(i, p.magic_nk);
-                const int k = i - bp * nk;
-                bpv[u] = bp; kv[u] = k;
-                rk[u] = spim_ldg(p.pos + k);
-                rm[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
-                wv[u] = spim_ldg(p.wx + k);
-            }
-        }
-        float4 zkv[2], zmv[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int bp = bpv[u] < 0 ? 0 : bpv[u];
-            zkv[u] = tile[rk[u] * TP + ((bp + rk[u]) & (TP - 1))];
-            zmv[u] = tile[rm[u] * TP + ((bp + rm[u]) & (TP - 1))];
+        for (int g = 0; g < 4; ++g) {
+            const int bp = h * 4 + g;
+            zk[g] = tile[rk * TP + ((bp + rk) & (TP - 1))];
+            zm[g] = tile[rm * TP + ((bp + rm) & (TP - 1))];
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (bpv[u] < 0) continue;
-            const int bp = bpv[u], k = kv[u], km = N2 - k;
+        for (int g = 0; g < 4; ++g) {
+            const int bp = h * 4 + g;
             const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
             float2 xk, xm;
             if (d0 >= 0) {
-                split_fwd(lo2(zkv[u]), lo2(zmv[u]), wv[u], xk, xm);
+                split_fwd(lo2(zk[g]), lo2(zm[g]), w, xk, xm);
                 p.spec[d0 + k] = xk;
-                if (km != k) p.spec[d0 + km] = xm;
+                if (two) p.spec[d0 + km] = xm;
             }
             if (d1 >= 0) {
-                split_fwd(hi2(zkv[u]), hi2(zmv[u]), wv[u], xk, xm);
+                split_fwd(hi2(zk[g]), hi2(zm[g]), w, xk, xm);
                 p.spec[d1 + k] = xk;
-                if (km != k) p.spec[d1 + km] = xm;
+                if (two) p.spec[d1 + km] = xm;
             }
         }
     }
@@ -1129,6 +1118,41 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
 #endif
 }
 
+// inverse pre-step of one tile: the 8 complex sequences of the 16 lines' pairs from their half spectra.
+// One item = one frequency pair (k, N2 - k) of FOUR line pairs: the table lookups (pos[], twiddle) and the index split
+// are paid once per item, and 16 spectrum loads per thread are in flight before the first is consumed.
+constexpr int XG = 4;     // line pairs per split-step item
+SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* srcoff, int N2) {
+    const int nk = p.nk;
+    SPIM_FOR_ITEMS(i, nk * (TP / XG)) {
+        const int h = fastdiv(i, p.magic_nk);
+        const int k = i - h * nk;
+        const int km = N2 - k;
+        const float2 w = spim_ldg(p.wx + k);
+        const int rk = spim_ldg(p.pos + k);
+        const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
+        const bool two = (k != 0) && (km != k);
+        float2 A0[XG], B0[XG], A1[XG], B1[XG];
+#pragma unroll
+        for (int g = 0; g < XG; ++g) {
+            const int bp = h * XG + g;
+            const long long s0 = srcoff[2 * bp], s1 = srcoff[2 * bp + 1];
+            A0[g] = B0[g] = A1[g] = B1[g] = make_float2(0.f, 0.f);
+            if (s0 >= 0) { A0[g] = ldg_stream(p.spec + s0 + k); B0[g] = ldg_stream(p.spec + s0 + km); }
+            if (s1 >= 0) { A1[g] = ldg_stream(p.spec + s1 + k); B1[g] = ldg_stream(p.spec + s1 + km); }
+        }
+#pragma unroll
+        for (int g = 0; g < XG; ++g) {
+            const int bp = h * XG + g;
+            float2 zk0, zm0, zk1, zm1;
+            split_inv(A0[g], B0[g], w, zk0, zm0);
+            split_inv(A1[g], B1[g], w, zk1, zm1);
+            tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
+            if (two) tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
+        }
+    }
+}
+
 template <int EPI, int MATH>
 struct XInvT {
     typedef XInvParams Params;
@@ -1153,46 +1177,7 @@ struct XInvT {
             srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
         }
         SPIM_BARRIER();
-        // pre-step on line pairs; two items (8 loads) per thread are in flight before any is consumed
-        const int nk = p.nk;
-        const int total = nk * TP;
-        for (int i0 = SPIM_TID; i0 < total; i0 += 2 * SPIM_NTHREADS) {
-            float2 A0[2], B0[2], A1[2], B1[2], wv[2];
-            int bpv[2], kk[2], rkv[2], rmv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = i0 + u * SPIM_NTHREADS;
-                A0[u] = B0[u] = A1[u] = B1[u] = make_float2(0.f, 0.f);
-                wv[u] = make_float2(1.f, 0.f);
-                bpv[u] = -1; kk[u] = 0; rkv[u] = 0; rmv[u] = 0;
-                if (i < total) {
-                    const int bp = fastdiv(i, p.magic_nk);
-                    const int k = i - bp * nk;
-                    bpv[u] = bp; kk[u] = k;
-                    const long long s0 = srcoff[2 * bp], s1 = srcoff[2 * bp + 1];
-                    if (s0 >= 0) { A0[u] = ldg_stream(p.spec + s0 + k); B0[u] = ldg_stream(p.spec + s0 + (N2 - k)); }
-                    if (s1 >= 0) { A1[u] = ldg_stream(p.spec + s1 + k); B1[u] = ldg_stream(p.spec + s1 + (N2 - k)); }
-                    // table lookups issued together with the spectrum loads, not right before their use
-                    wv[u] = spim_ldg(p.wx + k);
-                    rkv[u] = spim_ldg(p.pos + k);
-                    rmv[u] = spim_ldg(p.pos + (k == 0 ? 0 : N2 - k));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (bpv[u] < 0) continue;
-                const int bp = bpv[u], k = kk[u], km = N2 - k;
-                float2 zk0, zm0, zk1, zm1;
-                split_inv(A0[u], B0[u], wv[u], zk0, zm0);
-                split_inv(A1[u], B1[u], wv[u], zk1, zm1);
-                const int rk = rkv[u];
-                tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
-                if (k != 0 && km != k) {
-                    const int rm = rmv[u];
-                    tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
-                }
-            }
-        }
+        xinv_presplit(p, tile, srcoff, N2);
         SPIM_BARRIER();
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
