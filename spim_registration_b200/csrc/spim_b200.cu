@@ -172,8 +172,8 @@ struct HaloFillK {
                 const long long r = idx / ext_[2];
                 c[1] = (int)(r % ext_[1]);
                 c[0] = (int)(r / ext_[1]);
-                // coordinate along the axis (array index), lo side: [0, width), hi side: [origin+n, origin+n+width)
-                const int ai = p.side == 0 ? c[p.axis] : p.origin[p.axis] + p.n[p.axis] + c[p.axis];
+                // coordinate along the axis (array index), lo side: [origin-width, origin), hi side: [origin+n, origin+n+width)
+                const int ai = p.side == 0 ? p.origin[p.axis] - p.width + c[p.axis] : p.origin[p.axis] + p.n[p.axis] + c[p.axis];
                 const int a = ai - p.origin[p.axis];
                 const int e = ext_map(a, p.n[p.axis], p.ext);
                 int d[3] = {c[0], c[1], c[2]};
@@ -690,8 +690,17 @@ static int session_prepare(mvd_session* s) {
     s->plan_ok = true;
     s->dev_bytes += (long long)s->plan.spec_bytes();
     for (int d = 0; d < 3; ++d) {
-        if (s->prm.haloed) { s->pdims[d] = s->n[d] + s->plan.hp[d] + s->plan.hm[d]; s->porigin[d] = s->plan.hm[d]; }
-        else { s->pdims[d] = s->n[d]; s->porigin[d] = 0; }
+        if (s->prm.haloed) {
+            s->porigin[d] = s->plan.hm[d];
+            s->pdims[d] = s->porigin[d] + s->n[d] + s->plan.hp[d];
+            if (d == 2) {
+                // x: keep the brick's first voxel and the row length 8-byte aligned so that the x passes run their
+                // vectorised paths in brick mode too (an odd PSF/2 halo would shift every row by one float)
+                s->porigin[d] += s->porigin[d] & 1;
+                s->pdims[d] = s->porigin[d] + s->n[d] + s->plan.hp[d];
+                s->pdims[d] += s->pdims[d] & 1;
+            }
+        } else { s->pdims[d] = s->n[d]; s->porigin[d] = 0; }
     }
     s->pelems = (long long)s->pdims[0] * s->pdims[1] * s->pdims[2];
     if (!s->d_psi) s->d_psi = (float*)s->dalloc((size_t)s->pelems * sizeof(float));

@@ -227,3 +227,30 @@ def test_randomized_deconvolutions(emu_lib):
         P.decon_case(emu_lib, shape, V, ks, typ, gen, int(rng.integers(1, 4)), lam=float(rng.choice([0.0, 0.006, 0.06])),
                      weight_mode=str(rng.choice(["normalized", "blending", "ones"])), use_weights=bool(rng.integers(0, 2)),
                      osem_index=int(rng.integers(0, 3)) if gen == 1 else 0, seed=int(rng.integers(0, 1000)))
+
+
+@pytest.mark.parametrize("ks", [3, 5, 7])
+def test_brick_mode_without_neighbours_equals_plain_session(emu_lib, ks):
+    """A haloed (brick-mode) session whose every face is a volume face reproduces the plain session bit for bit; odd
+    PSF/2 halos (ks = 3, 7) exercise the even-x-origin padding of the haloed buffers."""
+    from spim_registration_b200 import synthetic
+    from spim_registration_b200.deconvolution import Session
+    shape, V = (10, 12, 14), 2
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, ks)
+    plain, *_ = P.run_session(emu_lib, imgs, ws, psfs, 2, 2, 2)
+    with Session(shape, V, 2, generation=2, haloed=True, lib=emu_lib) as s:
+        for v in range(V):
+            s.set_view(v, imgs[v], ws[v], psfs[v])
+        s.init()
+        part = s.init_partials()
+        s.set_avg(part[0] / part[1], 1.0)
+        s.set_halo_mask(0, 0)
+        ptr, dims, origin = s.device_buffer(0)
+        assert origin[2] % 2 == 0 and dims[2] % 2 == 0 and origin[2] >= s.info().halo_lo[2]
+        for _ in range(2):
+            for v in range(V):
+                s.view_phase(v, 0)
+                s.view_phase(v, 1)
+        s.finish()
+        psi = s.get_psi()
+    assert np.array_equal(plain, psi)
