@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion-leg", action="store_true")
+    ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
     ap.add_argument("--views", type=int, default=None)
     args = ap.parse_args()
@@ -252,6 +253,9 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.fusion_leg_only:
+        print(json.dumps(fusion_prestep_leg(BRICK, VIEWS, peaks()[0])))
         return
 
     tlog("start")
@@ -424,8 +428,14 @@ def main():
     # ---------------- reported extra: the device-side fusion pre-step (never allowed to break the line) ------------
     fusion_leg = None
     if rank == 0 and N == 1 and not args.no_fusion_leg:
+        # in a child process: a fault in this extra can then never take the benchmark line with it
         try:
-            fusion_leg = fusion_prestep_leg(BRICK, VIEWS, peak)
+            cmd = [sys.executable, os.path.abspath(__file__), "--fusion-leg-only", "--views", str(VIEWS),
+                   "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2])]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+            out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            fusion_leg = json.loads(out[-1]) if (r.returncode == 0 and out) else {
+                "error": f"child exited with {r.returncode}: {(r.stderr or '').strip()[-300:]}"}
         except Exception as e:      # noqa: BLE001
             fusion_leg = {"error": f"{type(e).__name__}: {e}"}
         tlog("fusion leg done")

@@ -48,10 +48,13 @@ typedef struct mvd_params {
     int exact_tikhonov;    /* 0 (default): Tikhonov step in the algebraically identical, cancellation-free fp32 form
                               2v/(1+sqrt(1+2*lambda*v)) (<= 2 ulp from the reference's fp64 expression);
                               1: evaluate (sqrt(1+2*lambda*v)-1)/lambda in fp64 exactly like the Java code */
-    int fast_epilogue;     /* 0 (default): IEEE fp32 division / square root in the fused ratio and update epilogues;
-                              1: branch-free refinement of the hardware approximations -- the same correctly rounded values
-                              for operands in the normal range, NaN instead of 0 / infinity for zero, denormal or infinite
-                              operands (csrc/fast_math.h) */
+    int fast_epilogue;     /* 1 (set by mvd_params_default): division / square root of the fused ratio and update epilogues as a
+                              branch-free FMA refinement of the hardware approximations (csrc/fast_math.h) -- the correctly
+                              rounded IEEE values for operands in the normal range; the update step as a whole is identical to
+                              the IEEE evaluation for EVERY input below 2^126 (tests/cpp/fast_epilogue_composite.cpp, exhaustive);
+                              a blurred value that is zero, denormal or infinite gives a NaN quotient where IEEE gives +-inf / 0
+                              (both poison the next FFT convolution, in the reference too);
+                              0: IEEE fp32 division / square root intrinsics.  SPIM_FAST_EPI=0/1 overrides either way */
     int reserved[6];
 } mvd_params;
 

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "spim_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("spim_b200.cu", "engine.h", "kernels.h", "fft_math.h", "hd.h", "runtime.h", "fusion.h", "fusion_api.h")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("spim_b200.cu", "engine.h", "kernels.h", "fft_math.h", "fast_math.h", "hd.h", "runtime.h", "fusion.h", "fusion_api.h")] + \
        [os.path.join(HERE, "..", "include", f) for f in ("spim_fftconv.h", "spim_mvdecon.h", "spim_fusion.h")]
 OUT = os.path.join(HERE, "libConvolution3D_fftCUDAlib.so")
 ALIAS = os.path.join(HERE, "libFourierConvolutionCUDALib.so")

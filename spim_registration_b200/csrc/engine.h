@@ -182,7 +182,7 @@ struct EpiDesc {            // what XInv does with the result
     float min_value = 1e-4f;
     int gen2_quotient = 1;
     int exact_tikhonov = 0;
-    int fast_epilogue = 0;
+    int fast_epilogue = 1;
     double* stat_sum = nullptr;
     unsigned int* stat_max = nullptr;
 };
@@ -403,8 +403,8 @@ public:
         p.lambda = e.lambda; p.min_value = e.min_value; p.gen2_quotient = e.gen2_quotient;
         p.two_lambda = (float)(2.0 * e.lambda);
         p.exact_tikhonov = e.exact_tikhonov;
-        static int fast_env = env_int("SPIM_FAST_EPI", 0);       // A/B switch for the benchmarks
-        p.fast_epilogue = (e.fast_epilogue || fast_env) ? 1 : 0;
+        static int fast_env = env_int("SPIM_FAST_EPI", -1);      // A/B switch for the benchmarks: 0 / 1 override the parameter
+        p.fast_epilogue = fast_env >= 0 ? (fast_env ? 1 : 0) : (e.fast_epilogue ? 1 : 0);
         p.stat_sum = e.stat_sum; p.stat_max = e.stat_max;
         auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
         p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);

@@ -586,6 +586,7 @@ void mvd_params_default(mvd_params* p) {
     p->conv2_ext = -1;
     p->device = 0;
     p->haloed = 0;
+    p->fast_epilogue = 1;
 }
 
 int mvd_session_create(const mvd_params* p, mvd_session** out) {

@@ -43,7 +43,7 @@ class Session:
     def __init__(self, dims: Sequence[int], num_views: int, iteration_type: int, generation: int = 2,
                  lam: float = 0.006, osem_speedup: float = 1.0, osem_index: int = 0, device: int = 0,
                  conv1_ext: int = -1, conv2_ext: int = -1, haloed: bool = False, min_value: float = 0.0001,
-                 exact_tikhonov: bool = False, fast_epilogue: bool = False, lib: Optional[C.CDLL] = None):
+                 exact_tikhonov: bool = False, fast_epilogue: Optional[bool] = None, lib: Optional[C.CDLL] = None):
         self.lib = lib or native.load_library()
         p = native.MvdParams()
         self.lib.mvd_params_default(C.byref(p))
@@ -60,7 +60,8 @@ class Session:
         p.device = int(device)
         p.haloed = 1 if haloed else 0
         p.exact_tikhonov = 1 if exact_tikhonov else 0
-        p.fast_epilogue = 1 if fast_epilogue else 0
+        if fast_epilogue is not None:           # None = the library default (on, see spim_mvdecon.h)
+            p.fast_epilogue = 1 if fast_epilogue else 0
         self.dims = tuple(int(d) for d in dims)
         self.num_views = int(num_views)
         self.psf_dims: List[tuple] = [()] * self.num_views
