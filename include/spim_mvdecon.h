@@ -127,6 +127,29 @@ int mvd_halo_unpack(mvd_session* s, int which, int npieces, const int* regions, 
 /* fill the halo faces flagged in lo_mask / hi_mask (bit d = axis d of (z,y,x)) of buffer `which`
  * from the brick's own interior using the convolution's out-of-bounds rule (volume faces) */
 int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask);
+/* Direct halo push (the exchange as ONE fused copy + signal kernel over NVLink peer memory -- no staging buffer, no
+ * NCCL call on the data path; replaces the 3-phase ncclSend/ncclRecv plan of SURVEY.md section 8e):
+ *   mvd_p2p_export   after mvd_init: a 288-byte record (process id, device, pointers and CUDA IPC handles of the psi
+ *                    buffer, the ratio buffer and a flag page) for the other ranks of the node; the caller all-gathers it
+ *   mvd_p2p_connect  per neighbour piece i: the neighbour's record; boxes[i] = 9 ints (z0, y0, x0 of the box in MY
+ *                    buffer, nz, ny, nx, z0, y0, x0 of the same box in the NEIGHBOUR's halo -- all bricks share one
+ *                    geometry); slots[i] = 2 ints in [0, 27): the flag I raise at the neighbour, the flag it raises here
+ *                    (by convention (dz+1)*9 + (dy+1)*3 + (dx+1) of the sender as seen from the receiver).  Same-process
+ *                    peers are reached through their raw pointers (peer access is enabled), others through the IPC handles
+ *   mvd_p2p_push     asynchronous on the session stream: store every piece of buffer `which` into the neighbours' halos,
+ *                    then raise this buffer's next epoch flag at each neighbour (system-scope release)
+ *   mvd_p2p_wait     asynchronous: a one-block kernel that spins (system-scope acquire) until every neighbour has raised
+ *                    the same epoch here; after SPIM_P2P_TIMEOUT_S (30) seconds it gives up and sets an error word
+ *   mvd_p2p_status   synchronous: *timed_out = 1 if any wait gave up (results are then invalid)
+ * Pushes of the two buffers must alternate between two pushes of the same buffer (they do in an iteration: psi, ratio,
+ * psi, ...) or be separated by a barrier across ranks -- that is what makes overwriting a neighbour's halo safe. */
+#define MVD_P2P_RECORD_BYTES 288
+int mvd_p2p_export(mvd_session* s, unsigned char record[MVD_P2P_RECORD_BYTES]);
+int mvd_p2p_connect(mvd_session* s, int npieces, const unsigned char* records, const int* boxes, const int* slots);
+int mvd_p2p_push(mvd_session* s, int which);
+int mvd_p2p_wait(mvd_session* s, int which);
+int mvd_p2p_status(mvd_session* s, int* timed_out);
+int mvd_p2p_disconnect(mvd_session* s);
 /* one half of a view-step: phase 0 = conv1 + quotient, phase 1 = conv2 + update.
  * stats: optional 2 doubles (sum, max) accumulated for phase 1. */
 int mvd_view_phase(mvd_session* s, int view, int phase, double* stats);

@@ -76,6 +76,8 @@ class BrickRunner:
         self.session = Session(brick, num_views, iteration_type, generation=generation, lam=lam,
                                osem_speedup=osem_speedup, device=device, haloed=self.haloed, lib=lib)
         self._bufs = None
+        self.use_pack = False
+        self.use_p2p = False
         self._tmp = {}
         self._graph = None
         self._graph_failed = False
@@ -173,35 +175,44 @@ class BrickRunner:
             return None
         return coords_rank(c, self.grid)
 
+    def _boxes(self, off):
+        """(send, recv) slices of my haloed buffers for the neighbour at offset ``off`` in {-1,0,1}^3 (z, y, x), or None when
+        a halo involved has zero width.  Every brick has the same geometry, so the same formula describes any rank."""
+        n = self.session.dims
+        _, dims, origin = self._bufs[0]
+        send, recv = [], []
+        for d in range(3):
+            o, wlo, whi = origin[d], self.halo_lo[d], self.halo_hi[d]
+            if off[d] == 0:
+                send.append(slice(o, o + n[d])); recv.append(slice(o, o + n[d]))
+            elif off[d] < 0:       # neighbour below: it needs my first `whi` interior cells; I get its last `wlo`
+                if whi == 0 or wlo == 0:
+                    return None
+                send.append(slice(o, o + whi)); recv.append(slice(o - wlo, o))
+            else:                   # neighbour above: it needs my last `wlo` interior cells; I get its first `whi`
+                if whi == 0 or wlo == 0:
+                    return None
+                send.append(slice(o + n[d] - wlo, o + n[d])); recv.append(slice(o + n[d], o + n[d] + whi))
+        return tuple(send), tuple(recv)
+
     def _plan_exchange(self):
         """Neighbour list for the one-shot exchange: every existing neighbour at offset (dz,dy,dx) in
         {-1,0,1}^3 gets the interior cells it needs (face, edge or corner piece) and sends back the
         matching piece for my halo.  Volume faces need nothing: the convolution loader applies the
         out-of-bounds rule there (mvd_set_halo_mask)."""
         import itertools
-        n = self.session.dims
-        _, dims, origin = self._bufs[0]
-        plan = []
+        plan, offs = [], []
         for off in itertools.product((-1, 0, 1), repeat=3):
             if off == (0, 0, 0):
                 continue
             c = [self.coords[d] + off[d] for d in range(3)]
             if any(c[d] < 0 or c[d] >= self.grid[d] for d in range(3)):
                 continue
-            send, recv = [], []
-            empty = False
-            for d in range(3):
-                o, wlo, whi = origin[d], self.halo_lo[d], self.halo_hi[d]
-                if off[d] == 0:
-                    send.append(slice(o, o + n[d])); recv.append(slice(o, o + n[d]))
-                elif off[d] < 0:       # neighbour below: it needs my first `whi` interior cells; I get its last `wlo`
-                    send.append(slice(o, o + whi)); recv.append(slice(o - wlo, o))
-                    empty = empty or whi == 0 or wlo == 0
-                else:                   # neighbour above: it needs my last `wlo` interior cells; I get its first `whi`
-                    send.append(slice(o + n[d] - wlo, o + n[d])); recv.append(slice(o + n[d], o + n[d] + whi))
-                    empty = empty or whi == 0 or wlo == 0
-            if not empty:
-                plan.append((coords_rank(c, self.grid), tuple(send), tuple(recv)))
+            b = self._boxes(off)
+            if b is not None:
+                plan.append((coords_rank(c, self.grid), b[0], b[1]))
+                offs.append(off)
+        self._xoffs = offs
         self._xplan = plan
         # flat staging buffers for the single-launch pack / unpack path
         import torch
@@ -221,43 +232,100 @@ class BrickRunner:
         self.session.set_halo_mask(lo_mask, hi_mask)
         self.use_pack = os.environ.get("SPIM_BRICK_PACK", "1") != "0"
         if self.use_pack and plan and self.dist is not None:
-            self._verify_pack_path()
+            self.use_pack = self._verify_mode("pack")
+            if not self.use_pack and self.rank == 0:
+                print("[bricks] halo exchange: using slab copies (pack-path self-check failed)", flush=True)
+        # direct halo push over NVLink peer memory (mvd_p2p_*): opt-in until it has been timed on hardware
+        self.use_p2p = False
+        self._p2p_last = None
+        if os.environ.get("SPIM_BRICK_P2P", "0") == "1" and plan and self.dist is not None:
+            self._setup_p2p()
 
-    def _verify_pack_path(self):
-        """One-time self-check: the single-launch pack / unpack exchange must reproduce the halo the plain
-        slab-copy exchange produces, bit for bit, on every rank -- otherwise all ranks fall back together."""
+    def _setup_p2p(self):
+        """Exchange the export records, connect every neighbour piece, and adopt the push path only if EVERY rank connected
+        and the pushed halos equal the slab-copy exchange bit for bit (otherwise all ranks stay on the NCCL path)."""
+        import torch
+        s = self.session
+        dev = "cpu" if self.cpu else torch.device("cuda", self.device)
+        ok = True
+        try:
+            rec = s.p2p_export()
+        except Exception as e:                    # noqa: BLE001
+            rec, ok = bytes(s.P2P_RECORD_BYTES), False
+            if self.rank == 0:
+                print(f"[bricks] direct halo push unavailable ({type(e).__name__}: {e})", flush=True)
+        mine = torch.tensor(list(rec), dtype=torch.uint8, device=dev)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(every, mine)
+        if ok:
+            try:
+                slot = lambda o: (o[0] + 1) * 9 + (o[1] + 1) * 3 + (o[2] + 1)
+                records, boxes, slots = [], [], []
+                for (peer, ssl, _), off in zip(self._xplan, self._xoffs):
+                    neg = tuple(-o for o in off)
+                    dst = self._boxes(neg)[1]                  # where the neighbour receives what comes from my direction
+                    records.append(bytes(every[peer].cpu().numpy().tobytes()))
+                    boxes.append([sl.start for sl in ssl] + [sl.stop - sl.start for sl in ssl] + [sl.start for sl in dst])
+                    slots.append((slot(neg), slot(off)))
+                s.p2p_connect(records, boxes, slots)
+            except Exception as e:                # noqa: BLE001
+                ok = False
+                if self.rank == 0:
+                    print(f"[bricks] direct halo push unavailable ({type(e).__name__}: {e})", flush=True)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            return
+        self.use_p2p = self._verify_mode("p2p")
+        if self.rank == 0:
+            print("[bricks] halo exchange: direct push over peer memory" if self.use_p2p else
+                  "[bricks] halo exchange: direct-push self-check failed, staying on the NCCL path", flush=True)
+
+    def _verify_mode(self, mode: str) -> bool:
+        """One-time self-check of an exchange path ("pack": single-launch pack / unpack around one NCCL batch; "p2p": direct
+        push over peer memory): it must reproduce the halo the plain slab-copy exchange produces, bit for bit, on every
+        rank -- otherwise all ranks fall back together."""
         import torch
         t = self._bufs[1][0]                      # the ratio buffer is scratch at this point
         keep = t.clone()
-        g = torch.Generator(device=t.device).manual_seed(1234 + self.rank)
-        t.copy_(torch.rand(t.shape, generator=g, device=t.device, dtype=t.dtype))
-        filled = t.clone()
+        if self.cpu:
+            g = torch.Generator().manual_seed(1234 + self.rank)
+            fill = torch.rand(t.shape, generator=g, dtype=t.dtype)
+        else:
+            g = torch.Generator(device=t.device).manual_seed(1234 + self.rank)
+            fill = torch.rand(t.shape, generator=g, device=t.device, dtype=t.dtype)
+        t.copy_(fill)
+        saved = (self.use_pack, self.use_p2p)
         ok = True
         try:
             # torch fills the buffer on ITS current stream; the exchange runs on the session's (non-blocking) stream:
             # synchronise the device between the two, or the exchange may pack the buffer before it is filled
             self._sync_stream()
-            self.use_pack = False
+            self.use_pack, self.use_p2p = False, False
             self.exchange(1)
             self._sync_stream()
             want = t.clone()
-            t.copy_(filled)
+            t.copy_(fill)
             self._sync_stream()
-            self.use_pack = True
+            self.dist.barrier()                   # nobody may push into a halo its owner is still reading
+            self.use_pack, self.use_p2p = (mode == "pack"), (mode == "p2p")
             self.exchange(1)
             self._sync_stream()
             ok = bool(torch.equal(t, want))
+            if mode == "p2p" and self.session.p2p_timed_out():
+                ok = False
         except Exception as e:                    # argument / launch errors surface before any NCCL call is posted
             ok = False
             if self.rank == 0:
-                print(f"[bricks] pack path unavailable ({type(e).__name__}: {e})", flush=True)
+                print(f"[bricks] {mode} path unavailable ({type(e).__name__}: {e})", flush=True)
+        self.use_pack, self.use_p2p = saved
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=t.device)
         self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
-        self.use_pack = bool(int(flag.item()))
-        if not self.use_pack and self.rank == 0:
-            print("[bricks] halo exchange: using slab copies (pack-path self-check failed)", flush=True)
+        self.dist.barrier()
         t.copy_(keep)
         self._sync_stream()
+        self._p2p_last = None
+        return bool(int(flag.item()))
 
     def _sync_stream(self):
         self.session.sync()
@@ -271,6 +339,17 @@ class BrickRunner:
         import torch
         t, dims, origin = self._bufs[which]
         if not self._xplan:
+            return
+        if self.use_p2p:
+            # one fused copy + signal kernel into the neighbours' halos, one wait kernel; nothing else.  Pushes of the two
+            # buffers alternate inside an iteration, which is what orders a push after the neighbour's last read of that
+            # halo; anything else (two pushes of one buffer in a row) is separated by a barrier across ranks.
+            if self._p2p_last == which:
+                self._sync_stream()
+                self.dist.barrier()
+            self._p2p_last = which
+            self.session.p2p_push(which)
+            self.session.p2p_wait(which)
             return
         if self.use_pack:
             # one gather kernel, one NCCL batch on slices of the flat buffers, one scatter kernel
@@ -361,12 +440,16 @@ class BrickRunner:
         if not self.cpu:
             import torch
             torch.cuda.current_stream().synchronize()
+        if self.use_p2p and self.session.p2p_timed_out():
+            raise RuntimeError("direct halo push: a neighbour's halo did not arrive within SPIM_P2P_TIMEOUT_S seconds")
         return None
 
     def extra_launches_per_iteration(self) -> int:
         if not self.haloed:
             return 0
-        return 4 * self.num_views if getattr(self, "use_pack", False) else 0    # pack + unpack per exchange
+        if getattr(self, "use_p2p", False) or getattr(self, "use_pack", False):
+            return 4 * self.num_views        # push + wait, or pack + unpack, per exchange; two exchanges per view-step
+        return 0
 
     def finish(self):
         self.session.finish()
@@ -381,4 +464,11 @@ class BrickRunner:
             torch.cuda.synchronize()
             self._graph = None
         self._bufs = None
+        if getattr(self, "use_p2p", False):
+            # nobody unmaps or frees a buffer a neighbour may still be pushing into
+            self._sync_stream()
+            self.dist.barrier()
+            self.session.p2p_disconnect()
+            self.dist.barrier()
+            self.use_p2p = False
         self.session.close()

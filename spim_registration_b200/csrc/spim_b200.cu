@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <time.h>
+#include <unistd.h>
 #include <map>
 #include <array>
 
@@ -216,6 +218,103 @@ struct HaloPackK {
     }
 };
 
+// brick mode, direct halo push (fused copy + signal over peer memory, no staging buffer and no NCCL on the data path):
+// up to 26 box-shaped pieces of MY buffer are stored straight into the neighbours' halos through their peer-mapped
+// (CUDA IPC / NVLink) buffers; the last block to finish raises this buffer's epoch flag at every neighbour with a
+// system-scope release store.  All bricks share one geometry, so a destination is (peer base pointer, box origin).
+struct HaloPushK {
+    struct Params {
+        const float* buf; int dims[3]; int npieces; int nblocks;
+        float* dst[MAX_PIECES];            // base of the neighbour's buffer
+        unsigned int* flag[MAX_PIECES];    // the neighbour's flag word for (this buffer, my direction)
+        int lo[MAX_PIECES][3]; int dlo[MAX_PIECES][3]; int ext[MAX_PIECES][3]; long long off[MAX_PIECES + 1];
+        unsigned int* done;                // my block counter
+        unsigned int* epoch;               // my push counter for this buffer
+    };
+    SPIM_DEV static void run(const Params& p, int bid, float2*) {
+        const long long total = p.off[p.npieces];
+        for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
+            SPIM_FOR_ITEMS(i, kChunk) {
+                const long long idx = base + i;
+                if (idx >= total) continue;
+                int pc = 0;
+                while (pc + 1 < p.npieces && idx >= p.off[pc + 1]) ++pc;
+                long long r = idx - p.off[pc];
+                const int x = (int)(r % p.ext[pc][2]); r /= p.ext[pc][2];
+                const int y = (int)(r % p.ext[pc][1]);
+                const int z = (int)(r / p.ext[pc][1]);
+                const long long a = ((long long)(z + p.lo[pc][0]) * p.dims[1] + (y + p.lo[pc][1])) * p.dims[2] + x + p.lo[pc][2];
+                const long long b = ((long long)(z + p.dlo[pc][0]) * p.dims[1] + (y + p.dlo[pc][1])) * p.dims[2] + x + p.dlo[pc][2];
+                p.dst[pc][b] = p.buf[a];
+            }
+        }
+#if defined(SPIM_HOST_EMU)
+        if (bid == p.nblocks - 1) {        // blocks run in order: every piece has been written
+            const unsigned int e = *p.epoch + 1u;
+            *p.epoch = e;
+            for (int i = 0; i < p.npieces; ++i) __atomic_store_n(p.flag[i], e, __ATOMIC_RELEASE);
+        }
+#else
+        __threadfence_system();            // my stores are visible system-wide ...
+        __syncthreads();                   // ... before thread 0 counts this block as done
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(p.done, 1u);
+            if (t == (unsigned int)p.nblocks - 1u) {
+                *p.done = 0u;              // ready for the next launch (stream order)
+                __threadfence_system();
+                const unsigned int e = *p.epoch + 1u;
+                *p.epoch = e;
+                for (int i = 0; i < p.npieces; ++i)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag[i]), "r"(e) : "memory");
+            }
+        }
+#endif
+    }
+};
+
+// the matching wait: one thread per neighbour spins (system-scope acquire loads) until that neighbour's flag has reached
+// my own epoch for this buffer -- every rank pushes the same sequence, so equal epochs pair up.  A timeout raises an
+// error word instead of hanging the GPU.
+struct HaloWaitK {
+    struct Params {
+        unsigned int* flags; int nslots; int slot[MAX_PIECES]; const unsigned int* epoch; unsigned int* err;
+        unsigned long long timeout_ns;
+    };
+    SPIM_DEV static void run(const Params& p, int, float2*) {
+#if defined(SPIM_HOST_EMU)
+        const unsigned int want = *p.epoch;
+        for (int i = 0; i < p.nslots; ++i) {
+            struct timespec t0, t1;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            while ((int)(__atomic_load_n(p.flags + p.slot[i], __ATOMIC_ACQUIRE) - want) < 0) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                const double ns = (double)(t1.tv_sec - t0.tv_sec) * 1e9 + (double)(t1.tv_nsec - t0.tv_nsec);
+                if (ns > (double)p.timeout_ns) { __atomic_fetch_or(p.err, 1u, __ATOMIC_RELAXED); break; }
+                struct timespec nap = {0, 50000};
+                nanosleep(&nap, nullptr);
+            }
+        }
+#else
+        const int i = (int)threadIdx.x;
+        if (i < p.nslots) {
+            const unsigned int want = *p.epoch;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                unsigned int f;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(p.flags + p.slot[i]) : "memory");
+                if ((int)(f - want) >= 0) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > p.timeout_ns) { atomicOr(p.err, 1u); break; }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+#endif
+    }
+};
+
 inline int ew_blocks(long long n) {
     long long b = (n + kChunk - 1) / kChunk;
     const long long cap = 148LL * 16;
@@ -397,6 +496,18 @@ struct mvd_session {
     bool virtual_weights = false, wn_valid = false;
     int wn_min = 0;
     double wn_avg = 0.0;
+    // brick mode, direct halo push over peer memory (mvd_p2p_*)
+    struct P2P {
+        unsigned int* d_ctl = nullptr;     // words [0,64) flags[buffer][slot], [64] block counter, [65,66] epochs, [67] error
+        bool connected = false;
+        int npieces = 0;
+        float* peer_buf[2][MAX_PIECES];
+        unsigned int* peer_ctl[MAX_PIECES];
+        int lo[MAX_PIECES][3], dlo[MAX_PIECES][3], ext[MAX_PIECES][3];
+        int slot_there[MAX_PIECES], slot_here[MAX_PIECES];
+        std::vector<void*> opened;         // cudaIpcOpenMemHandle mappings to close
+        long long pushes[2] = {0, 0}, waits[2] = {0, 0};
+    } p2p;
 
     int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
     int conv2_ext() const { return prm.conv2_ext >= 0 ? prm.conv2_ext : (prm.generation == 2 ? EXT_CONSTANT : EXT_MIRROR_SINGLE); }
@@ -558,6 +669,15 @@ struct mvd_session {
     }
 };
 
+static void p2p_disconnect(mvd_session* s) {
+#if !defined(SPIM_HOST_EMU)
+    for (void* q : s->p2p.opened) cudaIpcCloseMemHandle(q);
+#endif
+    s->p2p.opened.clear();
+    s->p2p.connected = false;
+    s->p2p.npieces = 0;
+}
+
 // ================================================================================================
 // session C ABI
 // ================================================================================================
@@ -627,6 +747,8 @@ void mvd_session_destroy(mvd_session* s) {
         rt::dfree(s->d_psi); rt::dfree(s->d_tmp);
         rt::dfree(s->d_stat_sum); rt::dfree(s->d_stat_max);
         rt::dfree(s->d_stack); rt::dfree(s->d_lut); rt::dfree(s->d_sumw);
+        p2p_disconnect(s);
+        rt::dfree(s->p2p.d_ctl);
         if (s->plan_ok) s->plan.destroy();
         rt::stream_destroy(s->stream);
     } catch (...) {}
@@ -1050,6 +1172,191 @@ int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask) {
             rt::launch<HaloFillK>(p, p.nblocks, kThreads, 0, s->stream);
         }
     }
+    return 0;
+    SPIM_API_END
+}
+
+// ---- direct halo push over peer memory (NVLink / CUDA IPC) -------------------------------------
+struct P2PBlob {               // 96 bytes: how another rank reaches one of my device buffers
+    char magic[8];             // "SPIMP2P1"
+    int pid, device;
+    unsigned long long ptr;    // valid inside the exporting process
+    unsigned char ipc[64];     // cudaIpcMemHandle_t, valid in every other process of the node
+    unsigned char pad[8];
+};
+static_assert(sizeof(P2PBlob) == 96, "P2PBlob layout");
+constexpr size_t kCtlBytes = 2u << 20;   // a whole 2 MiB page: an IPC mapping never exposes anything else
+
+static void p2p_fill_blob(P2PBlob& b, int device, void* ptr) {
+    memset(&b, 0, sizeof(b));
+    memcpy(b.magic, "SPIMP2P1", 8);
+    b.pid = (int)getpid();
+    b.device = device;
+    b.ptr = (unsigned long long)(uintptr_t)ptr;
+#if !defined(SPIM_HOST_EMU)
+    cudaIpcMemHandle_t h;
+    SPIM_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    memcpy(b.ipc, &h, 64);
+#endif
+}
+
+static void* p2p_resolve(mvd_session* s, const P2PBlob& b) {
+    if (memcmp(b.magic, "SPIMP2P1", 8) != 0) throw rt::Error("mvd_p2p_connect: bad peer record");
+    if (b.pid == (int)getpid()) {
+#if !defined(SPIM_HOST_EMU)
+        if (b.device != s->prm.device) {
+            int can = 0;
+            SPIM_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, s->prm.device, b.device));
+            if (!can) throw rt::Error("mvd_p2p_connect: no peer access between devices " + std::to_string(s->prm.device) + " and " + std::to_string(b.device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw rt::Error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+#endif
+        return (void*)(uintptr_t)b.ptr;
+    }
+#if defined(SPIM_HOST_EMU)
+    (void)s;
+    throw rt::Error("mvd_p2p_connect: the peer lives in another process (the emulator has no shared device memory)");
+#else
+    cudaIpcMemHandle_t h;
+    memcpy(&h, b.ipc, 64);
+    void* q = nullptr;
+    SPIM_CUDA_CHECK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    s->p2p.opened.push_back(q);
+    return q;
+#endif
+}
+
+int mvd_p2p_export(mvd_session* s, unsigned char record[MVD_P2P_RECORD_BYTES]) {
+    SPIM_API_BEGIN
+    if (!s || !record) return fail("mvd_p2p_export: null argument");
+    if (!s->prm.haloed || !s->d_psi || !s->d_tmp) return fail("mvd_p2p_export: not a brick-mode session / not initialised (mvd_init)");
+    rt::set_device(s->prm.device);
+    if (!s->p2p.d_ctl) {
+        s->p2p.d_ctl = (unsigned int*)rt::dmalloc(kCtlBytes);
+        rt::dzero(s->p2p.d_ctl, kCtlBytes, s->stream);
+        rt::stream_sync(s->stream);
+    }
+    P2PBlob b[3];
+    p2p_fill_blob(b[0], s->prm.device, s->d_psi);
+    p2p_fill_blob(b[1], s->prm.device, s->d_tmp);
+    p2p_fill_blob(b[2], s->prm.device, s->p2p.d_ctl);
+    static_assert(sizeof(b) == MVD_P2P_RECORD_BYTES, "record size");
+    memcpy(record, b, sizeof(b));
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_p2p_connect(mvd_session* s, int npieces, const unsigned char* records, const int* boxes, const int* slots) {
+    SPIM_API_BEGIN
+    if (!s || !records || !boxes || !slots) return fail("mvd_p2p_connect: null argument");
+    if (!s->p2p.d_ctl) return fail("mvd_p2p_connect: call mvd_p2p_export first");
+    if (npieces < 1 || npieces > MAX_PIECES) return fail("mvd_p2p_connect: piece count out of range");
+    rt::set_device(s->prm.device);
+    p2p_disconnect(s);
+    mvd_session::P2P& q = s->p2p;
+    try {
+        for (int i = 0; i < npieces; ++i) {
+            P2PBlob b[3];
+            memcpy(b, records + (size_t)i * MVD_P2P_RECORD_BYTES, sizeof(b));
+            q.peer_buf[0][i] = (float*)p2p_resolve(s, b[0]);
+            q.peer_buf[1][i] = (float*)p2p_resolve(s, b[1]);
+            q.peer_ctl[i] = (unsigned int*)p2p_resolve(s, b[2]);
+            for (int d = 0; d < 3; ++d) {
+                q.lo[i][d] = boxes[i * 9 + d]; q.ext[i][d] = boxes[i * 9 + 3 + d]; q.dlo[i][d] = boxes[i * 9 + 6 + d];
+                if (q.ext[i][d] < 1 || q.lo[i][d] < 0 || q.dlo[i][d] < 0 || q.lo[i][d] + q.ext[i][d] > s->pdims[d] ||
+                    q.dlo[i][d] + q.ext[i][d] > s->pdims[d])
+                    throw rt::Error("mvd_p2p_connect: box out of range");
+            }
+            q.slot_there[i] = slots[i * 2]; q.slot_here[i] = slots[i * 2 + 1];
+            if ((unsigned)q.slot_there[i] >= 27u || (unsigned)q.slot_here[i] >= 27u) throw rt::Error("mvd_p2p_connect: flag slot out of range");
+        }
+    } catch (...) {
+        p2p_disconnect(s);
+        throw;
+    }
+    q.npieces = npieces;
+    q.connected = true;
+    q.pushes[0] = q.pushes[1] = q.waits[0] = q.waits[1] = 0;
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_p2p_push(mvd_session* s, int which) {
+    SPIM_API_BEGIN
+    if (!s || (which != 0 && which != 1)) return fail("mvd_p2p_push: bad argument");
+    if (!s->p2p.connected) return fail("mvd_p2p_push: not connected (mvd_p2p_connect)");
+    if (s->p2p.pushes[which] != s->p2p.waits[which]) return fail("mvd_p2p_push: the previous push of this buffer has not been waited for");
+    rt::set_device(s->prm.device);
+    const mvd_session::P2P& q = s->p2p;
+    HaloPushK::Params p;
+    memset(&p, 0, sizeof(p));
+    p.buf = which == 0 ? s->d_psi : s->d_tmp;
+    for (int d = 0; d < 3; ++d) p.dims[d] = s->pdims[d];
+    p.npieces = q.npieces;
+    long long off = 0;
+    for (int i = 0; i < q.npieces; ++i) {
+        p.dst[i] = q.peer_buf[which][i];
+        p.flag[i] = q.peer_ctl[i] + which * 32 + q.slot_there[i];
+        p.off[i] = off;
+        long long n = 1;
+        for (int d = 0; d < 3; ++d) { p.lo[i][d] = q.lo[i][d]; p.dlo[i][d] = q.dlo[i][d]; p.ext[i][d] = q.ext[i][d]; n *= q.ext[i][d]; }
+        off += n;
+    }
+    p.off[q.npieces] = off;
+    p.nblocks = ew_blocks(off);
+    p.done = s->p2p.d_ctl + 64;
+    p.epoch = s->p2p.d_ctl + 65 + which;
+    rt::launch<HaloPushK>(p, p.nblocks, kThreads, 0, s->stream);
+    s->p2p.pushes[which] += 1;
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_p2p_wait(mvd_session* s, int which) {
+    SPIM_API_BEGIN
+    if (!s || (which != 0 && which != 1)) return fail("mvd_p2p_wait: bad argument");
+    if (!s->p2p.connected) return fail("mvd_p2p_wait: not connected (mvd_p2p_connect)");
+    if (s->p2p.pushes[which] != s->p2p.waits[which] + 1) return fail("mvd_p2p_wait: no outstanding push of this buffer");
+    rt::set_device(s->prm.device);
+    const mvd_session::P2P& q = s->p2p;
+    HaloWaitK::Params p;
+    memset(&p, 0, sizeof(p));
+    p.flags = s->p2p.d_ctl + which * 32;
+    p.nslots = q.npieces;
+    for (int i = 0; i < q.npieces; ++i) p.slot[i] = q.slot_here[i];
+    p.epoch = s->p2p.d_ctl + 65 + which;
+    p.err = s->p2p.d_ctl + 67;
+    static int timeout_ms = env_int("SPIM_P2P_TIMEOUT_S", 30) * 1000;
+    p.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+    rt::launch<HaloWaitK>(p, 1, 32, 0, s->stream);
+    s->p2p.waits[which] += 1;
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_p2p_status(mvd_session* s, int* timed_out) {
+    SPIM_API_BEGIN
+    if (!s || !timed_out) return fail("mvd_p2p_status: null argument");
+    *timed_out = 0;
+    if (!s->p2p.d_ctl) return 0;
+    rt::set_device(s->prm.device);
+    unsigned int e = 0;
+    rt::d2h(&e, s->p2p.d_ctl + 67, sizeof(e), s->stream);
+    rt::stream_sync(s->stream);
+    *timed_out = e ? 1 : 0;
+    return 0;
+    SPIM_API_END
+}
+
+int mvd_p2p_disconnect(mvd_session* s) {
+    SPIM_API_BEGIN
+    if (!s) return fail("mvd_p2p_disconnect: null session");
+    rt::set_device(s->prm.device);
+    rt::stream_sync(s->stream);
+    p2p_disconnect(s);
     return 0;
     SPIM_API_END
 }

@@ -187,6 +187,39 @@ class Session:
         fn = self.lib.mvd_halo_unpack if unpack else self.lib.mvd_halo_pack
         native.check(self.lib, fn(self._h, which, n, arr, C.c_void_p(flat_ptr)), "mvd_halo_unpack" if unpack else "mvd_halo_pack")
 
+    # direct halo push over peer memory (spim_mvdecon.h, mvd_p2p_*)
+    P2P_RECORD_BYTES = 288
+
+    def p2p_export(self) -> bytes:
+        rec = (C.c_ubyte * self.P2P_RECORD_BYTES)()
+        native.check(self.lib, self.lib.mvd_p2p_export(self._h, rec), "mvd_p2p_export")
+        return bytes(rec)
+
+    def p2p_connect(self, records: Sequence[bytes], boxes, slots):
+        """records[i]: the neighbour's export record; boxes[i] = (z0, y0, x0, nz, ny, nx, dz0, dy0, dx0); slots[i] =
+        (flag raised at the neighbour, flag the neighbour raises here)."""
+        n = len(records)
+        blob = b"".join(records)
+        assert len(blob) == n * self.P2P_RECORD_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        barr = (C.c_int * (9 * n))(*[int(v) for b in boxes for v in b])
+        sarr = (C.c_int * (2 * n))(*[int(v) for s_ in slots for v in s_])
+        native.check(self.lib, self.lib.mvd_p2p_connect(self._h, n, buf, barr, sarr), "mvd_p2p_connect")
+
+    def p2p_push(self, which: int):
+        native.check(self.lib, self.lib.mvd_p2p_push(self._h, which), "mvd_p2p_push")
+
+    def p2p_wait(self, which: int):
+        native.check(self.lib, self.lib.mvd_p2p_wait(self._h, which), "mvd_p2p_wait")
+
+    def p2p_timed_out(self) -> bool:
+        t = C.c_int(0)
+        native.check(self.lib, self.lib.mvd_p2p_status(self._h, C.byref(t)), "mvd_p2p_status")
+        return bool(t.value)
+
+    def p2p_disconnect(self):
+        native.check(self.lib, self.lib.mvd_p2p_disconnect(self._h), "mvd_p2p_disconnect")
+
     def fill_halo(self, which: int, lo_mask: int, hi_mask: int):
         native.check(self.lib, self.lib.mvd_fill_halo(self._h, which, lo_mask, hi_mask), "mvd_fill_halo")
 

@@ -72,7 +72,7 @@ SESSION_SYMBOLS = (
     "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_upload_region", "mvd_init", "mvd_run",
     "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_get_stream", "mvd_set_timing",
     "mvd_get_timing", "mvd_get_device_buffer", "mvd_set_halo_mask", "mvd_halo_pack", "mvd_halo_unpack", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
-    "mvd_set_avg", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
+    "mvd_set_avg", "mvd_p2p_export", "mvd_p2p_connect", "mvd_p2p_push", "mvd_p2p_wait", "mvd_p2p_status", "mvd_p2p_disconnect", "mvd_convolve", "mvd_fft_size", "mvd_last_error", "mvd_version",
 )
 
 #: include/spim_fusion.h
@@ -167,6 +167,18 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_halo_unpack.restype = C.c_int
     lib.mvd_fill_halo.argtypes = [S, C.c_int, C.c_int, C.c_int]
     lib.mvd_fill_halo.restype = C.c_int
+    lib.mvd_p2p_export.argtypes = [S, C.c_void_p]
+    lib.mvd_p2p_export.restype = C.c_int
+    lib.mvd_p2p_connect.argtypes = [S, C.c_int, C.c_void_p, c_int_p, c_int_p]
+    lib.mvd_p2p_connect.restype = C.c_int
+    lib.mvd_p2p_push.argtypes = [S, C.c_int]
+    lib.mvd_p2p_push.restype = C.c_int
+    lib.mvd_p2p_wait.argtypes = [S, C.c_int]
+    lib.mvd_p2p_wait.restype = C.c_int
+    lib.mvd_p2p_status.argtypes = [S, c_int_p]
+    lib.mvd_p2p_status.restype = C.c_int
+    lib.mvd_p2p_disconnect.argtypes = [S]
+    lib.mvd_p2p_disconnect.restype = C.c_int
     lib.mvd_view_phase.argtypes = [S, C.c_int, C.c_int, c_double_p]
     lib.mvd_view_phase.restype = C.c_int
     lib.mvd_init_partials.argtypes = [S, c_double_p]
