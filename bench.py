@@ -331,6 +331,9 @@ def main():
     runner.init()
     tlog("init done")
     info = runner.session.info()
+    exchange_path = ("direct push over peer memory (mvd_p2p_*)" if runner.use_p2p else
+                     "single-launch pack / unpack around one NCCL batch" if runner.use_pack else
+                     "slab copies around one NCCL batch") if N > 1 else None
     np_brick = int(info.np_voxels)
     stream = torch.cuda.ExternalStream(runner.session.stream(), device=torch.device("cuda", local))
     for _ in range(args.warmup):
@@ -355,6 +358,7 @@ def main():
 
     # ---------------- per-kernel timing for the roofline (separate run, events around every launch) -----
     runner.session.set_timing(True)
+    runner.use_graph = False          # brick mode: eager launches here, so that every kernel is bracketed by its events
     runner.run(max(2, min(args.steps, 5)))
     kms, kcnt = runner.session.get_timing()
     runner.session.set_timing(False)
@@ -432,7 +436,7 @@ def main():
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--fusion-leg-only", "--views", str(VIEWS),
                    "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2])]
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
             out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             fusion_leg = json.loads(out[-1]) if (r.returncode == 0 and out) else {
                 "error": f"child exited with {r.returncode}: {(r.stderr or '').strip()[-300:]}"}
@@ -447,7 +451,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(N)[0],
                        "fft_dims_zyx": list(info.fft_dims), "np_voxels_per_brick": np_brick,
-                       "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), NCCL halo exchange" if N > 1 else "single GPU",
+                       "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), halo exchange: {exchange_path}" if N > 1 else "single GPU",
                        "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / args.steps,
                     "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e,

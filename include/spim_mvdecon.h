@@ -163,6 +163,8 @@ int mvd_convolve(const float* img, const int im_dims[3], const float* kernel, co
                  int ext, float ext_value, float* out, int device);
 /* smallest supported FFT length >= min_n */
 int mvd_fft_size(int min_n, int need_even);
+/* host-side launch counters for tests: which 0 = column passes launched with narrow (8-column) tiles */
+long long mvd_debug_counter(int which);
 const char* mvd_last_error(void);
 const char* mvd_version(void);
 

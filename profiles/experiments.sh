@@ -26,12 +26,16 @@ run "SPIM_COLP=2 SPIM_COLP_Y=3 SPIM_THREADS_COLT=352"
 run "SPIM_COLP=4"                                   # warp-private columns
 run "SPIM_COLP=2 SPIM_COLP_Z=4"                     # warp-private columns for the small z tiles only
 run "SPIM_COLP=2 SPIM_KSTAGE=1"
-run "SPIM_FAST_EPI=1"                               # branch-free MUFU-seeded division / sqrt in the ratio / update epilogues
-run "SPIM_FAST_EPI=1 SPIM_COLP_Y=3"
+run "SPIM_FAST_EPI=0"                               # IEEE intrinsics instead of the (default) branch-free MUFU-seeded division / sqrt
+run "SPIM_COLP_Y=3"
+run "SPIM_PDL=1"                                    # programmatic dependent launch: tail of one sweep overlaps the ramp-up of the next
+run "SPIM_PDL=1 SPIM_COL_NARROW=1"
+run "SPIM_COL_NARROW=1"                             # 8-column tiles (six 36 KB y tiles / eleven 18 KB z tiles per SM) on the C2 sizes
 run "SPIM_THREADS_XFWD=128"
 run "SPIM_THREADS_XFWD=256"
 run "SPIM_THREADS_XINV=192"
-check "SPIM_FAST_EPI=1"
+check "SPIM_FAST_EPI=0"
+check "SPIM_PDL=1"
 check "SPIM_COLP=3"
 check "SPIM_COLP=2 SPIM_COLP_Y=3"
 check "SPIM_COLP=4"
@@ -39,3 +43,13 @@ check "SPIM_COLP=2 SPIM_REGCAP=1 SPIM_THREADS_COL=256"
 # fusion pre-step (round-2 first run on hardware): parity, then one ncu pass over its kernels
 echo "== fusion pre-step GPU tests"
 timeout 600 python -m pytest tests/test_zz_gpu_fusion.py -x -q 2>&1 | tail -3
+
+# written after the last hardware run of round 1: narrow column tiles, then a race check of the hot-path kernels
+echo "== narrow-tile GPU tests"
+timeout 600 python -m pytest tests/test_zzz_gpu_narrow_tiles.py -x -q 2>&1 | tail -3
+echo "== racecheck (small parity subset)"
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "conv_all_extensions or golden" 2>&1 | tail -15
+# multi-GPU (run with gpurun --gpus 2): direct halo push over peer memory, then its timing against the NCCL paths
+#   python -m pytest tests/test_multigpu_nccl.py -q
+#   for e in "SPIM_BRICK_P2P=0" "SPIM_BRICK_P2P=1" "SPIM_BRICK_PACK=0"; do env $e python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+#       --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 2 --steps 5 --warmup 3; done

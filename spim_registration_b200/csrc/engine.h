@@ -9,8 +9,12 @@
 #include <memory>
 #include <mutex>
 #include <tuple>
+#include <atomic>
 
 namespace spim {
+
+// host-side launch counters (mvd_debug_counter): [0] column passes launched with narrow tiles
+inline std::atomic<long long>& debug_counter(int i) { static std::atomic<long long> c[4]; return c[i & 3]; }
 
 enum KernelId { K_XFWD = 0, K_YFWD, K_ZMID, K_YINV, K_XINV, K_ZFWD, K_MISC, K_COUNT };
 
@@ -133,6 +137,8 @@ inline int env_int(const char* name, int dflt) {
     const int r = atoi(v);
     return (r >= 0 && r <= 1024) ? r : dflt;
 }
+// the same, read on every call (switches the tests flip inside one process)
+inline int env_int_now(const char* name, int dflt) { return env_int(name, dflt); }
 inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); return t; }
 inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 // Column tiles larger than a third of the shared memory leave room for only two / one block per SM: scale the block
@@ -315,23 +321,37 @@ public:
         memset(&p, 0, sizeof(p));
         p.data = data; p.khat = khat;
         p.plan = (axis == 1) ? fy.dev : fz.dev;
-        p.ntx = pitch / TC;
+        const int Pa = P[axis];
+        // narrow tiles (8 columns, 64-byte rows): automatically where a 16-column tile would leave one block per SM
+        // (FFT lengths above ~880, e.g. the 1080-long axes of a 1024^2 x 512 volume on one GPU); SPIM_COL_NARROW=0/1 forces
+        const size_t lim = rt::max_smem();
+        const int narrow_env = env_int_now("SPIM_COL_NARROW", -1);
+        const bool narrow = use_colp_for(axis) == 2 &&
+                            (narrow_env >= 0 ? narrow_env != 0 : 2 * ((size_t)Pa * TC * sizeof(float2) + 1024) > lim);
+        const int tcols = narrow ? TC / 2 : TC;
+        p.ntx = pitch / tcols;
         if (axis == 1) { p.row_stride = pitch; p.outer_stride = (long long)pitch * P[1]; }
         else { p.row_stride = (long long)pitch * P[1]; p.outer_stride = pitch; }
         // outer index map: first outer_valid_lo indices map to themselves, the rest to the top of the axis
         p.outer_split = outer_valid_lo;
         p.outer_shift = outer_P - outer_count;
-        const int Pa = P[axis];
         if (mode == COL_INV) { p.va = Pa; p.vb = Pa; }
         else { p.va = g.n[axis] + g.hp[axis]; p.vb = Pa - g.hm[axis]; }
         p.sa = out_rows;
         p.mode = mode;
         const long long grid = (long long)p.ntx * outer_count;
-        const size_t smem = (size_t)Pa * TC * sizeof(float2);
+        const size_t smem = (size_t)Pa * tcols * sizeof(float2);
         if (timer) timer->begin(id, st);
-        const size_t lim = rt::max_smem();
         const int colp = use_colp_for(axis);
-        if (colp == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
+        if (narrow) {
+            debug_counter(0) += 1;
+            p.ntiles = -1;    // async mode flag
+            p.kstage = 0;
+            const int T = threads_col_for(smem, lim);
+            // 36 KB tiles and smaller: keep five 128-thread blocks per SM, like the 16-column small-tile instantiation
+            if (smem <= 40 * 1024 && T <= 128) rt::launch<ColPassNarrow, 128, 5>(p, grid, T, smem, st);
+            else rt::launch<ColPassNarrow>(p, grid, T, smem, st);
+        } else if (colp == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
             // experimental TMA / mbarrier pipeline: correct, but slower than the default in round 1 (see kernels.h)
             p.kstage = 0;
             p.ntiles = (int)grid;

@@ -146,7 +146,9 @@ SPIM_DEV void mul_twiddles1(float2 (&a)[R], const float2 (&w)[R]) {
 // transposing first / last phases are conflict-free)
 SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
 
-template <int R, bool INV, bool TW>
+// W = float4 column pairs per tile row: TP (16 columns, 128-byte rows) or TP / 2 (narrow tiles: 8 columns, 64-byte rows, for
+// axes so long that a 16-column tile would leave one block per SM)
+template <int R, bool INV, bool TW, int W = TP>
 SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
     const int M = pl.M[s];
     const int L = M * R;
@@ -155,9 +157,11 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
     const float2* twp = pl.tws + pl.tw_off[s];
     const long long gs4 = g.stride >> 1;
     const long long gstep = (long long)M * gs4;
-    SPIM_FOR_ITEMS_TG(tg, i, nb * TP) {
-        const int c2 = i & (TP - 1);
-        const int m = i >> 3;
+    constexpr int LW = (W == 8) ? 3 : 2;
+    static_assert(W == 8 || W == 4, "tile rows hold 8 or 4 column pairs");
+    SPIM_FOR_ITEMS_TG(tg, i, nb * W) {
+        const int c2 = i & (W - 1);
+        const int m = i >> LW;
         const int blk = (M == 1) ? m : fastdiv(m, magic);
         const int j = m - blk * M;
         const int base = blk * L + j;
@@ -173,10 +177,10 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
                 a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
                 b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
             }
-        } else if (!swz) {
-            const float4* sp = tile + base * TP + c2;
+        } else if (W != TP || !swz) {
+            const float4* sp = tile + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) { const float4 v = sp[q * M * TP]; a[q] = lo2(v); b[q] = hi2(v); }
+            for (int q = 0; q < R; ++q) { const float4 v = sp[q * M * W]; a[q] = lo2(v); b[q] = hi2(v); }
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
@@ -202,10 +206,10 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
                 stg_stream_if(gp, pack4(a[q], b[q]), base + q * M < g.sa);
                 gp += gstep;
             }
-        } else if (!swz) {
-            float4* sp = tile + base * TP + c2;
+        } else if (W != TP || !swz) {
+            float4* sp = tile + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) sp[q * M * TP] = pack4(a[q], b[q]);
+            for (int q = 0; q < R; ++q) sp[q * M * W] = pack4(a[q], b[q]);
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q) {
@@ -218,19 +222,20 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
 }
 
 // last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
-template <int R>
+template <int R, int W = TP>
 SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
     const int nb = pl.n / R;
     const long long gs4 = g.stride >> 1;
-    SPIM_FOR_ITEMS_TG(tg, i, nb * TP) {
-        const int c2 = i & (TP - 1);
-        const int base = (i >> 3) * R;
+    constexpr int LW = (W == 8) ? 3 : 2;
+    SPIM_FOR_ITEMS_TG(tg, i, nb * W) {
+        const int c2 = i & (W - 1);
+        const int base = (i >> LW) * R;
         float2 a[R], b[R];
         float4 kv[R];
         if (ks) {      // kernel-spectrum tile staged in shared memory
-            const float4* kp = ks + base * TP + c2;
+            const float4* kp = ks + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) kv[q] = kp[q * TP];
+            for (int q = 0; q < R; ++q) kv[q] = kp[q * W];
         } else {
             const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * ks4 + c2;
 #pragma unroll
@@ -247,9 +252,9 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
                 b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
             }
         } else {
-            const float4* sp = tile + base * TP + c2;
+            const float4* sp = tile + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) { const float4 v = sp[q * TP]; a[q] = lo2(v); b[q] = hi2(v); }
+            for (int q = 0; q < R; ++q) { const float4 v = sp[q * W]; a[q] = lo2(v); b[q] = hi2(v); }
         }
         dft<R, false>(a);
         dft<R, false>(b);
@@ -265,9 +270,9 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
                 gp += gs4;
             }
         } else {
-            float4* sp = tile + base * TP + c2;
+            float4* sp = tile + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) sp[q * TP] = pack4(a[q], b[q]);
+            for (int q = 0; q < R; ++q) sp[q * W] = pack4(a[q], b[q]);
         }
     }
     tg_barrier(tg);
@@ -289,13 +294,14 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
         default: break;                                                                          \
     }
 
-template <bool INV>
+template <bool INV, int W = TP>
 SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
-    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, true>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
-    else { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, false>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, true, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+    else { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, false, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
 }
+template <int W = TP>
 SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
-    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
+    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR, W>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,20 +325,22 @@ struct ColPassParams {
     SpimTensorMap tmap;
 };
 
-// asynchronous copy of tile rows [row_lo, row_hi) (16 float2 = 8 x 16 B each) from global to shared memory.
+// asynchronous copy of tile rows [row_lo, row_hi) (W float4 = W x 16 B each) from global to shared memory.
 // Each thread keeps its column pair and walks rows with a constant stride: ~4 instructions per 16-byte chunk.
+template <int W>
 SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_lo, int row_hi) {
 #if defined(SPIM_HOST_EMU)
     for (int row = row_lo; row < row_hi; ++row)
-        for (int c2 = 0; c2 < TP; ++c2) cp_async16(buf + row * TP + c2, gp + (long long)row * gs4 + c2);
+        for (int c2 = 0; c2 < W; ++c2) cp_async16(buf + row * W + c2, gp + (long long)row * gs4 + c2);
 #else
-    const int c2 = threadIdx.x & (TP - 1);
-    const int rstep = blockDim.x >> 3;
-    int row = row_lo + (threadIdx.x >> 3);
-    float4* d = buf + row * TP + c2;
+    constexpr int LW = (W == 8) ? 3 : 2;
+    const int c2 = threadIdx.x & (W - 1);
+    const int rstep = blockDim.x >> LW;
+    int row = row_lo + (threadIdx.x >> LW);
+    float4* d = buf + row * W + c2;
     const float4* g = gp + (long long)row * gs4 + c2;
     const long long gstep = (long long)rstep * gs4;
-    const int dstep = rstep * TP;
+    const int dstep = rstep * W;
     // four rows per trip: one bounds check and one pointer update per four 16-byte copies
     for (; row + 3 * rstep < row_hi; row += 4 * rstep, d += 4 * dstep, g += 4 * gstep) {
         cp_async16(d, g);
@@ -344,7 +352,11 @@ SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_l
 #endif
 }
 
-struct ColPass {
+// W = TP: tiles of 16 x-frequencies (the default); W = TP / 2: narrow tiles of 8 (ntx = pitch / 8), half the shared memory
+// per block -- for FFT lengths above ~880, where a 16-column tile would leave a single block per SM and nothing to overlap
+// its load / compute / store phases with
+template <int W>
+struct ColPassN {
     typedef ColPassParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
@@ -352,7 +364,7 @@ struct ColPass {
         const int o = bid / p.ntx;
         const int tx = bid - o * p.ntx;
         const int outer = o < p.outer_split ? o : o + p.outer_shift;
-        const long long base = (long long)outer * p.outer_stride + (long long)tx * TC;
+        const long long base = (long long)outer * p.outer_stride + (long long)tx * (2 * W);
         GRows g;
         g.p = p.data + base;
         g.stride = p.row_stride;
@@ -366,19 +378,19 @@ struct ColPass {
             const long long gs4 = p.row_stride >> 1;
             const float4* gp = reinterpret_cast<const float4*>(g.p);
             if (p.va < p.vb) {
-                async_rows(tile, gp, gs4, 0, p.va);
-                async_rows(tile, gp, gs4, p.vb, P);
+                async_rows<W>(tile, gp, gs4, 0, p.va);
+                async_rows<W>(tile, gp, gs4, p.vb, P);
             } else {
-                async_rows(tile, gp, gs4, 0, P);
+                async_rows<W>(tile, gp, gs4, 0, P);
             }
             if (p.mode == COL_MID && p.kstage) {
-                float4* kb = tile + (size_t)P * TP;
-                async_rows(kb, reinterpret_cast<const float4*>(p.khat + base), gs4, 0, P);
+                float4* kb = tile + (size_t)P * W;
+                async_rows<W>(kb, reinterpret_cast<const float4*>(p.khat + base), gs4, 0, P);
                 ks = kb;
             }
             cp_async_commit();
             if (p.va < p.vb) {
-                SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                SPIM_FOR_ITEMS(i, (p.vb - p.va) * W) tile[p.va * W + i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             cp_async_wait<0>();
             SPIM_BARRIER();
@@ -386,16 +398,18 @@ struct ColPass {
             g.va = P; g.vb = P;
         }
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false, W>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true, W>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
-            mid_dispatch(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false, W>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
+            mid_dispatch<W>(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true, W>(tg, pl, s, tile, 0, 0, s == 0, g);
         }
     }
 };
+typedef ColPassN<TP> ColPass;
+typedef ColPassN<TP / 2> ColPassNarrow;
 
 // tile index -> offset of its first element (x tiles fastest, outer index mapped over the zero gap)
 SPIM_DEV void col_tile_base(const ColPassParams& p, int t, long long& base) {

@@ -105,16 +105,44 @@ inline int sm_count() {
     return v;
 }
 
+// Programmatic dependent launch (opt-in, SPIM_PDL=1): every block first lets the NEXT kernel of the stream start launching
+// and then waits for the PREVIOUS kernel to complete and flush.  The next kernel's blocks become resident in the slots the
+// last wave of this one frees, parked at their own wait, so the tail of one sweep and the ramp-up of the next overlap instead
+// of adding up.  Both instructions are no-ops for a kernel launched without the attribute (the default).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <class Body, int MAXT>
 __global__ void __launch_bounds__(MAXT) kernel_entry(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
+    pdl_prologue();
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
 // experiment hook: MINB blocks of MAXT threads per SM must fit (caps the registers per thread)
 template <class Body, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) kernel_entry_capped(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
+    pdl_prologue();
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
+}
+
+inline bool use_pdl() {
+    static int v = [] { const char* e = getenv("SPIM_PDL"); return (e && *e == '1') ? 1 : 0; }();
+    return v != 0;
+}
+template <class K, class P>
+inline void launch_kernel(K kernel, const P& p, unsigned grid, int block, size_t smem, Stream s) {
+    if (!use_pdl()) { kernel<<<grid, block, smem, s>>>(p); return; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SPIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
 }
 
 template <class Body, int MAXT = 256, int MINB = 1>
@@ -129,13 +157,13 @@ inline void launch(const typename Body::Params& p, long long grid, int block, si
             SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry_capped<Body, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured[dev] = smem;
         }
-        kernel_entry_capped<Body, MAXT, MINB><<<(unsigned)grid, block, smem, s>>>(p);
+        launch_kernel(kernel_entry_capped<Body, MAXT, MINB>, p, (unsigned)grid, block, smem, s);
     } else {
         if (dev < 64 && smem > configured[dev]) {
             SPIM_CUDA_CHECK(cudaFuncSetAttribute(kernel_entry<Body, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured[dev] = smem;
         }
-        kernel_entry<Body, MAXT><<<(unsigned)grid, block, smem, s>>>(p);
+        launch_kernel(kernel_entry<Body, MAXT>, p, (unsigned)grid, block, smem, s);
     }
     SPIM_CUDA_CHECK(cudaGetLastError());
 }

@@ -1389,6 +1389,7 @@ int mvd_convolve(const float* img, const int im_dims[3], const float* kernel, co
     SPIM_API_END
 }
 
+long long mvd_debug_counter(int which) { return debug_counter(which).load(); }
 int mvd_fft_size(int min_n, int need_even) { return choose_fft_size(min_n, need_even != 0); }
 
 // ================================================================================================

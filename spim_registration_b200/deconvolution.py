@@ -344,10 +344,41 @@ class _ViewFFT:
         bs = self.blockSize
         block = np.empty((bs[2], bs[1], bs[0]), dtype=np.float32)
         kdim = kernel.shape
-        for b in self.blocks:
-            b.copyBlock(image, block, ext, value)
-            cuda.convolution3DfftCUDAInPlace(block, block.shape, kernel, kdim, self.device0)
-            b.pasteBlock(result, block)
+        if len(self.deviceList) == 1:
+            for b in self.blocks:
+                b.copyBlock(image, block, ext, value)
+                cuda.convolution3DfftCUDAInPlace(block, block.shape, kernel, kdim, self.device0)
+                b.pasteBlock(result, block)
+            return result
+        # multi-device mode (LRFFT.java:499-522, MVDeconFFT.java:447-469): one host thread per entry of deviceList, each
+        # taking the next block index from a shared counter (the reference's AtomicInteger) until none are left; blocks
+        # paste disjoint effective regions, and the native side serialises per device, not globally
+        import itertools
+        import threading
+        counter, lock, errors = itertools.count(), threading.Lock(), []
+
+        def worker(dev: int):
+            try:
+                mine = np.empty((bs[2], bs[1], bs[0]), dtype=np.float32)
+                while True:
+                    with lock:
+                        i = next(counter)
+                    if i >= len(self.blocks):
+                        return
+                    b = self.blocks[i]
+                    b.copyBlock(image, mine, ext, value)
+                    cuda.convolution3DfftCUDAInPlace(mine, mine.shape, kernel, kdim, dev)
+                    b.pasteBlock(result, mine)
+            except BaseException as e:      # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(d,)) for d in self.deviceList]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
         return result
 
     def convolve1(self, image: np.ndarray, result: Optional[np.ndarray] = None) -> np.ndarray:

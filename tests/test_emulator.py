@@ -254,3 +254,64 @@ def test_brick_mode_without_neighbours_equals_plain_session(emu_lib, ks):
         s.finish()
         psi = s.get_psi()
     assert np.array_equal(plain, psi)
+
+
+# ---- narrow column tiles (8 columns / 64-byte rows; automatic for FFT lengths above ~880) ----------------------
+@pytest.mark.parametrize("n", [16, 18, 20, 28, 30, 36, 42, 48, 50, 54, 56, 60, 70, 72, 80, 90, 96, 100, 112, 126, 140, 144])
+def test_narrow_tiles_every_radix_path(emu_lib, monkeypatch, n):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    for shape in ((n, 4, 8), (4, n, 8)):
+        P.legacy_case(emu_lib, shape, (3, 3, 3), seed=n)
+
+
+@pytest.mark.parametrize("ext", [0, 1, 2, 3, 4])
+def test_narrow_tiles_conv_all_extensions(emu_lib, monkeypatch, ext):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    P.conv_case(emu_lib, (9, 7, 11), (3, 5, 3), ext)
+    P.conv_case(emu_lib, (5, 30, 33), (1, 7, 9), ext)      # pitch 32: two 16-column tiles = four narrow ones
+
+
+def test_narrow_tiles_deconvolution(emu_lib, monkeypatch):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    c0 = emu_lib.mvd_debug_counter(0)
+    P.decon_case(emu_lib, (14, 18, 22), 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
+    P.golden_case(emu_lib, 1, 1)
+    P.golden_conv_case(emu_lib)
+    assert emu_lib.mvd_debug_counter(0) > c0
+
+
+def test_long_axes_select_narrow_tiles_automatically(emu_lib):
+    # 1080-long y / z axes (a 1024^2 x 512 volume with a 31^3 PSF on one GPU): a 16-column tile would be 138 KB
+    c0 = emu_lib.mvd_debug_counter(0)
+    P.conv_case(emu_lib, (3, 1050, 6), (3, 31, 3), 2)
+    c1 = emu_lib.mvd_debug_counter(0)
+    assert c1 > c0                       # the long y passes ran on narrow tiles ...
+    P.conv_case(emu_lib, (1040, 2, 6), (15, 1, 3), 1)
+    assert emu_lib.mvd_debug_counter(0) > c1
+    c2 = emu_lib.mvd_debug_counter(0)
+    P.conv_case(emu_lib, (8, 8, 8), (3, 3, 3), 2)
+    assert emu_lib.mvd_debug_counter(0) == c2     # ... and short axes stay on the 16-column tiles
+
+
+def test_multi_device_block_queue_of_the_view_classes(emu_lib):
+    """MVDeconFFT.convolve1 in the reference's multi-device mode (MVDeconFFT.java:447-469): one host thread per deviceList
+    entry pulling blocks from a shared counter.  Three threads on the emulator's single device exercise the queue and the
+    native side's per-device serialisation; the result must equal the single-thread block loop and the oracle."""
+    import __graft_entry__ as g
+    from spim_registration_b200 import MVDeconFFT, native, synthetic
+    from spim_registration_b200.deconvolution import _ViewFFT
+    saved = _ViewFFT.cuda
+    _ViewFFT.cuda = native.CUDAFourierConvolution(g.build_emulator())
+    try:
+        shape = (20, 22, 26)
+        _, imgs, ws, psfs = synthetic.make_dataset(shape, 1, 5)
+        psi = np.random.default_rng(0).random(shape, dtype=np.float32)
+        one = MVDeconFFT(imgs[0], ws[0], psfs[0], None, [0], True, (12, 10, 8), False)
+        many = MVDeconFFT(imgs[0], ws[0], psfs[0], None, [0, 0, 0], True, (12, 10, 8), False)
+        assert len(many.blocks) > 8
+        a, b = one.convolve1(psi), many.convolve1(psi)
+        assert np.array_equal(a, b)
+        r = O.convolve(psi, psfs[0], O.EXT_MIRROR_SINGLE, dtype=np.float64)
+        assert np.abs(b - r).max() / np.abs(r).max() < P.TOL_CONV
+    finally:
+        _ViewFFT.cuda = saved

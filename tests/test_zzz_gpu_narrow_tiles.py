@@ -1,0 +1,46 @@
+"""GPU parity tests of the narrow column tiles (8 x-frequencies per tile row, ColPassNarrow): selected automatically for FFT
+lengths above ~880 (the 1080-long axes of a 1024 x 1024 x 512 volume with a 31^3 PSF on ONE GPU, where a 16-column tile
+would leave a single block per SM), forced here with SPIM_COL_NARROW=1 on the ordinary cases as well.  The arithmetic per
+column is the same as in the 16-column tiles, so the bar is the same as in test_gpu_parity.py.
+
+The file sorts after every other GPU test on purpose: the variant was written after the round's GPU budget was spent
+(verified under the kernel emulator, tests/test_emulator.py), so under `pytest -x` nothing here can hide a result above."""
+import pytest
+
+import parity_cases as P
+from oracle import mvdecon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [18, 30, 48, 56, 70, 90, 126, 144, 288, 560])
+def test_narrow_tiles_radix_paths(gpu, monkeypatch, n):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    c0 = gpu.mvd_debug_counter(0)
+    for shape in ((n, 4, 8), (4, n, 8)):
+        P.legacy_case(gpu, shape, (3, 3, 3), seed=n)
+    assert gpu.mvd_debug_counter(0) > c0
+
+
+@pytest.mark.parametrize("ext", [0, 1, 2, 3, 4])
+def test_narrow_tiles_conv_all_extensions(gpu, monkeypatch, ext):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    P.conv_case(gpu, (9, 7, 11), (3, 5, 3), ext)
+    P.conv_case(gpu, (40, 50, 70), (7, 9, 5), ext)
+
+
+def test_narrow_tiles_deconvolution(gpu, monkeypatch):
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    P.decon_case(gpu, (40, 48, 56), 3, 7, O.EFFICIENT_BAYESIAN, 2, 3)
+    P.decon_case(gpu, (33, 41, 50), 2, 5, O.OPTIMIZATION_I, 1, 2)
+    P.golden_case(gpu, 2, 2)
+    P.golden_conv_case(gpu)
+
+
+def test_long_axes_select_narrow_tiles_automatically(gpu):
+    c0 = gpu.mvd_debug_counter(0)
+    P.conv_case(gpu, (6, 1050, 40), (3, 31, 3), 2)        # Py = 1080
+    c1 = gpu.mvd_debug_counter(0)
+    assert c1 > c0
+    P.conv_case(gpu, (1040, 6, 40), (15, 3, 3), 1)        # Pz = 1056 / 1080
+    assert gpu.mvd_debug_counter(0) > c1
