@@ -1,21 +1,32 @@
 """Build the CUDA shared library in-tree with nvcc for sm_100a (no JIT cache: the .so travels with
-the repository snapshot to the GPU box)."""
+the repository snapshot to the GPU box).
+
+The library is compiled from several translation units in parallel: csrc/spim_b200.cu (C ABI, session, element-wise
+and fusion kernels) and csrc/inst.cu once per group of csrc/instances.h (the FFT kernels' instantiations) -- the heavy
+templates cost minutes of compiler front-end time each, so one file per core turns a 5.5-minute build into about two.
+SPIM_SINGLE_TU=1 selects the plain one-file build (same code, implicit instantiation)."""
 from __future__ import annotations
 
 import os
+import re
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "spim_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("spim_b200.cu", "engine.h", "kernels.h", "fft_math.h", "fast_math.h", "hd.h", "runtime.h", "fusion.h", "fusion_api.h")] + \
+CSRC = os.path.join(HERE, "csrc")
+SRC = os.path.join(CSRC, "spim_b200.cu")
+INST = os.path.join(CSRC, "inst.cu")
+DEPS = [os.path.join(CSRC, f) for f in ("spim_b200.cu", "inst.cu", "instances.h", "engine.h", "kernels.h", "fft_math.h", "fast_math.h",
+                                        "hd.h", "runtime.h", "fusion.h", "fusion_api.h")] + \
        [os.path.join(HERE, "..", "include", f) for f in ("spim_fftconv.h", "spim_mvdecon.h", "spim_fusion.h")]
 OUT = os.path.join(HERE, "libConvolution3D_fftCUDAlib.so")
 ALIAS = os.path.join(HERE, "libFourierConvolutionCUDALib.so")
+OBJDIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 
 
 def is_stale() -> bool:
@@ -25,17 +36,48 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
+def instance_groups():
+    """the group names of csrc/instances.h (SPIM_INSTANCE_GROUPS)"""
+    txt = open(os.path.join(CSRC, "instances.h")).read()
+    m = re.search(r"#define SPIM_INSTANCE_GROUPS (.*)", txt)
+    return re.findall(r'"([A-Z_0-9]+)"', m.group(1))
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, r.stdout + r.stderr
+
+
 def build_cuda_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("SPIM_SINGLE_TU") == "1":
+        jobs, objs = [[nvcc] + NVCC_FLAGS + extra + ["-shared", SRC, "-o", OUT]], []
+    else:
+        os.makedirs(OBJDIR, exist_ok=True)
+        main_o = os.path.join(OBJDIR, "spim_b200.o")
+        jobs = [[nvcc] + NVCC_FLAGS + extra + ["-DSPIM_SPLIT_BUILD", "-c", SRC, "-o", main_o]]
+        objs = [main_o]
+        for g in instance_groups():
+            o = os.path.join(OBJDIR, f"inst_{g}.o")
+            jobs.append([nvcc] + NVCC_FLAGS + extra + ["-DSPIM_SPLIT_BUILD", f"-DSPIM_INST_GROUP={g}", "-c", INST, "-o", o])
+            objs.append(o)
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(_run, jobs))
+    log = "".join(out for _, out in results)
+    if any(rc != 0 for rc, _ in results):
+        sys.stderr.write(log)
         raise RuntimeError("nvcc failed building " + OUT)
+    if objs:
+        rc, out = _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", OUT])
+        log += out
+        if rc != 0:
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed linking " + OUT)
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write(log)
     # the second name the reference's library picker pre-selects (EfficientBayesianBased.java:1127-1131)
     shutil.copyfile(OUT, ALIAS)
     return OUT

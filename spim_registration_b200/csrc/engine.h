@@ -3,6 +3,7 @@
 #pragma once
 #include "kernels.h"
 #include "runtime.h"
+#include "instances.h"
 #include <algorithm>
 #include <cmath>
 #include <map>

@@ -15,7 +15,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #define SPIM_DEV inline
-#define SPIM_NOINLINE_DEV __attribute__((noinline))
+#define SPIM_NOINLINE_DEV static __attribute__((noinline))
 #define SPIM_HD inline
 #define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)
 #define SPIM_BARRIER() ((void)0)
@@ -63,7 +63,7 @@ static inline float spim_rsqrt_seed(float x) { volatile float r = (float)(1.0 / 
 #include <cuda.h>
 typedef CUtensorMap SpimTensorMap;
 #define SPIM_DEV __device__ __forceinline__
-#define SPIM_NOINLINE_DEV __device__ __noinline__
+#define SPIM_NOINLINE_DEV static __device__ __noinline__
 #define SPIM_HD __host__ __device__ __forceinline__
 #define SPIM_FOR_ITEMS(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)
 #define SPIM_BARRIER() __syncthreads()

@@ -145,8 +145,10 @@ inline void launch_kernel(K kernel, const P& p, unsigned grid, int block, size_t
     SPIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
 }
 
+// not `inline`: in the split build (instances.h) the engine kernels' launches are declared `extern template`, which only
+// suppresses the implicit instantiation of non-inline templates
 template <class Body, int MAXT = 256, int MINB = 1>
-inline void launch(const typename Body::Params& p, long long grid, int block, size_t smem, Stream s) {
+void launch(const typename Body::Params& p, long long grid, int block, size_t smem, Stream s) {
     if (grid <= 0) return;
     static thread_local size_t configured[64] = {0};   // per device
     int dev = 0;
