@@ -44,3 +44,25 @@ def test_long_axes_select_narrow_tiles_automatically(gpu):
     assert c1 > c0
     P.conv_case(gpu, (1040, 6, 40), (15, 3, 3), 1)        # Pz = 1056 / 1080
     assert gpu.mvd_debug_counter(0) > c1
+
+
+def test_configs2_size_on_one_gpu_delta_identity_and_shift(gpu):
+    """BASELINE configs[2] volume on ONE GPU (1024 x 1024 x 512, 31^3 PSF -> FFT size 1080 x 1080 x 560, 2 GiB per real
+    volume, 2.6 GB per spectrum): 64-bit index math and the automatically selected narrow tiles at full size, through
+    properties the oracle is not needed for -- a delta kernel is the identity, a shifted delta a mirrored shift."""
+    import numpy as np
+    from spim_registration_b200 import native
+    shape = (512, 1024, 1024)
+    rng = np.random.default_rng(5)
+    a = rng.random(shape, dtype=np.float32)
+    delta = np.zeros((31, 31, 31), np.float32)
+    delta[15, 15, 15] = 1.0
+    c0 = gpu.mvd_debug_counter(0)
+    out = native.convolve(a, delta, O.EXT_MIRROR_SINGLE, lib=gpu)
+    assert gpu.mvd_debug_counter(0) > c0                  # the 1080-long y passes ran on narrow tiles
+    assert np.abs(out - a).max() < 2e-6
+    sh = np.zeros((31, 31, 31), np.float32)
+    sh[20, 15, 15] = 1.0                                  # kernel index 20 along z = shift by +5 planes
+    out = native.convolve(a, sh, O.EXT_MIRROR_SINGLE, lib=gpu)
+    assert np.abs(out[5:] - a[:-5]).max() < 2e-6
+    assert np.abs(out[:5] - a[5:0:-1]).max() < 2e-6       # mirror-single at the low z face
