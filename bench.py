@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion-leg", action="store_true")
+    ap.add_argument("--no-cufft-leg", action="store_true")
     ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
     ap.add_argument("--views", type=int, default=None)
@@ -444,6 +445,26 @@ def main():
             fusion_leg = {"error": f"{type(e).__name__}: {e}"}
         tlog("fusion leg done")
 
+    # ---------------- reported extra: the same convolution built on cuFFT (comparison point only, separate executable) ----
+    cufft_leg = None
+    if rank == 0 and N == 1 and not args.no_cufft_leg:
+        try:
+            exe = b.build_cufft_comparison()
+            if exe:
+                fd = [int(v) for v in info.fft_dims]
+                cmd = [exe, str(BRICK[0]), str(BRICK[1]), str(BRICK[2]), str(PSF), str(fd[0]), str(fd[1]), str(fd[2]), "20"]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+                out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                cufft_leg = json.loads(out[-1]) if out else {"error": f"exit {r.returncode}: {(r.stderr or '').strip()[-200:]}"}
+                if conv_pass and "ms_per_conv" in cufft_leg:
+                    cufft_leg["ours_ms_per_conv"] = conv_pass["ms_per_conv"]
+                    cufft_leg["speedup_ours_vs_cufft"] = cufft_leg["ms_per_conv"] / conv_pass["ms_per_conv"]
+            else:
+                cufft_leg = {"error": "comparison binary not built"}
+        except Exception as e:      # noqa: BLE001
+            cufft_leg = {"error": f"{type(e).__name__}: {e}"}
+        tlog("cufft leg done")
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -463,6 +484,7 @@ def main():
             "roofline_view_step": view_step if dom else None,
             "cpu_baseline": cpu,
             "fusion_prestep": fusion_leg,
+            "cufft_comparison": cufft_leg,
         }
         print(json.dumps(line))
     sys.stdout.flush()

@@ -53,3 +53,6 @@ timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest
 #   python -m pytest tests/test_multigpu_nccl.py -q
 #   for e in "SPIM_BRICK_P2P=0" "SPIM_BRICK_P2P=1" "SPIM_BRICK_PACK=0"; do env $e python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
 #       --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 2 --steps 5 --warmup 3; done
+# cuFFT comparison point (separate executable, comparison only): timing, then its kernels under ncu
+#   profiles/microbench/cufft_conv 256 512 512 31 288 560 560 20
+#   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 profiles/microbench/cufft_conv 256 512 512 31 288 560 560 2

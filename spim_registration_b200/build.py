@@ -83,5 +83,20 @@ def build_cuda_library(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_cufft_comparison() -> str:
+    """profiles/microbench/cufft_conv: the cuFFT-based convolution bench.py times next to ours (comparison only -- it is a
+    separate executable and nothing of it is linked into the library).  Returns "" when it cannot be built."""
+    src = os.path.join(HERE, "..", "profiles", "microbench", "cufft_conv.cu")
+    out = os.path.join(HERE, "..", "profiles", "microbench", "cufft_conv")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    rc, log = _run([nvcc, "-O3", "-gencode", "arch=compute_100a,code=sm_100a", src, "-lcufft", "-o", out])
+    if rc != 0:
+        sys.stderr.write("cufft comparison binary not built:\n" + log)
+        return ""
+    return out
+
+
 if __name__ == "__main__":
     print(build_cuda_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
