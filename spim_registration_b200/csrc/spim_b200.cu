@@ -228,24 +228,29 @@ struct HaloPushK {
         float* dst[MAX_PIECES];            // base of the neighbour's buffer
         unsigned int* flag[MAX_PIECES];    // the neighbour's flag word for (this buffer, my direction)
         int lo[MAX_PIECES][3]; int dlo[MAX_PIECES][3]; int ext[MAX_PIECES][3]; long long off[MAX_PIECES + 1];
+        int vsh[MAX_PIECES];               // 2: the piece's rows are moved as float4 (x origin, extent and row length are
+                                           // multiples of 4 -- the y / z faces, i.e. almost all bytes), 0: float by float
         unsigned int* done;                // my block counter
         unsigned int* epoch;               // my push counter for this buffer
     };
     SPIM_DEV static void run(const Params& p, int bid, float2*) {
-        const long long total = p.off[p.npieces];
+        const long long total = p.off[p.npieces];      // in items: float4 for vectorised pieces, float otherwise
         for (long long base = (long long)bid * kChunk; base < total; base += (long long)p.nblocks * kChunk) {
             SPIM_FOR_ITEMS(i, kChunk) {
                 const long long idx = base + i;
                 if (idx >= total) continue;
                 int pc = 0;
                 while (pc + 1 < p.npieces && idx >= p.off[pc + 1]) ++pc;
+                const int sh = p.vsh[pc];
+                const int ex = p.ext[pc][2] >> sh;
                 long long r = idx - p.off[pc];
-                const int x = (int)(r % p.ext[pc][2]); r /= p.ext[pc][2];
+                const int x = (int)(r % ex) << sh; r /= ex;
                 const int y = (int)(r % p.ext[pc][1]);
                 const int z = (int)(r / p.ext[pc][1]);
                 const long long a = ((long long)(z + p.lo[pc][0]) * p.dims[1] + (y + p.lo[pc][1])) * p.dims[2] + x + p.lo[pc][2];
                 const long long b = ((long long)(z + p.dlo[pc][0]) * p.dims[1] + (y + p.dlo[pc][1])) * p.dims[2] + x + p.dlo[pc][2];
-                p.dst[pc][b] = p.buf[a];
+                if (sh) *reinterpret_cast<float4*>(p.dst[pc] + b) = *reinterpret_cast<const float4*>(p.buf + a);
+                else p.dst[pc][b] = p.buf[a];
             }
         }
 #if defined(SPIM_HOST_EMU)
@@ -1303,7 +1308,10 @@ int mvd_p2p_push(mvd_session* s, int which) {
         p.off[i] = off;
         long long n = 1;
         for (int d = 0; d < 3; ++d) { p.lo[i][d] = q.lo[i][d]; p.dlo[i][d] = q.dlo[i][d]; p.ext[i][d] = q.ext[i][d]; n *= q.ext[i][d]; }
-        off += n;
+        const bool vec = (q.ext[i][2] % 4 == 0) && (q.lo[i][2] % 4 == 0) && (q.dlo[i][2] % 4 == 0) && (s->pdims[2] % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.buf) | reinterpret_cast<uintptr_t>(p.dst[i])) & 15) == 0;
+        p.vsh[i] = vec ? 2 : 0;
+        off += vec ? n / 4 : n;
     }
     p.off[q.npieces] = off;
     p.nblocks = ew_blocks(off);

@@ -76,7 +76,7 @@ class ThreadDist:
         return [_Work() for _ in ops]
 
 
-def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, out, errors):
+def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, out, errors):  # noqa: PLR0913
     try:
         from spim_registration_b200 import bricks
         imgs, ws, psfs = data
@@ -100,8 +100,11 @@ def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, 
         shared.barrier.abort()
 
 
-@pytest.mark.parametrize("world,gen,typ,ks", [(2, 2, 2, 5), (4, 2, 0, 5), (8, 1, 1, 5), (8, 2, 2, 7), (4, 1, 3, 3)])
-def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, typ, ks):
+@pytest.mark.parametrize("world,gen,typ,ks,brick", [(2, 2, 2, 5, (8, 9, 10)), (4, 2, 0, 5, (8, 9, 10)), (8, 1, 1, 5, (8, 9, 10)),
+                                                      (8, 2, 2, 7, (8, 9, 10)), (4, 1, 3, 3, (8, 9, 10)),
+                                                      # x origin 4, row length 20, x extent 12: the float4 path of the y / z faces
+                                                      (8, 2, 2, 7, (8, 8, 12)), (4, 2, 3, 7, (7, 9, 12))])
+def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, typ, ks, brick):
     import torch
     import __graft_entry__ as g
     from oracle import mvdecon_oracle as O
@@ -109,7 +112,7 @@ def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, t
     monkeypatch.setenv("SPIM_BRICK_P2P", "1")
     torch.set_num_threads(1)
     lib = native.load_library(g.build_emulator())
-    brick, V, iters = (8, 9, 10), 2, 2
+    V, iters = 2, 2
     grid = bricks.grid_for(world)
     gshape = tuple(brick[d] * grid[d] for d in range(3))
     _, imgs, ws, psfs = synthetic.make_dataset(gshape, V, ks, kind="beads", seed=3)
