@@ -223,6 +223,67 @@ def fusion_prestep_leg(shape, views, peak, lib=None, timed=None, stack_planes=No
             "timing": "host clock around the synchronous C-ABI call (kernel launch + stream synchronise)"}
 
 
+# A/B matrix of the in-tree kernel variants, measured in the same run as the headline number (rank 0, N = 1, child processes
+# without torch: numpy inputs, the session C-ABI, host clock around the synchronous mvd_run and the library's own per-kernel
+# CUDA events).  The first entry is the control: the default configuration in the very same harness.
+VARIANTS = [
+    ("default", {}),
+    ("ieee_epilogue", {"SPIM_FAST_EPI": "0"}),                     # IEEE division / sqrt instead of the branch-free refinement
+    ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
+    ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
+    ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
+    ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
+    ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
+    ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
+    ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+]
+
+
+def variant_child():
+    """One configuration of the A/B matrix (environment already set by the parent); prints one JSON line."""
+    from spim_registration_b200 import synthetic
+    from spim_registration_b200.deconvolution import Session
+    rng = np.random.default_rng(1)
+    img = (0.05 + 0.95 * rng.random(BRICK, dtype=np.float32)).astype(np.float32)
+    w = np.full(BRICK, np.float32(1.0 / VIEWS), np.float32)
+    psfs = synthetic.make_psfs(VIEWS, PSF)
+    iters = 6
+    with Session(BRICK, VIEWS, ITER_TYPE, generation=2, lam=LAMBDA) as s:
+        for v in range(VIEWS):
+            s.set_view(v, img, w, psfs[v])
+        s.init()
+        s.run(2, stats=False)
+        t0 = time.perf_counter()
+        s.run(iters, stats=False)
+        dt = time.perf_counter() - t0
+        s.set_timing(True)
+        s.run(2, stats=False)
+        kms, kcnt = s.get_timing()
+        psi_ok = bool(np.isfinite(s.get_psi()[::8, ::16, ::16]).all())
+    per = {KERNEL_NAMES[i]: kms[i] / kcnt[i] for i in range(len(KERNEL_NAMES)) if kcnt[i] > 0}
+    print(json.dumps({"value": int(np.prod(BRICK)) * VIEWS * iters / dt, "ms_per_step": 1e3 * dt / iters,
+                      "ms_per_conv": sum(per.values()), "per_kernel_ms": per, "finite": psi_ok}))
+
+
+def variants_leg(budget_s=150.0, per_child_s=45.0):
+    out, t_start = {}, time.perf_counter()
+    for name, env in VARIANTS:
+        if time.perf_counter() - t_start > budget_s:
+            out[name] = {"skipped": "time budget of this extra used up"}
+            continue
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--variant-child", "--views", str(VIEWS),
+                   "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2])]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=per_child_s, env=dict(os.environ, **env))
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out[name] = json.loads(lines[-1]) if (r.returncode == 0 and lines) else {
+                "error": f"exit {r.returncode}: {(r.stderr or '').strip()[-200:]}"}
+        except Exception as e:      # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        out[name]["env"] = env
+    return out
+
+
 _T0 = time.perf_counter()
 
 
@@ -241,6 +302,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion-leg", action="store_true")
     ap.add_argument("--no-cufft-leg", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the A/B matrix of kernel variants (an extra of the default run)")
+    ap.add_argument("--variant-child", action="store_true", help="internal: one configuration of the A/B matrix")
     ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
     ap.add_argument("--views", type=int, default=None)
@@ -257,6 +320,9 @@ def main():
         return
     if args.fusion_leg_only:
         print(json.dumps(fusion_prestep_leg(BRICK, VIEWS, peaks()[0])))
+        return
+    if args.variant_child:
+        variant_child()
         return
 
     tlog("start")
@@ -465,6 +531,15 @@ def main():
             cufft_leg = {"error": f"{type(e).__name__}: {e}"}
         tlog("cufft leg done")
 
+    # ---------------- reported extra: A/B matrix of the in-tree kernel variants (bounded: <= 150 s, child processes) --------
+    variants = None
+    if rank == 0 and N == 1 and not args.no_variants:
+        try:
+            variants = variants_leg()
+        except Exception as e:      # noqa: BLE001
+            variants = {"error": f"{type(e).__name__}: {e}"}
+        tlog("variants done")
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -485,6 +560,7 @@ def main():
             "cpu_baseline": cpu,
             "fusion_prestep": fusion_leg,
             "cufft_comparison": cufft_leg,
+            "variants": variants,
         }
         print(json.dumps(line))
     sys.stdout.flush()
