@@ -117,7 +117,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(shape, rank_seed=0):
+def make_inputs(shape, rank_seed=0, fast=False):
     """Synthetic specimen views for one brick; the forward blur runs on the GPU through mvd_convolve."""
     from spim_registration_b200 import native, synthetic
     lib = native.load_library()
@@ -126,8 +126,14 @@ def make_inputs(shape, rank_seed=0):
     def blur(t, k):
         return native.convolve(t, k, 2, 0.0, device=dev, lib=lib)
 
-    truth = synthetic.specimen_truth(shape, seed=2929 + rank_seed)
     psfs = synthetic.make_psfs(VIEWS, PSF)
+    if fast:
+        # timing-only child runs (the direct-push variant): uniform noise shared by all views, constant weights
+        rng = np.random.default_rng(11 + rank_seed)
+        img = (0.05 + 0.95 * rng.random(shape, dtype=np.float32)).astype(np.float32)
+        w = np.full(shape, np.float32(1.0 / VIEWS), np.float32)
+        return [img] * VIEWS, [w] * VIEWS, psfs
+    truth = synthetic.specimen_truth(shape, seed=2929 + rank_seed)
     imgs, ws = synthetic.make_views(truth, psfs, seed=7 + rank_seed, blur=blur)
     return imgs, ws, psfs
 
@@ -236,6 +242,9 @@ VARIANTS = [
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
     ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+    ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),
+    ("warp_private_columns_z", {"SPIM_COLP_Z": "4"}),
+    ("kernel_spectrum_staged", {"SPIM_KSTAGE": "1"}),
 ]
 
 
@@ -284,6 +293,42 @@ def variants_leg(budget_s=150.0, per_child_s=45.0):
     return out
 
 
+def p2p_variant_leg(n, steps, limit_s=240.0):
+    """Rank 0, N > 1: run this very benchmark once more as a child torchrun job with SPIM_BRICK_P2P=1 (noise inputs, no
+    extras) and return its throughput.  The child is its own process group and is killed as a group at the time limit."""
+    import signal
+    import socket
+    sk = socket.socket()
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
+    sk.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__), "--gpus", str(n), "--steps", str(max(3, min(steps, 10))),
+           "--warmup", "3", "--no-cpu-baseline", "--no-fusion-leg", "--no-cufft-leg", "--no-variants", "--no-p2p-variant",
+           "--fast-inputs", "--skip-e2e", "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2]), "--views", str(VIEWS)]
+    drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_NAME",
+            "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")
+    env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC_")}
+    env.update(SPIM_BRICK_P2P="1", SPIM_P2P_TIMEOUT_S="10")
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=limit_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)      # exactly the process group started above
+        except OSError:
+            pass
+        p.communicate()
+        return {"error": f"child job exceeded {limit_s:.0f} s and was stopped"}
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return {"error": f"child job exit {p.returncode}: {(err or '').strip()[-300:]}"}
+    d = json.loads(lines[-1])
+    return {"value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "steps": d.get("steps"),
+            "exchange": (d.get("config") or {}).get("parallelism"), "data": "noise inputs (timing only)",
+            "per_kernel_ms": {k: v.get("avg_ms") for k, v in ((d.get("roofline_conv_pass") or {}).get("per_kernel") or {}).items()}}
+
+
 _T0 = time.perf_counter()
 
 
@@ -304,6 +349,9 @@ def main():
     ap.add_argument("--no-cufft-leg", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the A/B matrix of kernel variants (an extra of the default run)")
     ap.add_argument("--variant-child", action="store_true", help="internal: one configuration of the A/B matrix")
+    ap.add_argument("--no-p2p-variant", action="store_true", help="N > 1: skip the child job that times the direct halo push")
+    ap.add_argument("--fast-inputs", action="store_true", help="internal: noise inputs instead of the synthetic specimen")
+    ap.add_argument("--skip-e2e", action="store_true", help="internal: timing-only child runs")
     ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
     ap.add_argument("--views", type=int, default=None)
@@ -356,7 +404,7 @@ def main():
     grid = bricks.grid_for(N)                        # bricks along (z, y, x)
     coords = bricks.rank_coords(rank, grid)
     gshape = tuple(BRICK[d] * grid[d] for d in range(3))
-    imgs, ws, psfs = make_inputs(BRICK, rank_seed=rank)
+    imgs, ws, psfs = make_inputs(BRICK, rank_seed=rank, fast=args.fast_inputs)
     tlog("inputs generated")
     nvox_brick = int(np.prod(BRICK))
     nvox_global = nvox_brick * N
@@ -467,18 +515,46 @@ def main():
 
     # ---------------- end to end through the reference-facing call -------------------------------------
     barrier()
-    t0 = time.perf_counter()
-    r2 = new_runner()
-    upload(r2)
-    r2.init()
-    r2.run(args.steps)
-    r2.finish()
-    r2.session.get_psi_ptr(pin_out.data_ptr())
-    torch.cuda.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    r2.close()
-    e2e_value = nvox_global * VIEWS * args.steps / t_e2e
-    tlog("e2e done")
+    t_e2e, e2e_value = None, None
+    if not args.skip_e2e:
+        t0 = time.perf_counter()
+        r2 = new_runner()
+        upload(r2)
+        r2.init()
+        r2.run(args.steps)
+        r2.finish()
+        r2.session.get_psi_ptr(pin_out.data_ptr())
+        torch.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        r2.close()
+        e2e_value = nvox_global * VIEWS * args.steps / t_e2e
+        tlog("e2e done")
+
+    # ---------------- reported extra at N > 1: the same job with the direct halo push (SPIM_BRICK_P2P=1) -------------------
+    # A separate torchrun job started by rank 0 (own process group, own NCCL communicator, hard time limit), so that the
+    # opt-in exchange path is timed on real links in every scaling run without being able to take this line with it.
+    # The other ranks wait on the host (a flag file), not in a collective, so no NCCL kernel spins on their GPUs meanwhile.
+    p2p_variant = None
+    if N > 1 and not args.no_p2p_variant and os.environ.get("SPIM_BRICK_P2P", "0") != "1":
+        flag = os.path.join("/tmp", "spim_bench_p2p_%s_%s" % (os.environ.get("MASTER_PORT", "0"),
+                                                              os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))))
+        if rank == 0:
+            try:
+                p2p_variant = p2p_variant_leg(N, args.steps)
+            except Exception as e:      # noqa: BLE001
+                p2p_variant = {"error": f"{type(e).__name__}: {e}"}
+            open(flag, "w").close()
+            tlog("p2p variant done")
+        else:
+            t_wait = time.perf_counter()
+            while not os.path.exists(flag) and time.perf_counter() - t_wait < 400:
+                time.sleep(0.2)
+        barrier()
+        if rank == 0:
+            try:
+                os.remove(flag)
+            except OSError:
+                pass
 
     # ---------------- CPU baseline: the oracle on a bounded sample (rank 0, N = 1 only) --------------------
     cpu = None
@@ -549,9 +625,10 @@ def main():
                        "fft_dims_zyx": list(info.fft_dims), "np_voxels_per_brick": np_brick,
                        "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), halo exchange: {exchange_path}" if N > 1 else "single GPU",
                        "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / args.steps,
-                    "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e,
-                    "note": "whole call: create + upload all views from pinned memory + init + K iterations + mask + download psi"},
+            "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / args.steps,
+                "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e,
+                "note": "whole call: create + upload all views from pinned memory + init + K iterations + mask + download psi"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -561,6 +638,7 @@ def main():
             "fusion_prestep": fusion_leg,
             "cufft_comparison": cufft_leg,
             "variants": variants,
+            "p2p_variant": p2p_variant,
         }
         print(json.dumps(line))
     sys.stdout.flush()
