@@ -274,7 +274,7 @@ def variant_child():
                       "ms_per_conv": sum(per.values()), "per_kernel_ms": per, "finite": psi_ok}))
 
 
-def variants_leg(budget_s=150.0, per_child_s=45.0):
+def variants_leg(budget_s=100.0, per_child_s=30.0):
     out, t_start = {}, time.perf_counter()
     for name, env in VARIANTS:
         if time.perf_counter() - t_start > budget_s:
@@ -607,7 +607,7 @@ def main():
             cufft_leg = {"error": f"{type(e).__name__}: {e}"}
         tlog("cufft leg done")
 
-    # ---------------- reported extra: A/B matrix of the in-tree kernel variants (bounded: <= 150 s, child processes) --------
+    # ---------------- reported extra: A/B matrix of the in-tree kernel variants (bounded: <= 100 s, child processes) --------
     variants = None
     if rank == 0 and N == 1 and not args.no_variants:
         try:
