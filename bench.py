@@ -238,6 +238,8 @@ VARIANTS = [
     ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
+    ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
+    ("z_tiles_6x128_threads", {"SPIM_REGCAP": "3"}),               # 24 resident warps on the z pass instead of 20 (80 registers)
     ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
@@ -268,10 +270,12 @@ def variant_child():
         s.set_timing(True)
         s.run(2, stats=False)
         kms, kcnt = s.get_timing()
-        psi_ok = bool(np.isfinite(s.get_psi()[::8, ::16, ::16]).all())
+        sample = s.get_psi()[::8, ::16, ::16].astype(np.float64)
+        psi_ok = bool(np.isfinite(sample).all())
     per = {KERNEL_NAMES[i]: kms[i] / kcnt[i] for i in range(len(KERNEL_NAMES)) if kcnt[i] > 0}
     print(json.dumps({"value": int(np.prod(BRICK)) * VIEWS * iters / dt, "ms_per_step": 1e3 * dt / iters,
-                      "ms_per_conv": sum(per.values()), "per_kernel_ms": per, "finite": psi_ok}))
+                      "ms_per_conv": sum(per.values()), "per_kernel_ms": per, "finite": psi_ok,
+                      "psi_checksum": float(sample.sum())}))
 
 
 def variants_leg(budget_s=100.0, per_child_s=30.0):
@@ -290,6 +294,10 @@ def variants_leg(budget_s=100.0, per_child_s=30.0):
         except Exception as e:      # noqa: BLE001
             out[name] = {"error": f"{type(e).__name__}: {e}"}
         out[name]["env"] = env
+    ref = out.get("default", {}).get("psi_checksum")
+    for name, d in out.items():      # same data, same iterations: every variant must land on the control's result
+        if ref and "psi_checksum" in d:
+            d["matches_default"] = bool(abs(d["psi_checksum"] - ref) <= 1e-5 * abs(ref))
     return out
 
 

@@ -152,7 +152,8 @@ inline int threads_col_for(size_t smem_bytes, size_t smem_limit) {
 }
 inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
 inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
-// SPIM_REGCAP=1 (experiment): run the column pass from an instantiation capped at 85 registers (3 x 256 threads per SM)
+// SPIM_REGCAP (experiments): 1 = column passes from an instantiation capped at 85 registers (3 x 256 threads per SM),
+// 2 = y tiles with 3 x 192 threads (<= 113 registers), 3 = z tiles with 6 x 128 threads (<= 85 registers)
 inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
 
@@ -390,7 +391,12 @@ public:
             p.ntiles = -1;    // async mode flag
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
-            if (use_regcap()) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            const int rc = use_regcap();
+            if (rc == 1) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            // SPIM_REGCAP=2: large tiles (three 72 KB y tiles per SM) with 192 threads each, <= 113 registers: 18 warps
+            else if (rc == 2 && smem > 40 * 1024 && 3 * (smem + 1024) <= lim && !p.kstage) rt::launch<ColPass, 192, 3>(p, grid, 192, smem, st);
+            // SPIM_REGCAP=3: small tiles (36 KB z tiles) as six blocks of 128 threads per SM, <= 85 registers: 24 warps
+            else if (rc == 3 && smem <= 37 * 1024 && !p.kstage) rt::launch<ColPass, 128, 6>(p, grid, 128, smem, st);
             else if (smem <= 40 * 1024 && threads_col() <= 128 && !p.kstage)
                 // small tiles (z pass of the 512x512x256 brick: 36 KB): registers, not shared memory, limit the resident
                 // blocks -- keep 5 blocks of 128 threads per SM (<= 102 registers) as in the measured round-1 binary
