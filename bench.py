@@ -236,6 +236,7 @@ VARIANTS = [
     ("default", {}),
     ("ieee_epilogue", {"SPIM_FAST_EPI": "0"}),                     # IEEE division / sqrt instead of the branch-free refinement
     ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
+    ("serpentine", {"SPIM_SERPENTINE": "1"}),                      # y-forward / x-inverse sweeps start on what is still in L2
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
     ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
@@ -244,6 +245,7 @@ VARIANTS = [
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
     ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+    ("pdl_serpentine", {"SPIM_PDL": "1", "SPIM_SERPENTINE": "1"}),
     ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),
     ("warp_private_columns_z", {"SPIM_COLP_Z": "4"}),
     ("kernel_spectrum_staged", {"SPIM_KSTAGE": "1"}),

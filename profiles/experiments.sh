@@ -29,6 +29,10 @@ run "SPIM_COLP=2 SPIM_KSTAGE=1"
 run "SPIM_FAST_EPI=0"                               # IEEE intrinsics instead of the (default) branch-free MUFU-seeded division / sqrt
 run "SPIM_COLP_Y=3"
 run "SPIM_PDL=1"                                    # programmatic dependent launch: tail of one sweep overlaps the ramp-up of the next
+run "SPIM_SERPENTINE=1"                             # y-forward / x-inverse sweeps reversed: start on the predecessor's L2 leftovers
+run "SPIM_PDL=1 SPIM_SERPENTINE=1"
+run "SPIM_REGCAP=2"                                 # y tiles: 3 x 192 threads
+run "SPIM_REGCAP=3"                                 # z tiles: 6 x 128 threads
 run "SPIM_PDL=1 SPIM_COL_NARROW=1"
 run "SPIM_COL_NARROW=1"                             # 8-column tiles (six 36 KB y tiles / eleven 18 KB z tiles per SM) on the C2 sizes
 run "SPIM_THREADS_XFWD=128"

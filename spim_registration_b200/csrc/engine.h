@@ -155,6 +155,10 @@ inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); re
 // SPIM_REGCAP (experiments): 1 = column passes from an instantiation capped at 85 registers (3 x 256 threads per SM),
 // 2 = y tiles with 3 x 192 threads (<= 113 registers), 3 = z tiles with 6 x 128 threads (<= 85 registers)
 inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
+// SPIM_SERPENTINE=1 (experiment): the y-forward pass and the x-inverse pass walk their tiles from the last to the first, so
+// that each starts on the ~100 MB its predecessor (x-forward / y-inverse, which end at the high planes) has just left in
+// the 126 MB L2, and the next x-forward pass (ascending) starts on what the x-inverse pass wrote last
+inline int use_serpentine() { return env_int_now("SPIM_SERPENTINE", 0); }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
 
 // per-axis override for A/B runs: SPIM_COLP_Y / SPIM_COLP_Z (e.g. the TMA pipeline for the 72 KB y tiles only)
@@ -331,6 +335,7 @@ public:
         const bool narrow = use_colp_for(axis) == 2 &&
                             (narrow_env >= 0 ? narrow_env != 0 : 2 * ((size_t)Pa * TC * sizeof(float2) + 1024) > lim);
         const int tcols = narrow ? TC / 2 : TC;
+        const int colp = use_colp_for(axis);
         p.ntx = pitch / tcols;
         if (axis == 1) { p.row_stride = pitch; p.outer_stride = (long long)pitch * P[1]; }
         else { p.row_stride = (long long)pitch * P[1]; p.outer_stride = pitch; }
@@ -342,9 +347,10 @@ public:
         p.sa = out_rows;
         p.mode = mode;
         const long long grid = (long long)p.ntx * outer_count;
+        p.nblocks = (int)grid;
+        p.reverse = (use_serpentine() && axis == 1 && mode == COL_FWD && colp == 2 && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)Pa * tcols * sizeof(float2);
         if (timer) timer->begin(id, st);
-        const int colp = use_colp_for(axis);
         if (narrow) {
             debug_counter(0) += 1;
             p.ntiles = -1;    // async mode flag
@@ -436,6 +442,8 @@ public:
         auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
         p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);
         const long long grid = (p.nlines + TC - 1) / TC;
+        p.nblocks = (int)grid;
+        p.reverse = (use_serpentine() && e.epi != EPI_STORE && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
         if (timer) timer->begin(K_XINV, st);
         const int T = threads_xinv();

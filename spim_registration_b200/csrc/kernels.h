@@ -319,6 +319,8 @@ struct ColPassParams {
     int mode;
     int ntiles, nctas;         // ColPassT (persistent): tiles in total / CTAs launched; ntiles < 0 selects the async mode of ColPass
     int kstage;                // COL_MID: kernel-spectrum tile staged in shared memory too
+    int reverse;               // ColPassN: tiles taken from the last to the first (serpentine sweep order, SPIM_SERPENTINE)
+    int nblocks;               // grid size, for the reversed order
     // ColPassT with tensor maps (use_tmap): y pass = 2-D map {2*pitch floats, Py*Pz rows}, box {32, box_rows};
     // z pass = 3-D map {2*pitch, Py, Pz}, box {32, 1, box_rows}; box_rows divides the FFT length
     int use_tmap, box_rows, tmap_rank;
@@ -361,6 +363,7 @@ struct ColPassN {
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
+        if (p.reverse) bid = p.nblocks - 1 - bid;
         const int o = bid / p.ntx;
         const int tx = bid - o * p.ntx;
         const int outer = o < p.outer_split ? o : o + p.outer_shift;
@@ -939,6 +942,8 @@ struct XInvParams {
     double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
     unsigned int* stat_max;    // max |change| as float bits
     int vec_ok;                // float2 accesses to dst / img / weight allowed and nx even
+    int reverse;               // tiles of lines taken from the last to the first (serpentine sweep order, SPIM_SERPENTINE)
+    int nblocks;
 };
 
 struct EpiAcc { double sum; float mx; };
@@ -1178,6 +1183,7 @@ struct XInvT {
         long long* srcoff = reinterpret_cast<long long*>(tile2 + (size_t)N2 * TC);
         long long* dstoff = srcoff + TC;
         long long* auxoff = dstoff + TC;
+        if (p.reverse) bid = p.nblocks - 1 - bid;
         SPIM_FOR_ITEMS(b, TC) {
             const long long l = (long long)bid * TC + b;
             long long so = -1, d_o = -1, a_o = -1;

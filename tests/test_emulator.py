@@ -315,3 +315,19 @@ def test_multi_device_block_queue_of_the_view_classes(emu_lib):
         assert np.abs(b - r).max() / np.abs(r).max() < P.TOL_CONV
     finally:
         _ViewFFT.cuda = saved
+
+
+def test_serpentine_sweep_order(emu_lib, monkeypatch):
+    """SPIM_SERPENTINE=1: the y-forward and x-inverse passes take their tiles from the last to the first (L2 reuse between
+    consecutive sweeps); the order of independent tiles must not change a single bit of the result."""
+    shape = (14, 18, 22)
+    _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
+    a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    monkeypatch.setenv("SPIM_SERPENTINE", "1")
+    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    assert np.array_equal(a, b)
+    P.conv_case(emu_lib, (9, 7, 11), (3, 5, 3), 2)
+    P.golden_case(emu_lib, 1, 1)
+    monkeypatch.setenv("SPIM_COL_NARROW", "1")
+    c, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    assert np.array_equal(a, c)

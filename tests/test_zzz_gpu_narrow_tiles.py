@@ -66,3 +66,15 @@ def test_configs2_size_on_one_gpu_delta_identity_and_shift(gpu):
     out = native.convolve(a, sh, O.EXT_MIRROR_SINGLE, lib=gpu)
     assert np.abs(out[5:] - a[:-5]).max() < 2e-6
     assert np.abs(out[:5] - a[5:0:-1]).max() < 2e-6       # mirror-single at the low z face
+
+
+def test_serpentine_sweep_order_is_bit_identical(gpu, monkeypatch):
+    """SPIM_SERPENTINE=1 only changes the order in which independent tiles are taken (L2 reuse between sweeps)."""
+    import numpy as np
+    from spim_registration_b200 import synthetic
+    shape = (40, 48, 56)
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 7, kind="beads")
+    a, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    monkeypatch.setenv("SPIM_SERPENTINE", "1")
+    b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    assert np.array_equal(a, b)
