@@ -39,6 +39,7 @@ VIEWS = 7
 PSF = 31
 LAMBDA = 0.006
 ITER_TYPE = 2                # EFFICIENT_BAYESIAN
+VARIANT_ITERS = 6            # timed iterations of a --variant-child run
 METRIC = "MV deconvolution voxel-view-iters/s"      # BASELINE.json: "MV deconvolution voxel-view-iters/s at 1/2/4/8 B200"
 UNIT = "voxel-view-iters/s"
 KERNEL_NAMES = ["x_fwd_r2c", "y_fwd", "z_fwd_mul_inv", "y_inv", "x_inv_c2r_epilogue"]
@@ -260,7 +261,7 @@ def variant_child():
     img = (0.05 + 0.95 * rng.random(BRICK, dtype=np.float32)).astype(np.float32)
     w = np.full(BRICK, np.float32(1.0 / VIEWS), np.float32)
     psfs = synthetic.make_psfs(VIEWS, PSF)
-    iters = 6
+    iters = VARIANT_ITERS
     with Session(BRICK, VIEWS, ITER_TYPE, generation=2, lam=LAMBDA) as s:
         for v in range(VIEWS):
             s.set_view(v, img, w, psfs[v])
@@ -272,12 +273,32 @@ def variant_child():
         s.set_timing(True)
         s.run(2, stats=False)
         kms, kcnt = s.get_timing()
+        info = s.info()
         sample = s.get_psi()[::8, ::16, ::16].astype(np.float64)
         psi_ok = bool(np.isfinite(sample).all())
     per = {KERNEL_NAMES[i]: kms[i] / kcnt[i] for i in range(len(KERNEL_NAMES)) if kcnt[i] > 0}
+    ms_conv = sum(per.values())
+    gbs = 44 * int(info.np_voxels) / (ms_conv * 1e-3) / 1e9 if ms_conv > 0 else None
     print(json.dumps({"value": int(np.prod(BRICK)) * VIEWS * iters / dt, "ms_per_step": 1e3 * dt / iters,
-                      "ms_per_conv": sum(per.values()), "per_kernel_ms": per, "finite": psi_ok,
+                      "ms_per_conv": ms_conv, "conv_pass_gbs": gbs, "conv_pass_frac": (gbs / peaks()[0]) if gbs else None,
+                      "per_kernel_ms": per, "fft_dims_zyx": list(info.fft_dims), "finite": psi_ok,
                       "psi_checksum": float(sample.sum())}))
+
+
+def config2_one_gpu_leg(limit_s=120.0):
+    """BASELINE configs[2] on ONE GPU -- the volume north_star quotes its 60 % target on: 6 views, 1024 x 1024 x 512, 31^3 PSFs,
+    Optimization II (FFT size 1080 x 1080 x 560, narrow column tiles selected automatically, ~62 GB of HBM).  Same torch-free
+    child as the variants; 2 + 2 iterations."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--variant-child", "--views", "6", "--brick", "512", "1024", "1024",
+           "--iter-type", "0", "--variant-iters", "2"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit_s)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        d = json.loads(lines[-1]) if (r.returncode == 0 and lines) else {"error": f"exit {r.returncode}: {(r.stderr or '').strip()[-200:]}"}
+    except Exception as e:      # noqa: BLE001
+        d = {"error": f"{type(e).__name__}: {e}"}
+    d["workload"] = "6-view 1024x1024x512 fp32, 31^3 PSFs, Optimization II, one GPU, noise inputs (timing only)"
+    return d
 
 
 def variants_leg(budget_s=100.0, per_child_s=30.0):
@@ -365,8 +386,14 @@ def main():
     ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-GPU brick (z y x), default 256 512 512")
     ap.add_argument("--views", type=int, default=None)
+    ap.add_argument("--iter-type", type=int, default=None, help="PSFTYPE ordinal (0 Optimization II ... 3 independent), default 2")
+    ap.add_argument("--variant-iters", type=int, default=None)
     args = ap.parse_args()
-    global BRICK, VIEWS
+    global BRICK, VIEWS, ITER_TYPE, VARIANT_ITERS
+    if args.iter_type is not None:
+        ITER_TYPE = args.iter_type
+    if args.variant_iters:
+        VARIANT_ITERS = args.variant_iters
     if args.brick:
         BRICK = tuple(args.brick)
     if args.views:
@@ -626,6 +653,12 @@ def main():
             variants = {"error": f"{type(e).__name__}: {e}"}
         tlog("variants done")
 
+    # ---------------- reported extra: the north_star target volume (configs[2]) on this one GPU ---------------------------
+    config2_leg = None
+    if rank == 0 and N == 1 and not args.no_variants and tuple(BRICK) == (256, 512, 512):
+        config2_leg = config2_one_gpu_leg()
+        tlog("configs[2] leg done")
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -649,6 +682,7 @@ def main():
             "cufft_comparison": cufft_leg,
             "variants": variants,
             "p2p_variant": p2p_variant,
+            "configs2_one_gpu": config2_leg,
         }
         print(json.dumps(line))
     sys.stdout.flush()
