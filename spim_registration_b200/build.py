@@ -26,7 +26,7 @@ ALIAS = os.path.join(HERE, "libFourierConvolutionCUDALib.so")
 OBJDIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
 
 
 def is_stale() -> bool:
