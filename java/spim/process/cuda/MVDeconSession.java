@@ -3,6 +3,7 @@ package spim.process.cuda;
 import com.sun.jna.Library;
 import com.sun.jna.Pointer;
 import com.sun.jna.Structure;
+import com.sun.jna.ptr.IntByReference;
 import com.sun.jna.ptr.PointerByReference;
 
 import java.util.Arrays;
@@ -55,5 +56,21 @@ public interface MVDeconSession extends Library
 	int mvd_get_psi( Pointer session, float[] out );
 	int mvd_set_psi( Pointer session, float[] in );
 	int mvd_get_kernel( Pointer session, int view, int which, float[] out );
+	/** views held in cells (CellImg) or beyond Java's 2^31-element arrays: one box of the image (which = 0) / weight (1) */
+	int mvd_upload_region( Pointer session, int view, int which, float[] data, int[] loZYX, int[] extZYX );
+
+	// ---- multi-device mode without host round trips (one Java thread per device, MVDeconFFT.java:447-469) ----------------
+	// one brick-mode session (Params.haloed = 1) per device; halos travel over NVLink peer memory, see spim_mvdecon.h
+	int mvd_set_halo_mask( Pointer session, int loMask, int hiMask );
+	int mvd_init_partials( Pointer session, double[] partial6 );
+	int mvd_set_avg( Pointer session, double avg, double osem );
+	int mvd_view_phase( Pointer session, int view, int phase, double[] stats2 );
+	int mvd_p2p_export( Pointer session, byte[] record288 );
+	int mvd_p2p_connect( Pointer session, int nPieces, byte[] records, int[] boxes9, int[] slots2 );
+	int mvd_p2p_push( Pointer session, int which );
+	int mvd_p2p_wait( Pointer session, int which );
+	int mvd_p2p_status( Pointer session, IntByReference timedOut );
+	int mvd_p2p_disconnect( Pointer session );
+
 	String mvd_last_error();
 }
