@@ -60,12 +60,12 @@ def test_configs2_size_on_one_gpu_delta_identity_and_shift(gpu):
     c0 = gpu.mvd_debug_counter(0)
     out = native.convolve(a, delta, O.EXT_MIRROR_SINGLE, lib=gpu)
     assert gpu.mvd_debug_counter(0) > c0                  # the 1080-long y passes ran on narrow tiles
-    assert np.abs(out - a).max() < 2e-6
+    assert np.abs(out - a).max() < 5e-6                   # fp32 round-off of a 1080 x 1080 x 560 transform pair on data in [0, 1)
     sh = np.zeros((31, 31, 31), np.float32)
     sh[20, 15, 15] = 1.0                                  # kernel index 20 along z = shift by +5 planes
     out = native.convolve(a, sh, O.EXT_MIRROR_SINGLE, lib=gpu)
-    assert np.abs(out[5:] - a[:-5]).max() < 2e-6
-    assert np.abs(out[:5] - a[5:0:-1]).max() < 2e-6       # mirror-single at the low z face
+    assert np.abs(out[5:] - a[:-5]).max() < 5e-6
+    assert np.abs(out[:5] - a[5:0:-1]).max() < 5e-6       # mirror-single at the low z face
 
 
 def test_serpentine_sweep_order_is_bit_identical(gpu, monkeypatch):
