@@ -245,6 +245,7 @@ VARIANTS = [
     ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
+    ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # 20 resident warps in the update kernel instead of 16 (spills)
     ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
     ("pdl_serpentine", {"SPIM_PDL": "1", "SPIM_SERPENTINE": "1"}),
     ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),

@@ -460,7 +460,13 @@ public:
             }
         }
         else if (e.exact_tikhonov) rt::launch<XInvT<EPI_UPDATE, MATH_EXACT64>>(p, grid, T, smem, st);
-        else if (p.fast_epilogue) rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
+        else if (p.fast_epilogue) {
+            // SPIM_XINV_CAP=5 (experiment): five 128-thread blocks of the update kernel per SM (96 registers, ~270 bytes of
+            // spills) instead of four at 128 registers
+            static int cap = env_int("SPIM_XINV_CAP", 0);
+            if (cap == 5 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
+            else rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
+        }
         else rt::launch<XInvT<EPI_UPDATE, MATH_IEEE>>(p, grid, T, smem, st);
         if (timer) timer->end(K_XINV, st);
     }
