@@ -245,6 +245,8 @@ VARIANTS = [
     ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
+    ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                 # x plan 5*7*8 instead of 8*7*5 (stage 0 = the register stage)
+    ("xinv_lean_update", {"SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),   # + update kernel compiled for stage-0 radix <= 5: 24 warps
     ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # 20 resident warps in the update kernel instead of 16 (spills)
     ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
     ("pdl_serpentine", {"SPIM_PDL": "1", "SPIM_SERPENTINE": "1"}),

@@ -88,8 +88,11 @@ struct FftPlanHost {
     std::vector<int> radices;
     std::vector<unsigned short> pos;   // pos[k]: row that holds frequency k after the DIF stages
 
-    void create(int n) {
+    // ascending: smallest radix first.  Stage 0 is the register-resident stage of the x kernels (first from global memory in
+    // x-forward, last with the fused epilogue in x-inverse); a small radix there keeps the epilogue's per-item state small
+    void create(int n, bool ascending = false) {
         if (!plan_radices(n, radices)) throw rt::Error("unsupported FFT length " + std::to_string(n));
+        if (ascending) std::reverse(radices.begin(), radices.end());
         memset(&dev, 0, sizeof(dev));
         dev.n = n;
         dev.nstages = (int)radices.size();
@@ -231,7 +234,7 @@ public:
         }
         N2 = P[2] / 2;
         pitch = ((N2 + 1 + TC - 1) / TC) * TC;
-        fx.create(N2); fy.create(P[1]); fz.create(P[0]);
+        fx.create(N2, env_int_now("SPIM_XPLAN_ASC", 0) != 0); fy.create(P[1]); fz.create(P[0]);
         const size_t need = std::max({(size_t)N2, (size_t)P[1], (size_t)P[0]}) * TC * sizeof(float2) + 512;
         if (need > rt::max_smem()) throw rt::Error("FFT axis too long for one shared-memory tile");
         d_pos = (unsigned short*)rt::dmalloc(sizeof(unsigned short) * N2);
@@ -464,7 +467,14 @@ public:
             // SPIM_XINV_CAP=5 (experiment): five 128-thread blocks of the update kernel per SM (96 registers, ~270 bytes of
             // spills) instead of four at 128 registers
             static int cap = env_int("SPIM_XINV_CAP", 0);
-            if (cap == 5 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
+            // SPIM_XINV_R0=1 (experiment, with SPIM_XPLAN_ASC=1): when the x plan starts with a small radix, run the update
+            // from an instantiation compiled for stage-0 radices <= 5 (80 registers, six 128-thread blocks per SM, no spills)
+            // or <= 7 (96 registers, five blocks) instead of the general one (128 registers, four blocks)
+            const int lean = env_int_now("SPIM_XINV_R0", 0);
+            const int r0 = fx.dev.radix[0];
+            if (lean && r0 <= 5 && T <= 128 && 6 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 128, 6>(p, grid, T, smem, st);
+            else if (lean && r0 <= 7 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR7, 128, 5>(p, grid, T, smem, st);
+            else if (cap == 5 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
             else rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
         }
         else rt::launch<XInvT<EPI_UPDATE, MATH_IEEE>>(p, grid, T, smem, st);

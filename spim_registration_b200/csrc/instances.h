@@ -14,6 +14,8 @@ typedef XInvT<EPI_RATIO, MATH_FAST> XInvRatioFast;
 typedef XInvT<EPI_UPDATE, MATH_IEEE> XInvUpdateIeee;
 typedef XInvT<EPI_UPDATE, MATH_FAST> XInvUpdateFast;
 typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
+typedef XInvT<EPI_UPDATE, MATH_FAST, 5> XInvUpdateFastR5;     // last stage compiled for radices <= 5 only (engine.h, SPIM_XINV_R0)
+typedef XInvT<EPI_UPDATE, MATH_FAST, 7> XInvUpdateFastR7;
 }
 
 #define SPIM_INSTANCES_COL_A(X) X(ColPass, 256, 1) X(ColPass, 384, 1)
@@ -24,7 +26,7 @@ typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
 #define SPIM_INSTANCES_X_A(X) X(XFwd, 256, 1) X(XFwd, 192, 4) X(XInvStore, 256, 1) X(XInvRatioIeee, 256, 1) X(XInvRatioIeee, 128, 6)
 #define SPIM_INSTANCES_X_B(X) X(XInvRatioFast, 256, 1) X(XInvRatioFast, 128, 6) X(XInvUpdateFast, 256, 1)
 #define SPIM_INSTANCES_X_C(X) X(XInvUpdateIeee, 256, 1) X(XInvUpdateExact64, 256, 1)
-#define SPIM_INSTANCES_X_D(X) X(XInvUpdateFast, 128, 5)
+#define SPIM_INSTANCES_X_D(X) X(XInvUpdateFast, 128, 5) X(XInvUpdateFastR5, 128, 6) X(XInvUpdateFastR7, 128, 5)
 #define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "COL_E", "X_A", "X_B", "X_C", "X_D"
 #define SPIM_INSTANCES_ALL(X)                                                                                      \
     SPIM_INSTANCES_COL_A(X) SPIM_INSTANCES_COL_B(X) SPIM_INSTANCES_COL_C(X) SPIM_INSTANCES_COL_D(X)                \

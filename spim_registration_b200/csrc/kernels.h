@@ -284,6 +284,17 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
 #define SPIM_MAX_RADIX 10
 #endif
 #define SPIM_RADIX_CASE(N, CALL) case N: if constexpr (N <= SPIM_MAX_RADIX) { constexpr int RR = N; CALL; } break;
+// the same switch restricted to radices <= MAXR (register-lean instantiations of a kernel phase)
+#define SPIM_RADIX_CASE_MAX(N, MAXR, CALL) case N: if constexpr (N <= SPIM_MAX_RADIX && N <= (MAXR)) { constexpr int RR = N; CALL; } break;
+#define SPIM_RADIX_SWITCH_MAX(R_, MAXR, CALL)                                                    \
+    switch (R_) {                                                                                \
+        SPIM_RADIX_CASE_MAX(2, MAXR, CALL) SPIM_RADIX_CASE_MAX(3, MAXR, CALL) SPIM_RADIX_CASE_MAX(4, MAXR, CALL)   \
+        SPIM_RADIX_CASE_MAX(5, MAXR, CALL) SPIM_RADIX_CASE_MAX(6, MAXR, CALL) SPIM_RADIX_CASE_MAX(7, MAXR, CALL)   \
+        SPIM_RADIX_CASE_MAX(8, MAXR, CALL) SPIM_RADIX_CASE_MAX(9, MAXR, CALL) SPIM_RADIX_CASE_MAX(10, MAXR, CALL)  \
+        SPIM_RADIX_CASE_MAX(11, MAXR, CALL) SPIM_RADIX_CASE_MAX(12, MAXR, CALL) SPIM_RADIX_CASE_MAX(13, MAXR, CALL) \
+        SPIM_RADIX_CASE_MAX(14, MAXR, CALL) SPIM_RADIX_CASE_MAX(15, MAXR, CALL) SPIM_RADIX_CASE_MAX(16, MAXR, CALL) \
+        default: break;                                                                          \
+    }
 #define SPIM_RADIX_SWITCH(R_, CALL)                                                              \
     switch (R_) {                                                                                \
         SPIM_RADIX_CASE(2, CALL) SPIM_RADIX_CASE(3, CALL) SPIM_RADIX_CASE(4, CALL)               \
@@ -1172,7 +1183,10 @@ SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* 
     }
 }
 
-template <int EPI, int MATH>
+// R0MAX: largest radix the register-resident last stage (plan.radix[0]) is compiled for.  The epilogue keeps 8 R floats per
+// item in registers (spectrum row, two prefetched inputs, twiddles), so an instantiation for R0MAX = 5 is much leaner than
+// the general one; the host only selects it when the x plan starts with a radix <= R0MAX (SPIM_XPLAN_ASC orders it so).
+template <int EPI, int MATH, int R0MAX = 16>
 struct XInvT {
     typedef XInvParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
@@ -1204,8 +1218,8 @@ struct XInvT {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
-        else { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
+        if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }
 };

@@ -331,3 +331,23 @@ def test_serpentine_sweep_order(emu_lib, monkeypatch):
     monkeypatch.setenv("SPIM_COL_NARROW", "1")
     c, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
     assert np.array_equal(a, c)
+
+
+def test_ascending_x_plan_and_lean_update_kernel(emu_lib, monkeypatch):
+    """SPIM_XPLAN_ASC=1 orders the x plan smallest radix first (stage 0 is the register-resident stage of the x kernels);
+    SPIM_XINV_R0=1 then runs the update from the instantiation compiled for small stage-0 radices.  Same arithmetic per
+    butterfly, different factor order: results agree with the default to round-off and meet the same parity bar."""
+    shape = (14, 18, 22)
+    _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
+    a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    monkeypatch.setenv("SPIM_XPLAN_ASC", "1")
+    monkeypatch.setenv("SPIM_XINV_R0", "1")
+    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    per, l2 = O.parity_errors(b, a)
+    assert per <= 2e-5 and l2 <= 2e-6, (per, l2)
+    P.decon_case(emu_lib, (14, 18, 22), 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
+    P.decon_case(emu_lib, (9, 11, 13), 2, 3, O.INDEPENDENT, 2, 2, lam=0.0, use_weights=False)
+    for n in (20, 30, 42, 56, 60, 70, 84, 100, 120, 140):          # x plans with several stages: 10 = 2*5 ... 70 = 2*5*7
+        P.legacy_case(emu_lib, (4, 4, n), (3, 3, 3), seed=n)
+    for ext in range(5):
+        P.conv_case(emu_lib, (5, 30, 33), (1, 7, 9), ext)

@@ -78,3 +78,15 @@ def test_serpentine_sweep_order_is_bit_identical(gpu, monkeypatch):
     monkeypatch.setenv("SPIM_SERPENTINE", "1")
     b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
     assert np.array_equal(a, b)
+
+
+def test_ascending_x_plan_and_lean_update_kernel(gpu, monkeypatch):
+    """SPIM_XPLAN_ASC=1 + SPIM_XINV_R0=1: x plan smallest radix first and the register-lean update kernel (80 registers, six
+    blocks per SM); same parity bar as the default."""
+    monkeypatch.setenv("SPIM_XPLAN_ASC", "1")
+    monkeypatch.setenv("SPIM_XINV_R0", "1")
+    P.decon_case(gpu, (40, 48, 56), 3, 7, O.EFFICIENT_BAYESIAN, 2, 3)
+    P.decon_case(gpu, (33, 41, 50), 2, 5, O.OPTIMIZATION_I, 1, 2)
+    P.decon_case(gpu, (16, 20, 524), 2, 31, O.EFFICIENT_BAYESIAN, 2, 2)      # x FFT length 560: N2 = 280 = 5 * 7 * 8, the bench plan
+    for ext in range(5):
+        P.conv_case(gpu, (40, 50, 70), (7, 9, 5), ext)
