@@ -240,6 +240,7 @@ VARIANTS = [
     ("serpentine", {"SPIM_SERPENTINE": "1"}),                      # y-forward / x-inverse sweeps start on what is still in L2
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
+    ("lean_z_pass", {"SPIM_COL_LEAN": "1"}),                       # z pass (288 = 8*6*6) compiled for radices <= 8: 80 registers, 24 warps
     ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
     ("z_tiles_6x128_threads", {"SPIM_REGCAP": "3"}),               # 24 resident warps on the z pass instead of 20 (80 registers)
     ("col_160_threads", {"SPIM_THREADS_COL": "160"}),

@@ -33,6 +33,7 @@ run "SPIM_SERPENTINE=1"                             # y-forward / x-inverse swee
 run "SPIM_PDL=1 SPIM_SERPENTINE=1"
 run "SPIM_XPLAN_ASC=1"                               # x plan smallest radix first
 run "SPIM_XPLAN_ASC=1 SPIM_XINV_R0=1"                # + register-lean update kernel (80 registers, 6 blocks per SM)
+run "SPIM_COL_LEAN=1"                               # z pass from the radix <= 8 instantiation (80 registers, 6 blocks)
 run "SPIM_REGCAP=2"                                 # y tiles: 3 x 192 threads
 run "SPIM_REGCAP=3"                                 # z tiles: 6 x 128 threads
 run "SPIM_PDL=1 SPIM_COL_NARROW=1"

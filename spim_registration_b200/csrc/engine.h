@@ -401,7 +401,16 @@ public:
             static int ks = env_int("SPIM_KSTAGE", 0);
             p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
             const int rc = use_regcap();
-            if (rc == 1) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
+            // SPIM_COL_LEAN=1 (experiment): plans without radices 9 / 10 (288 = 8*6*6, the z axis of the bench volume) run from
+            // an instantiation compiled for radices <= 8 only: 80 registers without spills instead of 127 (96 when capped), so
+            // six 128-thread blocks of a 36 KB tile are resident per SM instead of five
+            int rmax = 0;
+            for (int s_ = 0; s_ < p.plan.nstages; ++s_) rmax = std::max(rmax, p.plan.radix[s_]);
+            if (env_int_now("SPIM_COL_LEAN", 0) && rmax <= 8 && !p.kstage) {
+                if (smem <= 37 * 1024) rt::launch<ColPassR8, 128, 6>(p, grid, 128, smem, st);
+                else rt::launch<ColPassR8, 256, 1>(p, grid, threads_col_for(smem, lim), smem, st);
+            }
+            else if (rc == 1) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
             // SPIM_REGCAP=2: large tiles (three 72 KB y tiles per SM) with 192 threads each, <= 113 registers: 18 warps
             else if (rc == 2 && smem > 40 * 1024 && 3 * (smem + 1024) <= lim && !p.kstage) rt::launch<ColPass, 192, 3>(p, grid, 192, smem, st);
             // SPIM_REGCAP=3: small tiles (36 KB z tiles) as six blocks of 128 threads per SM, <= 85 registers: 24 warps

@@ -305,14 +305,15 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
         default: break;                                                                          \
     }
 
-template <bool INV, int W = TP>
+// RMAX: largest radix the instantiation is compiled for (register-lean variants for plans without large radices)
+template <bool INV, int W = TP, int RMAX = 16>
 SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
-    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, true, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
-    else { SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile<RR, INV, false, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, true, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+    else { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, false, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
 }
-template <int W = TP>
+template <int W = TP, int RMAX = 16>
 SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
-    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile<RR, W>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
+    SPIM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], RMAX, (mid_tile<RR, W>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,7 +369,7 @@ SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_l
 // W = TP: tiles of 16 x-frequencies (the default); W = TP / 2: narrow tiles of 8 (ntx = pitch / 8), half the shared memory
 // per block -- for FFT lengths above ~880, where a 16-column tile would leave a single block per SM and nothing to overlap
 // its load / compute / store phases with
-template <int W>
+template <int W, int RMAX = 16>
 struct ColPassN {
     typedef ColPassParams Params;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
@@ -412,18 +413,19 @@ struct ColPassN {
             g.va = P; g.vb = P;
         }
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false, W>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true, W>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false, W>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
-            mid_dispatch<W>(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch<true, W>(tg, pl, s, tile, 0, 0, s == 0, g);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
+            mid_dispatch<W, RMAX>(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, 0, s == 0, g);
         }
     }
 };
 typedef ColPassN<TP> ColPass;
 typedef ColPassN<TP / 2> ColPassNarrow;
+typedef ColPassN<TP, 8> ColPassR8;          // plans without radices 9 / 10 (e.g. 288 = 8 * 6 * 6): leaner in registers
 
 // tile index -> offset of its first element (x tiles fastest, outer index mapped over the zero gap)
 SPIM_DEV void col_tile_base(const ColPassParams& p, int t, long long& base) {

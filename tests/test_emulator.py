@@ -351,3 +351,18 @@ def test_ascending_x_plan_and_lean_update_kernel(emu_lib, monkeypatch):
         P.legacy_case(emu_lib, (4, 4, n), (3, 3, 3), seed=n)
     for ext in range(5):
         P.conv_case(emu_lib, (5, 30, 33), (1, 7, 9), ext)
+
+
+def test_lean_column_pass_for_small_radix_plans(emu_lib, monkeypatch):
+    """SPIM_COL_LEAN=1: column plans without radices 9 / 10 run from the instantiation compiled for radices <= 8 (same
+    butterflies, fewer registers); plans that do need them keep the general kernel.  Bit-identical results."""
+    shape = (14, 18, 22)
+    _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
+    a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    monkeypatch.setenv("SPIM_COL_LEAN", "1")
+    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    assert np.array_equal(a, b)
+    for n in (16, 24, 28, 36, 48, 56, 64, 72, 84, 96, 112, 128, 144, 288,      # radices <= 8 only
+              18, 20, 30, 50, 90, 100, 560):                                   # plans with 9 / 10: general kernel
+        for shp in ((n, 4, 8), (4, n, 8)):
+            P.legacy_case(emu_lib, shp, (3, 3, 3), seed=n)

@@ -90,3 +90,19 @@ def test_ascending_x_plan_and_lean_update_kernel(gpu, monkeypatch):
     P.decon_case(gpu, (16, 20, 524), 2, 31, O.EFFICIENT_BAYESIAN, 2, 2)      # x FFT length 560: N2 = 280 = 5 * 7 * 8, the bench plan
     for ext in range(5):
         P.conv_case(gpu, (40, 50, 70), (7, 9, 5), ext)
+
+
+def test_lean_column_pass_is_bit_identical(gpu, monkeypatch):
+    """SPIM_COL_LEAN=1: plans without radices 9 / 10 (the 288-point z axis of the bench volume) from the instantiation compiled
+    for radices <= 8 -- 80 registers, six resident blocks; the butterflies are the same code, so is every bit of the result."""
+    import numpy as np
+    from spim_registration_b200 import synthetic
+    shape = (40, 48, 56)
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 7, kind="beads")
+    a, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    monkeypatch.setenv("SPIM_COL_LEAN", "1")
+    b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+    assert np.array_equal(a, b)
+    for n in (48, 64, 96, 128, 288):
+        for shp in ((n, 4, 8), (4, n, 8)):
+            P.legacy_case(gpu, shp, (3, 3, 3), seed=n)
