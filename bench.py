@@ -236,21 +236,23 @@ def fusion_prestep_leg(shape, views, peak, lib=None, timed=None, stack_planes=No
 VARIANTS = [
     ("default", {}),
     ("ieee_epilogue", {"SPIM_FAST_EPI": "0"}),                     # IEEE division / sqrt instead of the branch-free refinement
+    ("lean_z_pass", {"SPIM_COL_LEAN": "1"}),                       # z pass (288 = 8*6*6) compiled for radices <= 8: 80 registers, 24 warps
+    ("xinv_lean_update", {"SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),   # x plan 5*7*8 + update kernel for stage-0 radix <= 5: 24 warps
     ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
     ("serpentine", {"SPIM_SERPENTINE": "1"}),                      # y-forward / x-inverse sweeps start on what is still in L2
+    ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
+    ("combined", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_PDL": "1", "SPIM_SERPENTINE": "1",
+                  "SPIM_REGCAP": "2"}),                            # everything above at once (are the gains additive?)
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
-    ("lean_z_pass", {"SPIM_COL_LEAN": "1"}),                       # z pass (288 = 8*6*6) compiled for radices <= 8: 80 registers, 24 warps
-    ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
-    ("z_tiles_6x128_threads", {"SPIM_REGCAP": "3"}),               # 24 resident warps on the z pass instead of 20 (80 registers)
-    ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
-    ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
-    ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
-    ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                 # x plan 5*7*8 instead of 8*7*5 (stage 0 = the register stage)
-    ("xinv_lean_update", {"SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),   # + update kernel compiled for stage-0 radix <= 5: 24 warps
-    ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # 20 resident warps in the update kernel instead of 16 (spills)
-    ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+    ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                  # the plan order alone
+    ("z_tiles_6x128_threads", {"SPIM_REGCAP": "3"}),               # general kernel capped to 80 registers (spills) on the z pass
     ("pdl_serpentine", {"SPIM_PDL": "1", "SPIM_SERPENTINE": "1"}),
+    ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
+    ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # general update kernel capped to 96 registers (spills)
+    ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
+    ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+    ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),
     ("warp_private_columns_z", {"SPIM_COLP_Z": "4"}),
     ("kernel_spectrum_staged", {"SPIM_KSTAGE": "1"}),
@@ -305,10 +307,10 @@ def config2_one_gpu_leg(limit_s=120.0):
     return d
 
 
-def variants_leg(budget_s=100.0, per_child_s=30.0):
+def variants_leg(budget_s=120.0, per_child_s=30.0):
     out, t_start = {}, time.perf_counter()
     for name, env in VARIANTS:
-        if time.perf_counter() - t_start > budget_s:
+        if time.perf_counter() - t_start > budget_s - 6.0:       # a child takes about six seconds
             out[name] = {"skipped": "time budget of this extra used up"}
             continue
         try:
@@ -613,55 +615,67 @@ def main():
                          "workload; CPU restatement of the reference (NumPy + SciPy pocketfft, all cores); "
                          "reference JVM unavailable"}
 
-    # ---------------- reported extra: the device-side fusion pre-step (never allowed to break the line) ------------
-    fusion_leg = None
-    if rank == 0 and N == 1 and not args.no_fusion_leg:
-        # in a child process: a fault in this extra can then never take the benchmark line with it
-        try:
-            cmd = [sys.executable, os.path.abspath(__file__), "--fusion-leg-only", "--views", str(VIEWS),
-                   "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2])]
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-            out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            fusion_leg = json.loads(out[-1]) if (r.returncode == 0 and out) else {
-                "error": f"child exited with {r.returncode}: {(r.stderr or '').strip()[-300:]}"}
-        except Exception as e:      # noqa: BLE001
-            fusion_leg = {"error": f"{type(e).__name__}: {e}"}
-        tlog("fusion leg done")
+    # ---------------- reported extras (rank 0, N = 1; child processes, so that none of them can take the line with it) ------
+    # All extras together respect one wall-clock deadline counted from the start of this process (SPIM_BENCH_EXTRAS_S, default
+    # 230 s): whatever does not fit is reported as skipped, so that the default run ends within about four minutes.
+    deadline = _T0 + float(os.environ.get("SPIM_BENCH_EXTRAS_S", "230"))
 
-    # ---------------- reported extra: the same convolution built on cuFFT (comparison point only, separate executable) ----
+    def time_left():
+        return deadline - time.perf_counter()
+
+    skipped = {"skipped": "time budget of the extras used up"}
+
+    # the same convolution built on cuFFT (comparison point only, separate executable)
     cufft_leg = None
     if rank == 0 and N == 1 and not args.no_cufft_leg:
         try:
-            exe = b.build_cufft_comparison()
+            exe = b.build_cufft_comparison() if time_left() > 15 else None
             if exe:
                 fd = [int(v) for v in info.fft_dims]
                 cmd = [exe, str(BRICK[0]), str(BRICK[1]), str(BRICK[2]), str(PSF), str(fd[0]), str(fd[1]), str(fd[2]), "20"]
-                r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=max(15.0, min(120.0, time_left())))
                 out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
                 cufft_leg = json.loads(out[-1]) if out else {"error": f"exit {r.returncode}: {(r.stderr or '').strip()[-200:]}"}
                 if conv_pass and "ms_per_conv" in cufft_leg:
                     cufft_leg["ours_ms_per_conv"] = conv_pass["ms_per_conv"]
                     cufft_leg["speedup_ours_vs_cufft"] = cufft_leg["ms_per_conv"] / conv_pass["ms_per_conv"]
             else:
-                cufft_leg = {"error": "comparison binary not built"}
+                cufft_leg = dict(skipped) if time_left() <= 15 else {"error": "comparison binary not built"}
         except Exception as e:      # noqa: BLE001
             cufft_leg = {"error": f"{type(e).__name__}: {e}"}
         tlog("cufft leg done")
 
-    # ---------------- reported extra: A/B matrix of the in-tree kernel variants (bounded: <= 100 s, child processes) --------
+    # A/B matrix of the in-tree kernel variants
     variants = None
     if rank == 0 and N == 1 and not args.no_variants:
         try:
-            variants = variants_leg()
+            variants = variants_leg(budget_s=min(120.0, time_left() - 35.0))      # keep room for the configs[2] leg
         except Exception as e:      # noqa: BLE001
             variants = {"error": f"{type(e).__name__}: {e}"}
         tlog("variants done")
 
-    # ---------------- reported extra: the north_star target volume (configs[2]) on this one GPU ---------------------------
+    # the north_star target volume (configs[2]) on this one GPU
     config2_leg = None
     if rank == 0 and N == 1 and not args.no_variants and tuple(BRICK) == (256, 512, 512):
-        config2_leg = config2_one_gpu_leg()
+        config2_leg = config2_one_gpu_leg(limit_s=max(30.0, min(120.0, time_left() + 30.0))) if time_left() > 10 else dict(skipped)
         tlog("configs[2] leg done")
+
+    # the device-side fusion pre-step
+    fusion_leg = None
+    if rank == 0 and N == 1 and not args.no_fusion_leg:
+        if time_left() > 20:
+            try:
+                cmd = [sys.executable, os.path.abspath(__file__), "--fusion-leg-only", "--views", str(VIEWS),
+                       "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2])]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=max(30.0, min(120.0, time_left() + 30.0)))
+                out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                fusion_leg = json.loads(out[-1]) if (r.returncode == 0 and out) else {
+                    "error": f"child exited with {r.returncode}: {(r.stderr or '').strip()[-300:]}"}
+            except Exception as e:      # noqa: BLE001
+                fusion_leg = {"error": f"{type(e).__name__}: {e}"}
+        else:
+            fusion_leg = dict(skipped)
+        tlog("fusion leg done")
 
     if rank == 0:
         line = {
