@@ -252,6 +252,7 @@ VARIANTS = [
     ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # general update kernel capped to 96 registers (spills)
     ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
     ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
+    ("xfwd_128_threads", {"SPIM_THREADS_XFWD": "128"}),
     ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
     ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),
     ("warp_private_columns_z", {"SPIM_COLP_Z": "4"}),
