@@ -243,6 +243,8 @@ VARIANTS = [
     ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
     ("combined", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_PDL": "1", "SPIM_SERPENTINE": "1",
                   "SPIM_REGCAP": "2"}),                            # everything above at once (are the gains additive?)
+    ("x_kernels_160_threads", {"SPIM_THREADS_XFWD": "160", "SPIM_THREADS_XINV": "160", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),
+                                                                   # item counts per phase fit 160 threads: 5 blocks of 160 per SM
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
     ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                  # the plan order alone

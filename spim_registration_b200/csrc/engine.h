@@ -319,7 +319,10 @@ public:
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         if (timer) timer->begin(K_XFWD, st);
         // four 192-thread blocks per SM (the measured round-1 configuration) need <= 85 registers
-        if (threads_xfwd() <= 192) rt::launch<XFwd, 192, 4>(p, grid, threads_xfwd(), smem, st);
+        // SPIM_THREADS_XFWD=160 (experiment): the phases of a 280-point tile hold 280 / 320 / 448 / 282 items -- 160 threads need
+        // the same 2 + 2 + 3 + 2 rounds as 192 do, so five blocks of 160 (72 registers) replace four of 192
+        if (threads_xfwd() == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XFwd, 160, 5>(p, grid, 160, smem, st);
+        else if (threads_xfwd() <= 192) rt::launch<XFwd, 192, 4>(p, grid, threads_xfwd(), smem, st);
         else rt::launch<XFwd>(p, grid, threads_xfwd(), smem, st);
         if (timer) timer->end(K_XFWD, st);
     }
@@ -464,7 +467,9 @@ public:
         if (e.epi == EPI_STORE) rt::launch<XInvT<EPI_STORE, MATH_IEEE>>(p, grid, T, smem, st);
         else if (e.epi == EPI_RATIO) {
             if (p.fast_epilogue) {
-                if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_FAST>, 128, 6>(p, grid, T, smem, st);
+                // SPIM_THREADS_XINV=160 (experiment): 11 rounds per tile instead of 15 with 128 threads, five blocks per SM
+                if (T == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvRatioFast, 160, 5>(p, grid, 160, smem, st);
+                else if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_FAST>, 128, 6>(p, grid, T, smem, st);
                 else rt::launch<XInvT<EPI_RATIO, MATH_FAST>>(p, grid, T, smem, st);
             } else {
                 if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_IEEE>, 128, 6>(p, grid, T, smem, st);
@@ -481,7 +486,8 @@ public:
             // or <= 7 (96 registers, five blocks) instead of the general one (128 registers, four blocks)
             const int lean = env_int_now("SPIM_XINV_R0", 0);
             const int r0 = fx.dev.radix[0];
-            if (lean && r0 <= 5 && T <= 128 && 6 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 128, 6>(p, grid, T, smem, st);
+            if (lean && r0 <= 5 && T == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 160, 5>(p, grid, 160, smem, st);
+            else if (lean && r0 <= 5 && T <= 128 && 6 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 128, 6>(p, grid, T, smem, st);
             else if (lean && r0 <= 7 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR7, 128, 5>(p, grid, T, smem, st);
             else if (cap == 5 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
             else rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);

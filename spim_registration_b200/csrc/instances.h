@@ -28,11 +28,12 @@ typedef XInvT<EPI_UPDATE, MATH_FAST, 7> XInvUpdateFastR7;
 #define SPIM_INSTANCES_X_B(X) X(XInvRatioFast, 256, 1) X(XInvRatioFast, 128, 6) X(XInvUpdateFast, 256, 1)
 #define SPIM_INSTANCES_X_C(X) X(XInvUpdateIeee, 256, 1) X(XInvUpdateExact64, 256, 1)
 #define SPIM_INSTANCES_X_D(X) X(XInvUpdateFast, 128, 5) X(XInvUpdateFastR5, 128, 6) X(XInvUpdateFastR7, 128, 5)
-#define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "COL_E", "COL_F", "X_A", "X_B", "X_C", "X_D"
+#define SPIM_INSTANCES_X_E(X) X(XFwd, 160, 5) X(XInvRatioFast, 160, 5) X(XInvUpdateFastR5, 160, 5)
+#define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "COL_E", "COL_F", "X_A", "X_B", "X_C", "X_D", "X_E"
 #define SPIM_INSTANCES_ALL(X)                                                                                      \
     SPIM_INSTANCES_COL_A(X) SPIM_INSTANCES_COL_B(X) SPIM_INSTANCES_COL_C(X) SPIM_INSTANCES_COL_D(X)                \
     SPIM_INSTANCES_COL_E(X) SPIM_INSTANCES_COL_F(X)                                                                                        \
-    SPIM_INSTANCES_X_A(X) SPIM_INSTANCES_X_B(X) SPIM_INSTANCES_X_C(X) SPIM_INSTANCES_X_D(X)
+    SPIM_INSTANCES_X_A(X) SPIM_INSTANCES_X_B(X) SPIM_INSTANCES_X_C(X) SPIM_INSTANCES_X_D(X) SPIM_INSTANCES_X_E(X)
 
 #if defined(SPIM_SPLIT_BUILD) && !defined(SPIM_HOST_EMU)
 namespace spim {
