@@ -241,10 +241,12 @@ VARIANTS = [
     ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
     ("serpentine", {"SPIM_SERPENTINE": "1"}),                      # y-forward / x-inverse sweeps start on what is still in L2
     ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
-    ("combined", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_PDL": "1", "SPIM_SERPENTINE": "1",
-                  "SPIM_REGCAP": "2"}),                            # everything above at once (are the gains additive?)
     ("x_kernels_160_threads", {"SPIM_THREADS_XFWD": "160", "SPIM_THREADS_XINV": "160", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),
                                                                    # item counts per phase fit 160 threads: 5 blocks of 160 per SM
+    ("combined", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_THREADS_XFWD": "160",
+                  "SPIM_THREADS_XINV": "160", "SPIM_SERPENTINE": "1", "SPIM_REGCAP": "2"}),   # are the gains additive?
+    ("combined_pdl", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_THREADS_XFWD": "160",
+                      "SPIM_THREADS_XINV": "160", "SPIM_SERPENTINE": "1", "SPIM_REGCAP": "2", "SPIM_PDL": "1"}),
     ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
     ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
     ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                  # the plan order alone
