@@ -1,9 +1,8 @@
 """Direct halo push over peer memory (mvd_p2p_*, SPIM_BRICK_P2P=1) on CPU: world_size 2 / 4 / 8 ranks as THREADS of one
 process, each driving the kernel emulator on its brick, so that the ranks really reach each other's buffers through raw
-pointers and really run concurrently (ctypes releases the GIL; the emulated wait kernel spins on the flag words).  A small
-in-process stand-in for torch.distributed supplies the few collectives the runner needs.  The assembled psi must equal the
+pointers and really run concurrently (ctypes releases the GIL; the emulated wait kernel spins on the flag words).  The package's
+in-process group (spim_registration_b200/inprocess.py) supplies the few collectives the runner needs.  The assembled psi must equal the
 oracle's result on the whole volume, and every rank must actually have adopted the push path (no silent fallback)."""
-import collections
 import os
 import sys
 import threading
@@ -14,68 +13,6 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class _Shared:
-    def __init__(self, world):
-        self.world = world
-        self.barrier = threading.Barrier(world)
-        self.slots = [None] * world
-        self.mail = collections.defaultdict(collections.deque)
-        self.lock = threading.Lock()
-
-
-class _Work:
-    def wait(self):
-        return True
-
-
-class ThreadDist:
-    """The subset of torch.distributed that bricks.BrickRunner uses, for N threads of one process."""
-
-    class ReduceOp:
-        SUM, MIN, MAX = "sum", "min", "max"
-
-    isend, irecv = "isend", "irecv"
-
-    def __init__(self, shared, rank):
-        self.sh, self.rank = shared, rank
-
-    @staticmethod
-    def P2POp(op, tensor, peer):
-        return (op, tensor, peer)
-
-    def barrier(self):
-        self.sh.barrier.wait()
-
-    def all_reduce(self, t, op=None):
-        import torch
-        self.sh.slots[self.rank] = t.clone()
-        self.sh.barrier.wait()
-        st = torch.stack(list(self.sh.slots))
-        res = {"sum": st.sum(0), "min": st.min(0).values, "max": st.max(0).values}[op or "sum"]
-        self.sh.barrier.wait()
-        t.copy_(res)
-
-    def all_gather(self, out, t):
-        self.sh.slots[self.rank] = t.clone()
-        self.sh.barrier.wait()
-        for r in range(self.sh.world):
-            out[r].copy_(self.sh.slots[r])
-        self.sh.barrier.wait()
-
-    def batch_isend_irecv(self, ops):
-        for op, t, peer in ops:
-            if op == "isend":
-                with self.sh.lock:
-                    self.sh.mail[(self.rank, peer)].append(t.clone())
-        self.sh.barrier.wait()
-        for op, t, peer in ops:
-            if op == "irecv":
-                with self.sh.lock:
-                    t.copy_(self.sh.mail[(peer, self.rank)].popleft())
-        self.sh.barrier.wait()
-        return [_Work() for _ in ops]
-
-
 def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, out, errors):  # noqa: PLR0913
     try:
         from spim_registration_b200 import bricks
@@ -84,7 +21,7 @@ def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, 
         c = bricks.rank_coords(rank, grid)
         sl = tuple(slice(c[d] * brick[d], (c[d] + 1) * brick[d]) for d in range(3))
         r = bricks.BrickRunner(brick, V, typ, generation=gen, lam=0.006, rank=rank, world=world, grid=grid,
-                               dist=ThreadDist(shared, rank), lib=lib, cpu=True)
+                               dist=shared.rank(rank), lib=lib, cpu=True)
         for v in range(V):
             r.session.set_view(v, np.ascontiguousarray(imgs[v][sl]), np.ascontiguousarray(ws[v][sl]), psfs[v])
         r.init()
@@ -97,7 +34,7 @@ def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, 
         r.close()
     except BaseException as e:         # noqa: BLE001
         errors.append((rank, repr(e)))
-        shared.barrier.abort()
+        shared.abort()
 
 
 @pytest.mark.parametrize("world,gen,typ,ks,brick", [(2, 2, 2, 5, (8, 9, 10)), (4, 2, 0, 5, (8, 9, 10)), (8, 1, 1, 5, (8, 9, 10)),
@@ -116,7 +53,8 @@ def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, t
     grid = bricks.grid_for(world)
     gshape = tuple(brick[d] * grid[d] for d in range(3))
     _, imgs, ws, psfs = synthetic.make_dataset(gshape, V, ks, kind="beads", seed=3)
-    shared = _Shared(world)
+    from spim_registration_b200.inprocess import ThreadGroup
+    shared = ThreadGroup(world)
     out, errors = {}, []
     threads = [threading.Thread(target=_rank_thread, args=(r, world, shared, brick, V, ks, typ, gen, iters, lib,
                                                            (imgs, ws, psfs), out, errors)) for r in range(world)]

@@ -37,3 +37,65 @@ def test_bricks_direct_push_over_peer_memory(gpu):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "BRICKS_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "EXCHANGE_PATH p2p" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.xfail(reason="written after the round's GPU budget was spent: verified under the emulator "
+                          "(tests/test_bricks_p2p_threads.py), not yet run on hardware", strict=False)
+def test_bricks_in_one_process_one_thread_per_device(gpu, monkeypatch):
+    """The reference's multi-device mode (one host thread per device, MVDeconFFT.java:447-469) with persistent bricks: the
+    ranks are threads of THIS process (spim_registration_b200/inprocess.py), peers are reached through raw device pointers
+    with peer access enabled, the halo exchange is the fused push + wait kernels alone."""
+    import threading
+    import numpy as np
+    import torch
+    from oracle import mvdecon_oracle as O
+    from spim_registration_b200 import bricks, synthetic
+    from spim_registration_b200.inprocess import ThreadGroup
+    n = gpu.getNumDevicesCUDA()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    monkeypatch.setenv("SPIM_BRICK_P2P", "1")
+    monkeypatch.setenv("SPIM_BRICK_GRAPH", "0")
+    brick, V, ks, iters = (24, 28, 32), 3, 7, 2
+    typ, gen = O.EFFICIENT_BAYESIAN, 2
+    grid = bricks.grid_for(world)
+    gshape = tuple(brick[d] * grid[d] for d in range(3))
+    _, imgs, ws, psfs = synthetic.make_dataset(gshape, V, ks, kind="beads", seed=3)
+    group = ThreadGroup(world)
+    out, errors = {}, []
+
+    def rank_main(r):
+        try:
+            torch.cuda.set_device(r)
+            c = bricks.rank_coords(r, grid)
+            sl = tuple(slice(c[d] * brick[d], (c[d] + 1) * brick[d]) for d in range(3))
+            run = bricks.BrickRunner(brick, V, typ, generation=gen, lam=0.006, device=r, rank=r, world=world, grid=grid,
+                                     dist=group.rank(r))
+            for v in range(V):
+                run.session.set_view(v, np.ascontiguousarray(imgs[v][sl]), np.ascontiguousarray(ws[v][sl]), psfs[v])
+            run.init()
+            used = run.use_p2p
+            run.run(iters, stats=True)
+            run.finish()
+            out[r] = (sl, run.get_psi(), used)
+            run.close()
+        except BaseException as e:      # noqa: BLE001
+            errors.append((r, repr(e)))
+            group.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=500)
+    assert not errors, errors
+    assert len(out) == world and all(u for _, _, u in out.values())
+    psi = np.zeros(gshape, np.float32)
+    for sl, p, _ in out.values():
+        psi[sl] = p
+    ref = O.deconvolve(imgs, ws, psfs, O.DeconParams(iteration_type=typ, num_iterations=iters, lam=0.006, gen=gen))
+    per, l2 = O.parity_errors(psi, ref.psi)
+    assert per <= 1e-3 and l2 <= 1e-4, (per, l2)
