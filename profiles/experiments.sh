@@ -9,7 +9,7 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=d["roofline_conv_pass
 print("  value %.4g  conv %.3f ms  frac %.3f " % (d["value"], c["ms_per_conv"], c["frac"]), {k: round(v["avg_ms"], 3) for k, v in c["per_kernel"].items()})'
 run() {   # run "<env assignments>"
     echo "== $1"
-    env $1 timeout 60 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "$summ" || echo "  FAILED"
+    env $1 timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-variants --no-cufft-leg --no-fusion-leg 2>/dev/null | python -c "$summ" || echo "  FAILED"
 }
 check() { # parity subset under a variant
     echo "== parity under: $1"
