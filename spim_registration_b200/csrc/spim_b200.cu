@@ -218,6 +218,16 @@ struct HaloPackK {
     }
 };
 
+// emulator only: memory orders of the epoch flags.  tests/cpp/p2p_tsan_driver.cpp builds a negative control with
+// -DSPIM_EMU_RELAXED_FLAGS, in which ThreadSanitizer must find the races the release / acquire pair prevents.
+#if defined(SPIM_EMU_RELAXED_FLAGS)
+#define SPIM_EMU_FLAG_STORE_ORDER __ATOMIC_RELAXED
+#define SPIM_EMU_FLAG_LOAD_ORDER __ATOMIC_RELAXED
+#else
+#define SPIM_EMU_FLAG_STORE_ORDER __ATOMIC_RELEASE
+#define SPIM_EMU_FLAG_LOAD_ORDER __ATOMIC_ACQUIRE
+#endif
+
 // brick mode, direct halo push (fused copy + signal over peer memory, no staging buffer and no NCCL on the data path):
 // up to 26 box-shaped pieces of MY buffer are stored straight into the neighbours' halos through their peer-mapped
 // (CUDA IPC / NVLink) buffers; the last block to finish raises this buffer's epoch flag at every neighbour with a
@@ -257,7 +267,7 @@ struct HaloPushK {
         if (bid == p.nblocks - 1) {        // blocks run in order: every piece has been written
             const unsigned int e = *p.epoch + 1u;
             *p.epoch = e;
-            for (int i = 0; i < p.npieces; ++i) __atomic_store_n(p.flag[i], e, __ATOMIC_RELEASE);
+            for (int i = 0; i < p.npieces; ++i) __atomic_store_n(p.flag[i], e, SPIM_EMU_FLAG_STORE_ORDER);
         }
 #else
         __threadfence_system();            // my stores are visible system-wide ...
@@ -291,7 +301,7 @@ struct HaloWaitK {
         for (int i = 0; i < p.nslots; ++i) {
             struct timespec t0, t1;
             clock_gettime(CLOCK_MONOTONIC, &t0);
-            while ((int)(__atomic_load_n(p.flags + p.slot[i], __ATOMIC_ACQUIRE) - want) < 0) {
+            while ((int)(__atomic_load_n(p.flags + p.slot[i], SPIM_EMU_FLAG_LOAD_ORDER) - want) < 0) {
                 clock_gettime(CLOCK_MONOTONIC, &t1);
                 const double ns = (double)(t1.tv_sec - t0.tv_sec) * 1e9 + (double)(t1.tv_nsec - t0.tv_nsec);
                 if (ns > (double)p.timeout_ns) { __atomic_fetch_or(p.err, 1u, __ATOMIC_RELAXED); break; }
