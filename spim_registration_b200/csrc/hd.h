@@ -10,6 +10,9 @@
 
 #if defined(SPIM_HOST_EMU)
 
+#include <condition_variable>
+#include <mutex>
+
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 struct alignas(16) float4 { float x, y, z, w; };
@@ -17,18 +20,38 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 #define SPIM_DEV inline
 #define SPIM_NOINLINE_DEV static __attribute__((noinline))
 #define SPIM_HD inline
-#define SPIM_FOR_ITEMS(i, n) for (int i = 0; i < (int)(n); ++i)
-#define SPIM_BARRIER() ((void)0)
+// Work items and barriers.  Normally the emulator runs a block as ONE thread (tid 0 of 1): the loop below visits every item
+// and a barrier is nothing.  With SPIM_EMU_THREADS=T the kernels that opt in (kEmuThreads: x-forward, column pass,
+// x-inverse) run each block as T real threads that split the items like the threads of a CUDA block and meet at real
+// barriers -- the mode tests/test_tsan_kernels.py runs under ThreadSanitizer to check barrier placement without a GPU.
+struct SpimEmuBlock {
+    int nthr, count = 0, gen = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    explicit SpimEmuBlock(int n) : nthr(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> l(m);
+        const int g = gen;
+        if (++count == nthr) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(l, [&] { return gen != g; });
+    }
+};
+inline thread_local int spim_emu_tid = 0;
+inline thread_local int spim_emu_nthr = 1;
+inline thread_local SpimEmuBlock* spim_emu_blk = nullptr;
+static inline void spim_emu_barrier() { if (spim_emu_blk) spim_emu_blk->wait(); }
+#define SPIM_FOR_ITEMS(i, n) for (int i = spim_emu_tid; i < (int)(n); i += spim_emu_nthr)
+#define SPIM_BARRIER() spim_emu_barrier()
 // a thread group = the threads that cooperate on one tile (the whole CTA, or one consumer group of a
 // warp-specialised kernel); the emulator runs every group as a single serial thread
 struct alignas(64) SpimTensorMap { unsigned long long opaque[16]; };   // CUtensorMap stand-in (unused by the emulator)
 struct TG { int tid, n, bar; };
-static inline TG tg_cta() { TG t; t.tid = 0; t.n = 1; t.bar = 0; return t; }
-static inline void tg_barrier(const TG&) {}
+static inline TG tg_cta() { TG t; t.tid = spim_emu_tid; t.n = spim_emu_nthr; t.bar = 0; return t; }
+static inline void tg_barrier(const TG&) { spim_emu_barrier(); }
 #define SPIM_FOR_ITEMS_TG(tg, i, cnt) for (int i = (tg).tid; i < (int)(cnt); i += (tg).n)
 static inline void spim_syncwarp() {}
-#define SPIM_NTHREADS 1
-#define SPIM_TID 0
+#define SPIM_NTHREADS spim_emu_nthr
+#define SPIM_TID spim_emu_tid
 template <class T> static inline T spim_ldg(const T* p) { return *p; }
 static inline float4 ldg_stream(const float4* p) { return *p; }
 static inline float2 ldg_stream(const float2* p) { return *p; }

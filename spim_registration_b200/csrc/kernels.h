@@ -218,7 +218,9 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
             }
         }
     }
+#if !defined(SPIM_EMU_NO_STAGE_BARRIER)      // negative control of tests/test_tsan_kernels.py: without it stages race
     tg_barrier(tg);
+#endif
 }
 
 // last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
@@ -344,7 +346,7 @@ struct ColPassParams {
 template <int W>
 SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_lo, int row_hi) {
 #if defined(SPIM_HOST_EMU)
-    for (int row = row_lo; row < row_hi; ++row)
+    for (int row = row_lo + spim_emu_tid; row < row_hi; row += spim_emu_nthr)
         for (int c2 = 0; c2 < W; ++c2) cp_async16(buf + row * W + c2, gp + (long long)row * gs4 + c2);
 #else
     constexpr int LW = (W == 8) ? 3 : 2;
@@ -372,6 +374,7 @@ SPIM_DEV void async_rows(float4* buf, const float4* gp, long long gs4, int row_l
 template <int W, int RMAX = 16>
 struct ColPassN {
     typedef ColPassParams Params;
+    static constexpr bool kEmuThreads = true;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
@@ -872,6 +875,7 @@ SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long lon
 
 struct XFwd {
     typedef XFwdParams Params;
+    static constexpr bool kEmuThreads = true;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
@@ -1117,6 +1121,8 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
     if (p.stat_sum == nullptr) return;
 #if defined(SPIM_HOST_EMU)
     (void)tile;
+    static std::mutex stat_mutex;          // the emulator's stand-in for the two atomics (blocks may run as several threads)
+    std::lock_guard<std::mutex> lock(stat_mutex);
     *p.stat_sum += acc.sum;
     unsigned int bits; memcpy(&bits, &acc.mx, 4);
     if (bits > *p.stat_max) *p.stat_max = bits;
@@ -1191,6 +1197,7 @@ SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* 
 template <int EPI, int MATH, int R0MAX = 16>
 struct XInvT {
     typedef XInvParams Params;
+    static constexpr bool kEmuThreads = true;
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);

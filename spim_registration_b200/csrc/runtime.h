@@ -7,6 +7,10 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <type_traits>
+#if defined(SPIM_HOST_EMU)
+#include <thread>
+#endif
 
 namespace spim { namespace rt {
 
@@ -38,10 +42,31 @@ inline void stream_sync(Stream) {}
 inline size_t max_smem() { return 227 * 1024; }
 inline int sm_count() { return 148; }
 
+// kernels that can run a block as several real threads (hd.h) declare `static constexpr bool kEmuThreads = true`
+template <class B, class = void> struct emu_threaded { static constexpr bool value = false; };
+template <class B> struct emu_threaded<B, std::void_t<decltype(B::kEmuThreads)>> { static constexpr bool value = B::kEmuThreads; };
+inline int emu_threads() { const char* e = getenv("SPIM_EMU_THREADS"); const int t = e ? atoi(e) : 1; return (t >= 1 && t <= 64) ? t : 1; }
+
 template <class Body, int MAXT = 256, int MINB = 1>
 inline void launch(const typename Body::Params& p, long long grid, int /*block*/, size_t smem, Stream) {
     std::vector<double> buf((smem + 7) / 8 + 1);
-    for (long long b = 0; b < grid; ++b) Body::run(p, (int)b, reinterpret_cast<float2*>(buf.data()));
+    float2* sm = reinterpret_cast<float2*>(buf.data());
+    const int T = emu_threaded<Body>::value ? emu_threads() : 1;
+    if (T <= 1) {
+        for (long long b = 0; b < grid; ++b) Body::run(p, (int)b, sm);
+        return;
+    }
+    for (long long b = 0; b < grid; ++b) {      // one block at a time, T threads sharing its "shared memory"
+        SpimEmuBlock blk(T);
+        std::vector<std::thread> ts;
+        for (int t = 0; t < T; ++t)
+            ts.emplace_back([&, t]() {
+                spim_emu_tid = t; spim_emu_nthr = T; spim_emu_blk = &blk;
+                Body::run(p, (int)b, sm);
+                spim_emu_tid = 0; spim_emu_nthr = 1; spim_emu_blk = nullptr;
+            });
+        for (auto& th : ts) th.join();
+    }
 }
 
 inline bool encode_tensor_map(SpimTensorMap*, void*, int, const unsigned long long*, const unsigned long long*, const unsigned int*) { return false; }
