@@ -142,7 +142,7 @@ struct VoxelWalker {
     }
 };
 #if defined(SPIM_HOST_EMU)
-#define SPIM_ITEM_STEP 1
+#define SPIM_ITEM_STEP spim_emu_nthr
 #else
 #define SPIM_ITEM_STEP ((int)blockDim.x)
 #endif
@@ -273,6 +273,7 @@ struct WeightNormK {
     SPIM_DEV static void flush(unsigned long long* scnt, unsigned int* smin, int portion, unsigned long long c, unsigned int mn) {
         if (portion < 0) return;
 #if defined(SPIM_HOST_EMU)
+        std::lock_guard<std::mutex> l(g_emu_atomic_mutex);
         scnt[portion] += c;
         if (mn < smin[portion]) smin[portion] = mn;
 #else
@@ -363,6 +364,7 @@ struct MinMaxK {
             }
         }
 #if defined(SPIM_HOST_EMU)
+        std::lock_guard<std::mutex> l(g_emu_atomic_mutex);
         if (lo < p.mm[0]) p.mm[0] = lo;
         if (hi > p.mm[1]) p.mm[1] = hi;
 #else

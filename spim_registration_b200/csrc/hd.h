@@ -21,8 +21,8 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 #define SPIM_NOINLINE_DEV static __attribute__((noinline))
 #define SPIM_HD inline
 // Work items and barriers.  Normally the emulator runs a block as ONE thread (tid 0 of 1): the loop below visits every item
-// and a barrier is nothing.  With SPIM_EMU_THREADS=T the kernels that opt in (kEmuThreads: x-forward, column pass,
-// x-inverse) run each block as T real threads that split the items like the threads of a CUDA block and meet at real
+// and a barrier is nothing.  With SPIM_EMU_THREADS=T every kernel that does not opt out (kEmuThreads = false) runs each
+// block as T real threads that split the items like the threads of a CUDA block and meet at real
 // barriers -- the mode tests/test_tsan_kernels.py runs under ThreadSanitizer to check barrier placement without a GPU.
 struct SpimEmuBlock {
     int nthr, count = 0, gen = 0;

@@ -446,6 +446,7 @@ SPIM_DEV void col_tile_base(const ColPassParams& p, int t, long long& base) {
 // filled by the other; results leave straight from the registers of the last stage.
 struct ColPassT {
     typedef ColPassParams Params;
+    static constexpr bool kEmuThreads = false;
     static constexpr int NSLOT = 3;
     SPIM_DEV static void consume(const TG& tg, const Params& p, int t, float4* tile) {
         const FftPlanDev& pl = p.plan;
@@ -679,6 +680,7 @@ SPIM_DEV void async_rows_w(float4* buf, const float4* gp, long long gs4, int row
 
 struct ColPassW {
     typedef ColPassParams Params;
+    static constexpr bool kEmuThreads = false;
     SPIM_DEV static void warp_work(const Params& p, int lane, int nlanes, int c0, float4* tile, const GRows& g, long long base) {
         const FftPlanDev& pl = p.plan;
         const int S = pl.nstages;

@@ -42,8 +42,9 @@ inline void stream_sync(Stream) {}
 inline size_t max_smem() { return 227 * 1024; }
 inline int sm_count() { return 148; }
 
-// kernels that can run a block as several real threads (hd.h) declare `static constexpr bool kEmuThreads = true`
-template <class B, class = void> struct emu_threaded { static constexpr bool value = false; };
+// every kernel can run a block as several real threads (hd.h) unless it declares `static constexpr bool kEmuThreads = false`
+// (bodies whose emulator branch is written for one thread per block: the TMA pipeline, warp-private columns, push / wait)
+template <class B, class = void> struct emu_threaded { static constexpr bool value = true; };
 template <class B> struct emu_threaded<B, std::void_t<decltype(B::kEmuThreads)>> { static constexpr bool value = B::kEmuThreads; };
 inline int emu_threads() { const char* e = getenv("SPIM_EMU_THREADS"); const int t = e ? atoi(e) : 1; return (t >= 1 && t <= 64) ? t : 1; }
 

@@ -51,9 +51,11 @@ struct ScaleClampK {   // adjustOSEMspeedup: w <- min(1, w * (float)osem)
 };
 
 #if defined(SPIM_HOST_EMU)
-SPIM_DEV void atomic_add_d(double* p, double v) { *p += v; }
-SPIM_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
-SPIM_DEV void atomic_min_u32(unsigned int* p, unsigned int v) { if (v < *p) *p = v; }
+// the emulator's stand-ins for the device atomics: one lock (a block may run as several real threads, hd.h)
+static std::mutex g_emu_atomic_mutex;
+SPIM_DEV void atomic_add_d(double* p, double v) { std::lock_guard<std::mutex> l(g_emu_atomic_mutex); *p += v; }
+SPIM_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { std::lock_guard<std::mutex> l(g_emu_atomic_mutex); *p += v; }
+SPIM_DEV void atomic_min_u32(unsigned int* p, unsigned int v) { std::lock_guard<std::mutex> l(g_emu_atomic_mutex); if (v < *p) *p = v; }
 SPIM_DEV double warp_sum_d(double v) { return v; }
 SPIM_DEV unsigned long long warp_sum_u64(unsigned long long v) { return v; }
 SPIM_DEV unsigned int warp_min_u32(unsigned int v) { return v; }
@@ -233,6 +235,7 @@ struct HaloPackK {
 // (CUDA IPC / NVLink) buffers; the last block to finish raises this buffer's epoch flag at every neighbour with a
 // system-scope release store.  All bricks share one geometry, so a destination is (peer base pointer, box origin).
 struct HaloPushK {
+    static constexpr bool kEmuThreads = false;     // the emulated signal step assumes one thread per block
     struct Params {
         const float* buf; int dims[3]; int npieces; int nblocks;
         float* dst[MAX_PIECES];            // base of the neighbour's buffer
@@ -291,6 +294,7 @@ struct HaloPushK {
 // my own epoch for this buffer -- every rank pushes the same sequence, so equal epochs pair up.  A timeout raises an
 // error word instead of hanging the GPU.
 struct HaloWaitK {
+    static constexpr bool kEmuThreads = false;
     struct Params {
         unsigned int* flags; int nslots; int slot[MAX_PIECES]; const unsigned int* epoch; unsigned int* err;
         unsigned long long timeout_ns;

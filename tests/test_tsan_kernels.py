@@ -1,5 +1,5 @@
 """Barrier placement of the FFT-convolution kernels under ThreadSanitizer, without a GPU.  With SPIM_EMU_THREADS=T the kernel
-emulator runs every block of the x-forward, column and x-inverse kernels as T real threads that split the work items like the
+emulator runs every block of every kernel as T real threads that split the work items like the
 threads of a CUDA block and meet at real barriers (csrc/hd.h, csrc/runtime.h); tests/cpp/kernel_tsan_driver.cpp drives all
 extension rules, narrow tiles, the register-lean instantiations, the serpentine order and a deconvolution with the fused
 update epilogue through the C ABI.  No data race may be reported and the threaded results must equal the single-thread ones
