@@ -337,6 +337,12 @@ def variants_leg(budget_s=120.0, per_child_s=30.0):
     return out
 
 
+def p2p_flag_path():
+    """host-side signal "the direct-push child job is over" from rank 0 to the other ranks of this job"""
+    return os.path.join("/tmp", "spim_bench_p2p_%s_%s" % (os.environ.get("MASTER_PORT", "0"),
+                                                          os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))))
+
+
 def p2p_variant_leg(n, steps, limit_s=240.0):
     """Rank 0, N > 1: run this very benchmark once more as a child torchrun job with SPIM_BRICK_P2P=1 (noise inputs, no
     extras) and return its throughput.  The child is its own process group and is killed as a group at the time limit."""
@@ -440,6 +446,11 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if rank == 0:       # a flag file left behind by an aborted earlier run must not release the other ranks early (see below)
+            try:
+                os.remove(p2p_flag_path())
+            except OSError:
+                pass
         dist.barrier()
         tlog("process group up")
     if world != args.gpus:
@@ -586,8 +597,7 @@ def main():
     # The other ranks wait on the host (a flag file), not in a collective, so no NCCL kernel spins on their GPUs meanwhile.
     p2p_variant = None
     if N > 1 and not args.no_p2p_variant and os.environ.get("SPIM_BRICK_P2P", "0") != "1":
-        flag = os.path.join("/tmp", "spim_bench_p2p_%s_%s" % (os.environ.get("MASTER_PORT", "0"),
-                                                              os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))))
+        flag = p2p_flag_path()
         if rank == 0:
             try:
                 p2p_variant = p2p_variant_leg(N, args.steps)
