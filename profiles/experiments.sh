@@ -1,6 +1,8 @@
 #!/bin/bash
 # A/B matrix of the kernel variants that are in tree behind environment switches (run on the GPU box):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/experiments.sh > gpurun_out/experiments.txt 2>&1'
+# Quickest A/B of a single switch (6 s, no torch):  env SPIM_PDL=1 python bench.py --variant-child   -> one JSON line with the
+# throughput, the per-kernel CUDA-event times and a result checksum; bench.py's own `variants` extra runs the whole matrix this way.
 # Every line: the switch setting, whole-iteration throughput and the per-kernel CUDA-event averages of bench.py.
 # A variant is only worth adopting if the parity subset below passes with it.
 set -u
