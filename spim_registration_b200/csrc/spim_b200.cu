@@ -531,7 +531,10 @@ struct mvd_session {
     int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
     int conv2_ext() const { return prm.conv2_ext >= 0 ? prm.conv2_ext : (prm.generation == 2 ? EXT_CONSTANT : EXT_MIRROR_SINGLE); }
 
+    size_t psi_bytes = 0, kh_bytes = 0;       // sizes the psi / ratio buffers and the kernel spectra were allocated with
+
     void* dalloc(size_t bytes) { dev_bytes += (long long)bytes; return rt::dmalloc(bytes); }
+    void dfree_counted(void* p, size_t bytes) { if (p) { rt::dfree(p); dev_bytes -= (long long)bytes; } }
 
     HostVol small_conv(const HostVol& a, const HostVol& b) {   // zero-extended PSF-sized convolution
         ConvWorkspace* ws = nullptr;
@@ -826,7 +829,7 @@ static int session_prepare(mvd_session* s) {
         s->kmax[d] = 0;
         for (int v = 0; v < V; ++v) s->kmax[d] = std::max(s->kmax[d], s->psf[v].d[d]);
     }
-    if (s->plan_ok) { s->plan.destroy(); s->plan_ok = false; }
+    if (s->plan_ok) { s->dev_bytes -= (long long)s->plan.spec_bytes(); s->plan.destroy(); s->plan_ok = false; }
     s->plan.create(s->n, s->kmax, false, true);
     s->plan.timer = &s->timer;
     s->plan_ok = true;
@@ -845,12 +848,29 @@ static int session_prepare(mvd_session* s) {
         } else { s->pdims[d] = s->n[d]; s->porigin[d] = 0; }
     }
     s->pelems = (long long)s->pdims[0] * s->pdims[1] * s->pdims[2];
-    if (!s->d_psi) s->d_psi = (float*)s->dalloc((size_t)s->pelems * sizeof(float));
-    if (!s->d_tmp) s->d_tmp = (float*)s->dalloc((size_t)s->pelems * sizeof(float));
+    // a second mvd_init after mvd_set_view changed a PSF re-plans: the padded FFT size, and with it the size of every
+    // spectrum and (brick mode) of the haloed psi / ratio buffers, may have changed -- buffers are re-created whenever
+    // their size did (a larger PSF would otherwise write past the allocations of the first plan)
+    const size_t pbytes = (size_t)s->pelems * sizeof(float);
+    if (pbytes != s->psi_bytes) {
+        if (s->p2p.connected) return fail("mvd_init: the haloed buffers change size while peers are connected (mvd_p2p_disconnect first)");
+        s->dfree_counted(s->d_psi, s->psi_bytes); s->dfree_counted(s->d_tmp, s->psi_bytes);
+        s->d_psi = (float*)s->dalloc(pbytes);
+        s->d_tmp = (float*)s->dalloc(pbytes);
+        s->psi_bytes = pbytes;
+    }
     s->init_kernels();
+    const size_t sbytes = s->plan.spec_bytes();
+    if (sbytes != s->kh_bytes) {
+        for (int v = 0; v < V; ++v) {
+            s->dfree_counted(s->d_kh1[v], s->kh_bytes); s->d_kh1[v] = nullptr;
+            s->dfree_counted(s->d_kh2[v], s->kh_bytes); s->d_kh2[v] = nullptr;
+        }
+        s->kh_bytes = sbytes;
+    }
     for (int v = 0; v < V; ++v) {
-        if (!s->d_kh1[v]) s->d_kh1[v] = (float2*)s->dalloc(s->plan.spec_bytes());
-        if (!s->d_kh2[v]) s->d_kh2[v] = (float2*)s->dalloc(s->plan.spec_bytes());
+        if (!s->d_kh1[v]) s->d_kh1[v] = (float2*)s->dalloc(sbytes);
+        if (!s->d_kh2[v]) s->d_kh2[v] = (float2*)s->dalloc(sbytes);
         // kernels smaller than kmax are spectrum-transformed with their own dims
         ConvPlan& pl = s->plan;
         int save[3] = {pl.k[0], pl.k[1], pl.k[2]};

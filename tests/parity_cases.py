@@ -173,3 +173,40 @@ def fast_epilogue_case(lib, shape=(14, 16, 18), bit_identical=False):
         else:
             per, l2 = O.parity_errors(a, b)
             assert per <= 2e-5 and l2 <= 2e-6, (gen, typ, per, l2)
+
+
+def reinit_case(lib, shape=(16, 16, 16)):
+    """mvd_init a second time after mvd_set_view replaced the PSFs by larger ones (3^3 -> 15^3): the session re-plans
+    (larger padded FFT size) and must re-create every buffer whose size changed; the second run equals a fresh session."""
+    _, imgs, ws, small = synthetic.make_dataset(shape, 2, 3, kind="beads")
+    _, _, _, big = synthetic.make_dataset(shape, 2, 15, kind="beads")
+    fresh, *_ = run_session(lib, imgs, ws, big, O.EFFICIENT_BAYESIAN, 2, 2)
+    for haloed in (False, True):
+        with Session(shape, 2, O.EFFICIENT_BAYESIAN, generation=2, lib=lib, haloed=haloed) as s:
+            for v in range(2):
+                s.set_view(v, imgs[v], ws[v], small[v])
+            s.init()
+            b0 = s.info().device_bytes
+            if haloed:
+                s.set_avg(0.5, 1.0)
+                s.view_phase(0, 0); s.view_phase(0, 1)
+            else:
+                s.run(1)
+            for v in range(2):
+                s.set_view(v, imgs[v], ws[v], big[v])
+            s.init()
+            i = s.info()
+            assert tuple(i.fft_dims) == tuple(lib.mvd_fft_size(n + 14, 1 if d == 2 else 0) for d, n in enumerate(shape))
+            assert i.device_bytes > b0
+            if haloed:
+                _, dims, origin = s.device_buffer(0)
+                assert tuple(dims)[:2] == tuple(n + 14 for n in shape[:2]) and tuple(origin)[:2] == (7, 7)
+                continue
+            s.run(2)
+            s.finish()
+            assert np.array_equal(s.get_psi(), fresh)
+            # and back to the small PSFs: the accounting shrinks again
+            for v in range(2):
+                s.set_view(v, imgs[v], ws[v], small[v])
+            s.init()
+            assert s.info().device_bytes == b0

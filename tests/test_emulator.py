@@ -70,6 +70,10 @@ def test_views_uploaded_in_cells(emu_lib):
     P.cells_case(emu_lib)
 
 
+def test_second_init_with_larger_psf_recreates_buffers(emu_lib):
+    P.reinit_case(emu_lib)
+
+
 def test_fast_epilogue_switch(emu_lib):
     P.fast_epilogue_case(emu_lib, bit_identical=True)
 

@@ -117,6 +117,10 @@ def test_gen1_osem_variants(gpu):
     P.decon_case(gpu, (24, 28, 32), 3, 5, O.EFFICIENT_BAYESIAN, 1, 2, osem=2.0, osem_index=0)
 
 
+def test_second_init_with_larger_psf_recreates_buffers(gpu):
+    P.reinit_case(gpu, (24, 28, 32))
+
+
 def test_exact_tikhonov_switch(gpu):
     P.exact_tikhonov_case(gpu, (30, 34, 38))
 
