@@ -77,7 +77,8 @@ int mvd_session_create(const mvd_params* p, mvd_session** out);
 void mvd_session_destroy(mvd_session* s);
 
 /* LRInput.add(new LRFFT(image, weight, kernel, ...)) / MVDeconInput.add(new MVDeconFFT(...)):
- * host pointers, copied to the device.  weight == NULL means constant 1 (LRFFT.java:201-204). */
+ * host pointers (pageable or pinned), copied to the device; pointers into device memory are accepted as well (unified
+ * addressing), for views that were produced on a GPU.  weight == NULL means constant 1 (LRFFT.java:201-204). */
 int mvd_set_view(mvd_session* s, int view, const float* img, const float* weight,
                  const float* psf, const int psf_dims[3]);
 

@@ -61,7 +61,7 @@ class BrickRunner:
 
     def __init__(self, brick: Sequence[int], num_views: int, iteration_type: int, generation: int = 2,
                  lam: float = 0.006, osem_speedup: float = 1.0, device: int = 0, rank: int = 0, world: int = 1,
-                 grid: Optional[Sequence[int]] = None, dist=None, lib=None, cpu: bool = False):
+                 grid: Optional[Sequence[int]] = None, dist=None, lib=None, cpu: bool = False, osem_index: int = 0):
         self.world = world
         self.rank = rank
         self.grid = tuple(grid) if grid else grid_for(world)
@@ -72,6 +72,7 @@ class BrickRunner:
         self.num_views = num_views
         self.generation = generation
         self.osem_speedup = osem_speedup
+        self.osem_index = osem_index
         self.haloed = world > 1
         self.session = Session(brick, num_views, iteration_type, generation=generation, lam=lam,
                                osem_speedup=osem_speedup, device=device, haloed=self.haloed, lib=lib)
@@ -124,6 +125,13 @@ class BrickRunner:
         else:
             avg = float(np.float32(part[0] / part[1])) if part[1] > 0 else 1.0
             osem = self.osem_speedup
+            # BayesMVDeconvolution.java:94-97: osemspeedupindex 1 = min #overlapping views, 2 = avg #overlapping views
+            # (both >= 1), from the all-reduced counts exactly like mvd_init does for a whole volume
+            if self.osem_index == 1:
+                osem = max(1.0, float(int(part[4])))
+            elif self.osem_index == 2:
+                osem = max(1.0, part[2] / part[3]) if part[3] > 0 else 1.0
+        self.avg, self.osem = avg, osem
         s.set_avg(avg, osem)
         bufs = []
         for which in (0, 1):
@@ -133,6 +141,15 @@ class BrickRunner:
         i = s.info()
         self.halo_lo = tuple(i.halo_lo)
         self.halo_hi = tuple(i.halo_hi)
+        for d in range(3):
+            if self.grid[d] > 1:
+                # a neighbour's halo is filled from MY interior cells only, and both directions are exchanged as a pair
+                if max(self.halo_lo[d], self.halo_hi[d]) > s.dims[d]:
+                    raise ValueError(f"brick extent {s.dims[d]} along axis {d} is smaller than the halo "
+                                     f"({self.halo_lo[d]}, {self.halo_hi[d]}): use fewer bricks along this axis")
+                if (self.halo_lo[d] == 0) != (self.halo_hi[d] == 0):
+                    raise NotImplementedError(f"PSF extent 2 along a split axis (halo {self.halo_lo[d]} / {self.halo_hi[d]}): "
+                                              "one-sided halos are not exchanged; use an odd PSF size or do not split this axis")
         self._plan_exchange()
 
     # ------------------------------------------------------------------------------------------
@@ -235,10 +252,11 @@ class BrickRunner:
             self.use_pack = self._verify_mode("pack")
             if not self.use_pack and self.rank == 0:
                 print("[bricks] halo exchange: using slab copies (pack-path self-check failed)", flush=True)
-        # direct halo push over NVLink peer memory (mvd_p2p_*): opt-in until it has been timed on hardware
+        # direct halo push over NVLink peer memory (mvd_p2p_*): the default; the NCCL batch is the fallback when a peer cannot be
+        # mapped or the one-time self-check fails (SPIM_BRICK_P2P=0 forces the NCCL path)
         self.use_p2p = False
         self._p2p_last = None
-        if os.environ.get("SPIM_BRICK_P2P", "0") == "1" and plan and self.dist is not None:
+        if os.environ.get("SPIM_BRICK_P2P", "1") == "1" and plan and self.dist is not None:
             self._setup_p2p()
 
     def _setup_p2p(self):

@@ -933,7 +933,23 @@ struct XFwd {
 // ---------------------------------------------------------------------------------------------
 // XInv: half spectrum -> real lines + fused epilogue (specialised at compile time per epilogue mode)
 // ---------------------------------------------------------------------------------------------
+// Brick mode: the halo push fused into the x-inverse epilogue.  Every voxel a neighbour needs for its halo is stored
+// straight into that neighbour's (peer-mapped, NVLink) buffer by the thread that has just computed it, next to the local
+// store -- the transfer overlaps the sweep tile by tile and no separate copy pass ever re-reads the faces.  All bricks share
+// one geometry, so the copy of local element i at the neighbour in direction (dz, dy, dx) is element i - shift[dir] of its
+// buffer, dir = (dz+1)*9 + (dy+1)*3 + (dx+1).  A neighbour below needs my first `whi` cells along that axis (its upper
+// halo), a neighbour above my last `wlo` cells.  Flags are raised afterwards by HaloSignalWaitK (spim_b200.cu).
+struct HaloFuse {
+    float* peer[27];           // base of the neighbour's buffer per direction, nullptr = no neighbour there
+    long long shift[27];
+    int n[3], wlo[3], whi[3];  // (z, y, x): brick size, halo before / after the brick
+    int has_lo, has_hi;        // bit d (0 = z, 1 = y, 2 = x): a neighbour exists below / above along axis d
+};
+constexpr int kFuseCombos = 4;         // (dz, dy) in {0, dzs} x {0, dys} per line
+constexpr int kFuseSlots = 3;          // per combo: whole line, x-low part, x-high part
+
 struct XInvParams {
+    const HaloFuse* fuse;      // device pointer, FUSE instantiations only
     const float2* spec;
     int pitch, Px, Py;
     int nx, ny, nz;            // output region (logical image size)
@@ -1053,8 +1069,9 @@ SPIM_DEV void epi_store_scalar(const XInvParams& p, const EpiFlags& f, long long
     if (u0 + 1 < p.nx) p.dst[di + 1] = epi_one<EPI, MATH>(p, f, v.y, x1.y, x2.y, csum, cmax);
 }
 
-template <int R, int EPI, int MATH, bool VEC>
-SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* auxoff, const long long* dstoff, EpiAcc& acc) {
+template <int R, int EPI, int MATH, bool VEC, bool FUSE = false>
+SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* auxoff, const long long* dstoff, EpiAcc& acc,
+                          float2* const* fptr = nullptr, const int* fnc = nullptr, int nlo2 = 0, int nhi2 = 0) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
     const float2* twp = pl.tws + pl.tw_off[0];
@@ -1106,9 +1123,21 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
                 const float r0 = epi_one<EPI, MATH>(p, f, a[q].x, x1[q].x, x2[q].x, s0, mx);
                 const float r1 = epi_one<EPI, MATH>(p, f, a[q].y, x1[q].y, x2[q].y, s1, mx);
                 if (n < nh) {
-                    out[n] = make_float2(r0, r1);
+                    const float2 v2 = make_float2(r0, r1);
+                    out[n] = v2;
                     csum += s0; csum += s1;
                     cmax = fmaxf(cmax, mx);
+                    if (FUSE) {
+                        // combo 0 = this line at the x neighbours only; further combos (lines inside a y / z face region) also
+                        // send the whole line.  Pointers are pre-offset per line, so the pair index n applies unchanged.
+                        float2* const* fp = fptr + b * (kFuseCombos * kFuseSlots);
+                        const int nc = fnc[b];
+                        for (int c = 0; c < nc; ++c, fp += kFuseSlots) {
+                            if (fp[0]) fp[0][n] = v2;
+                            if (n < nlo2 && fp[1]) fp[1][n] = v2;
+                            if (n >= nhi2 && fp[2]) fp[2][n] = v2;
+                        }
+                    }
                 }
             }
         } else {
@@ -1196,7 +1225,10 @@ SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* 
 // R0MAX: largest radix the register-resident last stage (plan.radix[0]) is compiled for.  The epilogue keeps 8 R floats per
 // item in registers (spectrum row, two prefetched inputs, twiddles), so an instantiation for R0MAX = 5 is much leaner than
 // the general one; the host only selects it when the x plan starts with a radix <= R0MAX (SPIM_XPLAN_ASC orders it so).
-template <int EPI, int MATH, int R0MAX = 16>
+// bytes of shared memory a FUSE instantiation needs behind the tile and the three line-offset arrays
+constexpr size_t kFuseSmemBytes = TC * kFuseCombos * kFuseSlots * sizeof(float2*) + TC * sizeof(int);
+
+template <int EPI, int MATH, int R0MAX = 16, bool FUSE = false>
 struct XInvT {
     typedef XInvParams Params;
     static constexpr bool kEmuThreads = true;
@@ -1208,18 +1240,37 @@ struct XInvT {
         long long* srcoff = reinterpret_cast<long long*>(tile2 + (size_t)N2 * TC);
         long long* dstoff = srcoff + TC;
         long long* auxoff = dstoff + TC;
+        float2** fptr = reinterpret_cast<float2**>(auxoff + TC);                   // FUSE: [TC][kFuseCombos][kFuseSlots]
+        int* fnc = reinterpret_cast<int*>(fptr + TC * kFuseCombos * kFuseSlots);   // FUSE: combos in use per line
         if (p.reverse) bid = p.nblocks - 1 - bid;
         SPIM_FOR_ITEMS(b, TC) {
             const long long l = (long long)bid * TC + b;
             long long so = -1, d_o = -1, a_o = -1;
+            int nc = 0;
             if (l < p.nlines) {
                 const int z = (int)(l / p.ny);
                 const int y = (int)(l - (long long)z * p.ny);
                 so = ((long long)z * p.Py + y) * (long long)p.pitch;
                 d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
                 a_o = ((long long)z * p.ny + y) * (long long)p.nx;
+                if (FUSE) {
+                    const HaloFuse& h = *p.fuse;
+                    const int dzs = (z < h.whi[0] && (h.has_lo & 1)) ? -1 : ((z >= h.n[0] - h.wlo[0] && (h.has_hi & 1)) ? 1 : 0);
+                    const int dys = (y < h.whi[1] && (h.has_lo & 2)) ? -1 : ((y >= h.n[1] - h.wlo[1] && (h.has_hi & 2)) ? 1 : 0);
+                    for (int iz = 0; iz < (dzs ? 2 : 1); ++iz)
+                        for (int iy = 0; iy < (dys ? 2 : 1); ++iy) {
+                            const int cz = iz ? dzs : 0, cy = iy ? dys : 0;
+                            const int dir = (cz + 1) * 9 + (cy + 1) * 3 + 1;
+                            float2** f = fptr + (b * kFuseCombos + nc) * kFuseSlots;
+                            f[0] = (cz || cy) ? reinterpret_cast<float2*>(h.peer[dir] + (d_o - h.shift[dir])) : nullptr;
+                            f[1] = ((h.has_lo & 4) && h.peer[dir - 1]) ? reinterpret_cast<float2*>(h.peer[dir - 1] + (d_o - h.shift[dir - 1])) : nullptr;
+                            f[2] = ((h.has_hi & 4) && h.peer[dir + 1]) ? reinterpret_cast<float2*>(h.peer[dir + 1] + (d_o - h.shift[dir + 1])) : nullptr;
+                            ++nc;
+                        }
+                }
             }
             srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
+            if (FUSE) fnc[b] = nc;
         }
         SPIM_BARRIER();
         xinv_presplit(p, tile, srcoff, N2);
@@ -1229,7 +1280,12 @@ struct XInvT {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        if (FUSE) {        // the host only selects a FUSE instantiation when the vectorised path applies
+            const int nlo2 = (p.fuse->whi[2] + 1) >> 1;              // pairs (2n, 2n+1) that reach into x < whi
+            const int nhi2 = (p.nx - p.fuse->wlo[2]) >> 1;           // ... into x >= nx - wlo
+            SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
+        }
+        else if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
         else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }

@@ -100,7 +100,9 @@ inline int device_count() {
 inline void set_device(int d) { SPIM_CUDA_CHECK(cudaSetDevice(d)); }
 inline void* dmalloc(size_t n) { void* p = nullptr; SPIM_CUDA_CHECK(cudaMalloc(&p, n ? n : 1)); return p; }
 inline void dfree(void* p) { if (p) cudaFree(p); }
-inline void h2d(void* d, const void* h, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+// the source may be pageable / pinned host memory or (unified addressing) memory of any device: views that already live on
+// a GPU -- generated there, or produced by the fusion pre-step of another session -- are handed over through the same entry points
+inline void h2d(void* d, const void* h, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyDefault, s)); }
 inline void d2h(void* h, const void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 inline void d2d(void* d, const void* s_, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
 inline void dzero(void* d, size_t n, Stream s) { SPIM_CUDA_CHECK(cudaMemsetAsync(d, 0, n, s)); }
@@ -112,7 +114,7 @@ inline void h2d_box(float* d, const int ddims[3], const int lo[3], const float* 
     q.dstPtr = make_cudaPitchedPtr(d, (size_t)ddims[2] * sizeof(float), (size_t)ddims[2], (size_t)ddims[1]);
     q.dstPos = make_cudaPos((size_t)lo[2] * sizeof(float), (size_t)lo[1], (size_t)lo[0]);
     q.extent = make_cudaExtent((size_t)ext[2] * sizeof(float), (size_t)ext[1], (size_t)ext[0]);
-    q.kind = cudaMemcpyHostToDevice;
+    q.kind = cudaMemcpyDefault;
     SPIM_CUDA_CHECK(cudaMemcpy3DAsync(&q, s));
 }
 inline Stream stream_create() { Stream s; SPIM_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }

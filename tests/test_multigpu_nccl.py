@@ -17,16 +17,17 @@ def test_bricks_over_nccl(gpu):
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "run_bricks_nccl.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    # the NCCL fallback path (pack / unpack kernels around one batch of send / recv): the direct push is switched off
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SPIM_BRICK_P2P="0", SPIM_TEST_EXTRA_ITERS="2"))
+    print(r.stdout[-600:])
     assert "BRICKS_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "EXCHANGE_PATH pack" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="opt-in path written after the round's GPU budget was spent: verified under the emulator "
-                          "(tests/test_bricks_p2p_threads.py), not yet run on hardware", strict=False)
 def test_bricks_direct_push_over_peer_memory(gpu):
-    """SPIM_BRICK_P2P=1: the halo exchange as one fused copy + signal kernel over CUDA-IPC peer memory (mvd_p2p_*), with
-    the statistics-free iterations captured into a CUDA graph; the run must really have adopted the push path."""
+    """The default exchange: one fused copy + signal kernel over CUDA-IPC peer memory (mvd_p2p_*), with the
+    statistics-free iterations captured into a CUDA graph; the run must really have adopted the push path."""
     n = gpu.getNumDevicesCUDA()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -35,14 +36,13 @@ def test_bricks_direct_push_over_peer_memory(gpu):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "run_bricks_nccl.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    print(r.stdout[-600:])
     assert "BRICKS_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "EXCHANGE_PATH p2p" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-@pytest.mark.xfail(reason="written after the round's GPU budget was spent: verified under the emulator "
-                          "(tests/test_bricks_p2p_threads.py), not yet run on hardware", strict=False)
 def test_bricks_in_one_process_one_thread_per_device(gpu, monkeypatch):
     """The reference's multi-device mode (one host thread per device, MVDeconFFT.java:447-469) with persistent bricks: the
     ranks are threads of THIS process (spim_registration_b200/inprocess.py), peers are reached through raw device pointers
