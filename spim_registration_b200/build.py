@@ -71,15 +71,19 @@ def build_cuda_library(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building " + OUT)
     if objs:
-        rc, out = _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", OUT])
+        # link under a temporary name and rename: a snapshot of the tree taken meanwhile never sees a half-written library
+        tmp = OUT + ".tmp"
+        rc, out = _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", tmp])
         log += out
         if rc != 0:
             sys.stderr.write(log)
             raise RuntimeError("nvcc failed linking " + OUT)
+        os.replace(tmp, OUT)
     if verbose:
         sys.stderr.write(log)
     # the second name the reference's library picker pre-selects (EfficientBayesianBased.java:1127-1131)
-    shutil.copyfile(OUT, ALIAS)
+    shutil.copyfile(OUT, ALIAS + ".tmp")
+    os.replace(ALIAS + ".tmp", ALIAS)
     return OUT
 
 

@@ -108,7 +108,8 @@ struct FftPlanHost {
         for (int s = 0; s < dev.nstages; ++s) {
             const int R = dev.radix[s], M = dev.M[s], L = M * R;
             dev.tw_off[s] = (int)tw.size();
-            if (M == 1) continue;
+            // M == 1 (the last stage): one butterfly's worth of ones, so that the register-resident stage of the x kernels can
+            // load and apply its twiddles unconditionally when it is the only stage of a plan
             for (int j = 0; j < M; ++j)
                 for (int p = 1; p < R; ++p) {
                     const double a = -2.0 * 3.14159265358979323846 * (double)j * (double)p / (double)L;
@@ -235,8 +236,12 @@ public:
         N2 = P[2] / 2;
         pitch = ((N2 + 1 + TC - 1) / TC) * TC;
         fx.create(N2, env_int_now("SPIM_XPLAN_ASC", 0) != 0); fy.create(P[1]); fz.create(P[0]);
-        const size_t need = std::max({(size_t)N2, (size_t)P[1], (size_t)P[0]}) * TC * sizeof(float2) + 512;
-        if (need > rt::max_smem()) throw rt::Error("FFT axis too long for one shared-memory tile");
+        // one tile per block: [N2][16] float2 along x, [P][16] -- or, for long axes, the narrow [P][8] -- along y / z
+        const size_t need_x = (size_t)N2 * TC * sizeof(float2) + 512;
+        const size_t need_c = (size_t)std::max(P[1], P[0]) * (TC / 2) * sizeof(float2) + 512;
+        if (std::max(need_x, need_c) > rt::max_smem())
+            throw rt::Error("FFT axis too long for one shared-memory tile (padded x <= 3624, padded y / z <= 3624 voxels): "
+                            "split the volume into blocks (blockSize) or bricks");
         d_pos = (unsigned short*)rt::dmalloc(sizeof(unsigned short) * N2);
         rt::h2d(d_pos, fx.pos.data(), sizeof(unsigned short) * N2, 0);
         const int nk = N2 / 2 + 1;
@@ -256,6 +261,10 @@ public:
         rt::dfree(d_pos); rt::dfree(d_wx); rt::dfree(spec); rt::dfree(d_kernel);
         for (auto& kv : xtables) rt::dfree(kv.second);
         xtables.clear();
+        for (auto& kv : xfixes) rt::dfree(kv.second.d);
+        xfixes.clear();
+        for (auto& kv : const_rows) rt::dfree(kv.second);
+        const_rows.clear();
         d_pos = nullptr; d_wx = nullptr; spec = nullptr; d_kernel = nullptr; kernel_cap = 0;
     }
     size_t spec_bytes() const { return spec_elems * sizeof(float2); }
@@ -290,6 +299,52 @@ public:
         return d;
     }
 
+    // fix-up list of the TMA-fed x-forward kernel (XFwdT): every padded position whose value is not already where the bulk
+    // copy of the array row puts it (staging index ox + u): {ox + u, source index | -1 zero gap | -2 constant}
+    struct XFix { int2* d = nullptr; int n = 0; };
+    std::map<XKey, XFix> xfixes;
+    XFix x_fix_table(int nx, int hp, int hm, int sx, int ox, int ext, int vlo, int vhi, rt::Stream st) {
+        const XKey key{nx, hp, hm, sx, ox, ext, vlo, vhi};
+        auto it = xfixes.find(key);
+        if (it != xfixes.end()) return it->second;
+        std::vector<int2> f;
+        for (int u = 0; u < P[2]; ++u) {
+            const int a = pad_to_coord(u, nx, hp, hm, P[2]);
+            int i;
+            if (a == kGap) i = -1;
+            else {
+                i = a + ox;
+                if ((unsigned)i >= (unsigned)sx || (a < 0 && !vlo) || (a >= nx && !vhi)) {
+                    const int e = ext_map(a, nx, ext);
+                    i = e < 0 ? -2 : e + ox;
+                }
+            }
+            if (i != ox + u) { int2 e; e.x = ox + u; e.y = i; f.push_back(e); }
+        }
+        XFix r;
+        r.n = (int)f.size();
+        r.d = (int2*)rt::dmalloc(sizeof(int2) * std::max<size_t>(1, f.size()));
+        if (!f.empty()) rt::h2d(r.d, f.data(), sizeof(int2) * f.size(), st);
+        rt::stream_sync(st);
+        xfixes[key] = r;
+        return r;
+    }
+    // a row of the out-of-bounds constant in global memory: lines that are constant along y / z are bulk-copied from it
+    std::map<std::pair<int, unsigned>, float*> const_rows;
+    const float* const_row(int sx, float value, rt::Stream st) {
+        unsigned bits;
+        memcpy(&bits, &value, 4);
+        const auto key = std::make_pair(sx, bits);
+        auto it = const_rows.find(key);
+        if (it != const_rows.end()) return it->second;
+        std::vector<float> h((size_t)sx, value);
+        float* d = (float*)rt::dmalloc(sizeof(float) * (size_t)sx);
+        rt::h2d(d, h.data(), sizeof(float) * (size_t)sx, st);
+        rt::stream_sync(st);
+        const_rows[key] = d;
+        return d;
+    }
+
     // ---- sweeps -------------------------------------------------------------------------
     struct Geom { int n[3], hp[3], hm[3]; };   // logical size + halos of whatever is being transformed
 
@@ -317,6 +372,42 @@ public:
         p.xidx = x_index_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
+        // TMA-fed persistent pipeline (XFwdT, the default): needs 16-byte aligned source rows and an even x origin
+        const int tma = env_int_now("SPIM_XFWD_TMA", 1);
+        if (tma && (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && p.sx % 4 == 0 && p.ox % 2 == 0 && grid <= 0x7fffffff) {
+            XFwdTParams q;
+            memset(&q, 0, sizeof(q));
+            q.x = p;
+            q.LS = (std::max(p.sx, p.ox + P[2]) + 3) & ~3;
+            q.row_bytes = (unsigned)p.sx * 4u;
+            const size_t slot_bytes = (size_t)TC * q.LS * sizeof(float);
+            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t);
+            const size_t lim = rt::max_smem();
+            // blocks per SM / slots per block: three blocks with one slot each where that fits (tiles up to ~36 KB), else two
+            // blocks with one slot, else one block with as many slots as fit
+            int nslot = env_int_now("SPIM_XFWD_SLOTS", 0), bps = 0;
+            if (nslot <= 0) nslot = 1;
+            nslot = std::min(nslot, (int)XFwdT::MAXSLOT);
+            while (nslot > 1 && fixed + nslot * slot_bytes + 1024 > lim) --nslot;
+            const size_t sm = fixed + nslot * slot_bytes;
+            if (sm + 1024 <= lim) {
+                bps = (int)std::min<size_t>(3, lim / (sm + 1024));
+                const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
+                q.fix = fx_.d; q.nfix = fx_.n;
+                q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
+                q.const_row = const_row(p.sx, q.cval, st);
+                q.nslot = nslot;
+                q.ntiles = (int)grid;
+                q.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count() * bps);
+                if (timer) timer->begin(K_XFWD, st);
+                const int T = env_int_now("SPIM_THREADS_XFWDT", 0);
+                if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, T > 0 ? T : 256, sm, st);
+                else if (bps == 2) rt::launch<XFwdT, 384, 2>(q, q.nctas, T > 0 ? T : 384, sm, st);
+                else rt::launch<XFwdT, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
+                if (timer) timer->end(K_XFWD, st);
+                return;
+            }
+        }
         if (timer) timer->begin(K_XFWD, st);
         // four 192-thread blocks per SM (the measured round-1 configuration) need <= 85 registers
         // SPIM_THREADS_XFWD=160 (experiment): the phases of a 280-point tile hold 280 / 320 / 448 / 282 items -- 160 threads need
@@ -460,6 +551,54 @@ public:
         p.nblocks = (int)grid;
         p.reverse = (use_serpentine() && e.epi != EPI_STORE && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
+        // TMA-fed persistent pipeline (XInvP, the default): spectrum rows are always 16-byte aligned
+        if (env_int_now("SPIM_XINV_TMA", 1) && grid <= 0x7fffffff) {
+            XInvPParams q;
+            memset(&q, 0, sizeof(q));
+            q.x = p;
+            q.row_bytes = (unsigned)pitch * (unsigned)sizeof(float2);
+            q.prefetch = env_int_now("SPIM_XINV_PREFETCH", 1);
+            const size_t slot_bytes = (size_t)TC * pitch * sizeof(float2);
+            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long) + 3 * sizeof(uint64_t);
+            const size_t lim = rt::max_smem();
+            int nslot = std::max(1, std::min(3, env_int_now("SPIM_XINV_SLOTS", 1)));
+            while (nslot > 1 && fixed + nslot * slot_bytes + 1024 > lim) --nslot;
+            const size_t sm = fixed + nslot * slot_bytes;
+            if (sm + 1024 <= lim) {
+                const int bps = (int)std::min<size_t>(3, lim / (sm + 1024));
+                q.nslot = nslot;
+                q.ntiles = (int)grid;
+                const int T = env_int_now("SPIM_THREADS_XINVP", 0);
+                if (timer) timer->begin(K_XINV, st);
+                const bool hot = p.fast_epilogue && !e.exact_tikhonov && e.epi != EPI_STORE;
+                if (hot && bps >= 3) {
+                    q.nctas = (int)std::min<long long>(grid, 3LL * rt::sm_count());
+                    // ratio: 80 registers, three blocks of 256 threads; update: 128 registers uncapped -- 160 threads run it
+                    // without spills, 192 threads (one round less per tile) cap it at 96 registers with ~130 bytes of spills
+                    if (e.epi == EPI_RATIO) rt::launch<XInvPRatioFast, 256, 3>(q, q.nctas, T > 0 ? T : 256, sm, st);
+                    else if (T > 0 && T <= 160) rt::launch<XInvPUpdateFast, 160, 3>(q, q.nctas, T, sm, st);
+                    else rt::launch<XInvPUpdateFast, 192, 3>(q, q.nctas, T > 0 ? T : 192, sm, st);
+                } else if (hot && bps == 1) {
+                    q.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
+                    if (e.epi == EPI_RATIO) rt::launch<XInvPRatioFast, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
+                    else rt::launch<XInvPUpdateFast, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
+                } else {
+                    const int b2 = std::min(bps, 2);
+                    q.nctas = (int)std::min<long long>(grid, (long long)b2 * rt::sm_count());
+                    const int T2 = T > 0 ? T : 256;
+                    if (e.epi == EPI_STORE) rt::launch<XInvPStore, 256, 2>(q, q.nctas, T2, sm, st);
+                    else if (e.epi == EPI_RATIO) {
+                        if (p.fast_epilogue) rt::launch<XInvPRatioFast, 256, 2>(q, q.nctas, T2, sm, st);
+                        else rt::launch<XInvPRatioIeee, 256, 2>(q, q.nctas, T2, sm, st);
+                    }
+                    else if (e.exact_tikhonov) rt::launch<XInvPUpdateExact64, 256, 2>(q, q.nctas, T2, sm, st);
+                    else if (p.fast_epilogue) rt::launch<XInvPUpdateFast, 256, 2>(q, q.nctas, T2, sm, st);
+                    else rt::launch<XInvPUpdateIeee, 256, 2>(q, q.nctas, T2, sm, st);
+                }
+                if (timer) timer->end(K_XINV, st);
+                return;
+            }
+        }
         if (timer) timer->begin(K_XINV, st);
         const int T = threads_xinv();
         // 36 KB tiles: six 128-thread blocks fit per SM as long as the ratio kernel stays within 85 registers

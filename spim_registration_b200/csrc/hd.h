@@ -15,6 +15,7 @@
 
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct alignas(8) int2 { int x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #define SPIM_DEV inline
@@ -161,6 +162,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const SpimTensorMap*
 __device__ __forceinline__ void tma_load_3d(void* dst_smem, const SpimTensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// pull the 16-byte granules that lie entirely inside [p, p + n floats) into L2 (no data is returned, nothing is ordered)
+__device__ __forceinline__ void bulk_prefetch_l2(const float* p, int n) {
+    const unsigned long long a = (reinterpret_cast<unsigned long long>(p) + 15ull) & ~15ull;
+    const unsigned long long e = (reinterpret_cast<unsigned long long>(p) + 4ull * (unsigned long long)n) & ~15ull;
+    if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // explicitly un-fused fp32 ops: the reference's Java float arithmetic has no FMA contraction

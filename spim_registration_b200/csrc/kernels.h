@@ -805,7 +805,7 @@ SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* sr
         dft<R, false>(a);
         dft<R, false>(b);
         // twiddles are fetched on use here: holding them across the loads and the butterfly costs the fourth resident block
-        if (M > 1) apply_twiddles2<R, false>(a, b, twp + m * (R - 1));
+        apply_twiddles2<R, false>(a, b, twp + m * (R - 1));     // M == 1: a table of ones
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
@@ -926,6 +926,172 @@ struct XFwd {
             const int j = i - b * npad;
             const long long d_o = dstoff[b];
             if (d_o >= 0) p.spec[d_o + N2 + 1 + j] = make_float2(0.f, 0.f);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// XFwdT: the x-forward pass as a persistent, TMA-fed pipeline (the default wherever the source rows are 16-byte aligned).
+//
+// A tile's 16 source rows are whole contiguous lines of the real volume, so each is fetched by ONE bulk copy
+// (cp.async.bulk, UBLKCP) into a line-major staging slot in shared memory, completion counted on an mbarrier.  The CTA is
+// persistent (tiles bid, bid + nctas, ...): while it runs the butterflies of tile i, the rows of tile i + nslot are
+// already in flight, so no warp ever waits on a global load, and the first stage is straight-line code -- every operand of
+// the padded line comes from the staging slot:
+//   * staging index ox + u holds padded position u.  The bulk copy drops the array row at index 0, which puts the image
+//     (and, in brick mode, the neighbour-provided halo after it) exactly there;
+//   * everything else -- the halo before the image (padded positions [P - hm, P)), mirrored / constant out-of-bounds
+//     values, the zero gap -- is patched in by a short fix-up list (dst index, src index | -1 zero | -2 constant) built on
+//     the host per geometry, ~3 entries per line-pair item;
+//   * lines that are constant by the out-of-bounds rule along y / z are copies of a constant row in global memory, so they
+//     take the same path as every other line.
+// The transposed tile, the remaining stages and the R2C split step are those of XFwd.
+// ---------------------------------------------------------------------------------------------
+struct XFwdTParams {
+    XFwdParams x;
+    int ntiles, nctas, nslot;
+    int LS;                    // floats per staging line (multiple of 4, >= max(sx, ox + Px))
+    unsigned row_bytes;        // sx * 4, multiple of 16
+    const float* const_row;    // sx floats of the out-of-bounds constant (0 for rules that never yield one)
+    float cval;                // that constant
+    const int2* fix;           // fix-up list: staging[fix.x] = fix.y >= 0 ? staging[fix.y] : (fix.y == -1 ? 0 : cval)
+    int nfix;
+};
+
+// source row of padded line l (nullptr beyond the last line) and its destination offset in the spectrum
+SPIM_DEV const float* xfwd_line(const XFwdTParams& q, long long l, long long& d_o) {
+    const XFwdParams& p = q.x;
+    d_o = -1;
+    if (l >= p.nlines) return nullptr;
+    const int iz = (int)(l / p.LY);
+    const int iy = (int)(l - (long long)iz * p.LY);
+    const int yp = iy < p.ny + p.hpy ? iy : iy + (p.Py - p.LY);
+    const int zp = iz < p.nz + p.hpz ? iz : iz + (p.Pz - p.LZ);
+    const int ay = iy < p.ny + p.hpy ? iy : iy - p.LY;
+    const int az = iz < p.nz + p.hpz ? iz : iz - p.LZ;
+    int jy = ay + p.oy, jz = az + p.oz;
+    bool cst = false;
+    if ((unsigned)jy >= (unsigned)p.sy || (ay < 0 && !(p.halo_lo & 2)) || (ay >= p.ny && !(p.halo_hi & 2))) {
+        const int e = ext_map(ay, p.ny, p.ext);
+        if (e < 0) cst = true; else jy = e + p.oy;
+    }
+    if ((unsigned)jz >= (unsigned)p.sz || (az < 0 && !(p.halo_lo & 1)) || (az >= p.nz && !(p.halo_hi & 1))) {
+        const int e = ext_map(az, p.nz, p.ext);
+        if (e < 0) cst = true; else jz = e + p.oz;
+    }
+    d_o = ((long long)zp * p.Py + yp) * (long long)p.pitch;
+    return cst ? q.const_row : p.src + ((long long)jz * p.sy + jy) * (long long)p.sx;
+}
+
+template <int R>
+SPIM_DEV void xfwdt_stage0(const XFwdParams& p, float4* tile, const float* stg, int LS) {
+    const FftPlanDev& pl = p.plan;
+    const int M = pl.M[0];
+    const float2* twp = pl.tws + pl.tw_off[0];
+    SPIM_FOR_ITEMS(i, M * TP) {
+        const int bp = (M == 1) ? i : fastdiv(i, p.magic_m0);
+        const int m = i - bp * M;
+        const float2* l0 = reinterpret_cast<const float2*>(stg + (2 * bp) * LS + p.ox) + m;
+        const float2* l1 = reinterpret_cast<const float2*>(stg + (2 * bp + 1) * LS + p.ox) + m;
+        float2 a[R], b[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) { a[q] = l0[q * M]; b[q] = l1[q * M]; }
+        dft<R, false>(a);
+        dft<R, false>(b);
+        apply_twiddles2<R, false>(a, b, twp + m * (R - 1));     // M == 1: a table of ones
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int row = m + q * M;
+            tile[row * TP + ((bp + row) & (TP - 1))] = pack4(a[q], b[q]);
+        }
+    }
+}
+
+struct XFwdT {
+    typedef XFwdTParams Params;
+    static constexpr bool kEmuThreads = true;
+    static constexpr int MAXSLOT = 3;
+    // descriptors of tile t into slot `slot`, and its 16 row copies.  GPU: the first warp; emulator: every thread its lines.
+    SPIM_DEV static void issue(const Params& q, int t, int slot, float* stg, long long* dsto, uint64_t* full) {
+#if defined(SPIM_HOST_EMU)
+        (void)full;
+        SPIM_FOR_ITEMS(b, TC) {
+            long long d_o;
+            const float* sp = xfwd_line(q, (long long)t * TC + b, d_o);
+            dsto[slot * TC + b] = d_o;
+            if (sp) memcpy(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes);
+        }
+#else
+        if (threadIdx.x < 32) {
+            const int b = (int)threadIdx.x;
+            long long d_o = -1;
+            const float* sp = nullptr;
+            if (b < TC) {
+                sp = xfwd_line(q, (long long)t * TC + b, d_o);
+                dsto[slot * TC + b] = d_o;
+            }
+            const unsigned live = __ballot_sync(0xffffffffu, sp != nullptr);
+            if (b == 0) mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes);
+            __syncwarp();
+            if (sp) bulk_g2s(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes, full + slot);
+        }
+#endif
+    }
+    SPIM_DEV static void run(const Params& q, int bid, float2* smem2) {
+        const XFwdParams& p = q.x;
+        const TG tg = tg_cta();
+        const FftPlanDev& pl = p.plan;
+        const int N2 = pl.n;
+        float4* tile = reinterpret_cast<float4*>(smem2);
+        float* stg = reinterpret_cast<float*>(smem2 + (size_t)N2 * TC);
+        long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * q.LS);     // [nslot][TC]
+        long long* dcur = dsto + MAXSLOT * TC;                                                 // [TC], the tile in work
+        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC);                               // [nslot]
+        const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
+#if !defined(SPIM_HOST_EMU)
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < q.nslot; ++s) mbar_init(full + s, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+#endif
+        for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, bid + j * q.nctas, j, stg, dsto, full);
+        SPIM_BARRIER();
+        GRows g;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        for (int i = 0; i < ntl; ++i) {
+            const int slot = i % q.nslot;
+            float* sl = stg + (size_t)slot * TC * q.LS;
+#if !defined(SPIM_HOST_EMU)
+            mbar_wait(full + slot, (unsigned)((i / q.nslot) & 1));
+#endif
+            // fix-ups: halo before the image, out-of-bounds values, zero gap
+            SPIM_FOR_ITEMS(it, TC * q.nfix) {
+                const int b = it / q.nfix;
+                const int j = it - b * q.nfix;
+                if (dsto[slot * TC + b] < 0) continue;
+                const int2 f = spim_ldg(q.fix + j);
+                float* ln = sl + b * q.LS;
+                ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
+            }
+            SPIM_FOR_ITEMS(b, TC) dcur[b] = dsto[slot * TC + b];
+            SPIM_BARRIER();
+            SPIM_RADIX_SWITCH(pl.radix[0], (xfwdt_stage0<RR>(p, tile, sl, q.LS)))
+#if !defined(SPIM_HOST_EMU)
+            fence_proxy_async();       // this slot's generic-proxy accesses are ordered before the async-proxy refill below
+#endif
+            SPIM_BARRIER();
+            if (i + q.nslot < ntl) issue(q, bid + (i + q.nslot) * q.nctas, slot, stg, dsto, full);
+            for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
+            xfwd_split(p, tile, dcur, N2);
+            const int npad = p.pitch - (N2 + 1);
+            SPIM_FOR_ITEMS(k, npad * TC) {
+                const int b = k / (npad > 0 ? npad : 1);
+                const int j = k - b * npad;
+                const long long d_o = dcur[b];
+                if (d_o >= 0) p.spec[d_o + N2 + 1 + j] = make_float2(0.f, 0.f);
+            }
+            SPIM_BARRIER();            // the tile and dcur are free for the next round
         }
     }
 };
@@ -1084,7 +1250,7 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
         if (d_o < 0) continue;
         const long long a_o = auxoff[b];
         float2 x1[R], x2[R], w[R];
-        if (M > 1) load_twiddles<R>(w, twp + m * (R - 1));
+        load_twiddles<R>(w, twp + m * (R - 1));     // single-stage plans (M == 1) have a table of ones: no conditional definition
         if (VEC) {
             // 8-byte accesses (nx even, aligned buffers): one base pointer per array and item, predicated accesses per row
             // pair instead of early exits, the weight's null check once per item
@@ -1109,7 +1275,7 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
         float2 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = tile2[xelem(b, m + q * M)];
-        if (M > 1) mul_twiddles1<R, true>(a, w);
+        mul_twiddles1<R, true>(a, w);
         dft<R, true>(a);
         float csum = 0.f, cmax = 0.f;
         if (VEC) {
@@ -1287,6 +1453,167 @@ struct XInvT {
         }
         else if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
         else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
+        if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// XInvP: the x-inverse pass as a persistent, TMA-fed pipeline (the default; XInvT remains for unaligned buffers and brick
+// sessions with the fused halo push).  The 16 spectrum lines of a tile are whole contiguous rows of `pitch` float2: each is
+// fetched by one bulk copy (UBLKCP) into a line-major staging slot while the previous tile is still being transformed; the
+// C2R pre-step reads the slot (conflict-free 8-byte accesses along k) instead of issuing 16 global loads per item, and the
+// rows of the epilogue inputs (observed image, or psi and weight) are pulled into L2 by bulk prefetches issued when the tile
+// starts, three shared-memory stages before the epilogue loads them.  Change statistics are accumulated over all tiles of a
+// CTA and committed once.
+// ---------------------------------------------------------------------------------------------
+struct XInvPParams {
+    XInvParams x;
+    int ntiles, nctas, nslot;
+    unsigned row_bytes;        // pitch * 8
+    int prefetch;              // bulk L2 prefetch of the epilogue input rows
+};
+
+SPIM_DEV void xinvp_presplit(const XInvParams& p, float4* tile, const float2* stg, int N2) {
+    const int nk = p.nk;
+    const int LSP = p.pitch;
+    SPIM_FOR_ITEMS(i, nk * (TP / XG)) {
+        const int h = fastdiv(i, p.magic_nk);
+        const int k = i - h * nk;
+        const int km = N2 - k;
+        const float2 w = spim_ldg(p.wx + k);
+        const int rk = spim_ldg(p.pos + k);
+        const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
+        const bool two = (k != 0) && (km != k);
+        const float2* l = stg + (size_t)(h * XG * 2) * LSP;
+#pragma unroll
+        for (int g = 0; g < XG; ++g) {
+            const int bp = h * XG + g;
+            const float2 A0 = l[k], B0 = l[km], A1 = l[LSP + k], B1 = l[LSP + km];
+            l += 2 * LSP;
+            float2 zk0, zm0, zk1, zm1;
+            split_inv(A0, B0, w, zk0, zm0);
+            split_inv(A1, B1, w, zk1, zm1);
+            tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
+            if (two) tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
+        }
+    }
+}
+
+template <int EPI, int MATH, int R0MAX = 16>
+struct XInvP {
+    typedef XInvPParams Params;
+    static constexpr bool kEmuThreads = true;
+    static constexpr int MAXSLOT = 3;
+    SPIM_DEV static void issue(const Params& q, int t, int slot, float2* stg, uint64_t* full) {
+        const XInvParams& p = q.x;
+#if defined(SPIM_HOST_EMU)
+        (void)full;
+        SPIM_FOR_ITEMS(b, TC) {
+            const long long l = (long long)t * TC + b;
+            if (l < p.nlines) {
+                const int z = (int)(l / p.ny);
+                const int y = (int)(l - (long long)z * p.ny);
+                memcpy(stg + ((size_t)slot * TC + b) * p.pitch, p.spec + ((long long)z * p.Py + y) * (long long)p.pitch, q.row_bytes);
+            }
+        }
+#else
+        if (threadIdx.x < 32) {
+            const int b = (int)threadIdx.x;
+            const long long l = (long long)t * TC + b;
+            const bool live1 = b < TC && l < p.nlines;
+            const unsigned live = __ballot_sync(0xffffffffu, live1);
+            if (b == 0) mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes);
+            __syncwarp();
+            if (live1) {
+                const int z = (int)(l / p.ny);
+                const int y = (int)(l - (long long)z * p.ny);
+                bulk_g2s(stg + ((size_t)slot * TC + b) * p.pitch, p.spec + ((long long)z * p.Py + y) * (long long)p.pitch, q.row_bytes, full + slot);
+                if (q.prefetch && EPI != EPI_STORE) {
+                    // epilogue inputs of the same tile -> L2 (rows of nx floats)
+                    const long long d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
+                    const long long a_o = ((long long)z * p.ny + y) * (long long)p.nx;
+                    if (EPI == EPI_RATIO) bulk_prefetch_l2(p.img + a_o, p.nx);
+                    else {
+                        bulk_prefetch_l2(p.dst + d_o, p.nx);
+                        if (p.weight) bulk_prefetch_l2(p.weight + a_o, p.nx);
+                    }
+                }
+            }
+        }
+#endif
+    }
+    // One tile.  (Every register array of a phase must be defined unconditionally: a definition under a predicate, like the
+    // stage-0 twiddles once were for M > 1, keeps its registers live around the whole persistent loop -- for every radix path
+    // at once, 255 registers and spills instead of 80.)
+    SPIM_DEV static void tile_body(const Params& q, int t, int nxt, int slot, unsigned parity, float2* tile2, float2* stg,
+                                     long long* dstoff, long long* auxoff, uint64_t* full, EpiAcc& acc_out) {
+        const XInvParams& p = q.x;
+        const TG tg = tg_cta();
+        float4* tile = reinterpret_cast<float4*>(tile2);
+        const FftPlanDev& pl = p.plan;
+        const int N2 = pl.n;
+        GRows g;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        SPIM_FOR_ITEMS(b, TC) {
+            const long long l = (long long)t * TC + b;
+            long long d_o = -1, a_o = -1;
+            if (l < p.nlines) {
+                const int z = (int)(l / p.ny);
+                const int y = (int)(l - (long long)z * p.ny);
+                d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
+                a_o = ((long long)z * p.ny + y) * (long long)p.nx;
+            }
+            dstoff[b] = d_o; auxoff[b] = a_o;
+        }
+#if !defined(SPIM_HOST_EMU)
+        mbar_wait(full + slot, parity);
+#else
+        (void)parity;
+#endif
+        xinvp_presplit(p, tile, stg + (size_t)slot * TC * p.pitch, N2);
+#if !defined(SPIM_HOST_EMU)
+        fence_proxy_async();
+#endif
+        SPIM_BARRIER();
+        if (nxt >= 0) issue(q, nxt, slot, stg, full);
+        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
+        EpiAcc acc;
+        acc.sum = 0.0; acc.mx = 0.f;
+        if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
+        if (EPI == EPI_UPDATE) { acc_out.sum += acc.sum; acc_out.mx = fmaxf(acc_out.mx, acc.mx); }
+        SPIM_BARRIER();            // the tile and the offset arrays are free for the next round
+    }
+    SPIM_DEV static void run(const Params& q, int bid, float2* tile2) {
+        const XInvParams& p = q.x;
+        const FftPlanDev& pl = p.plan;
+        const int N2 = pl.n;
+        float2* stg = tile2 + (size_t)N2 * TC;                                                   // [nslot][TC][pitch]
+        long long* dstoff = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * p.pitch);
+        long long* auxoff = dstoff + TC;
+        uint64_t* full = reinterpret_cast<uint64_t*>(auxoff + TC);
+        const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
+#if !defined(SPIM_HOST_EMU)
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < q.nslot; ++s) mbar_init(full + s, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+#endif
+        // tile of round i: bid, bid + nctas, ... (from the last tile downwards in the serpentine order)
+        const int t0 = p.reverse ? q.ntiles - 1 - bid : bid;
+        const int dt = p.reverse ? -q.nctas : q.nctas;
+#define tile_at(i) (t0 + (i) * dt)
+        for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, tile_at(j), j, stg, full);
+        SPIM_BARRIER();
+        EpiAcc acc;
+        acc.sum = 0.0; acc.mx = 0.f;
+        for (int i = 0; i < ntl; ++i) {
+            const int slot = i % q.nslot;
+            const int nxt = (i + q.nslot < ntl) ? tile_at(i + q.nslot) : -1;
+            tile_body(q, tile_at(i), nxt, slot, (unsigned)((i / q.nslot) & 1), tile2, stg, dstoff, auxoff, full, acc);
+        }
+#undef tile_at
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }
 };

@@ -1482,6 +1482,7 @@ void convolution3DfftCUDAInPlace(float* im, int* imDim, float* kernel, int* kern
     } catch (const std::exception& e) { fail(e.what()); }
     catch (...) { fail("unknown error"); }
     if (rc) fprintf(stderr, "convolution3DfftCUDAInPlace failed: %s (buffer left untouched)\n", g_last_error.c_str());
+    else g_last_error.clear();      // a void entry: callers that can read spim_fftconv_last_error() see "" after a success
 }
 
 float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA) {
@@ -1499,6 +1500,7 @@ float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim
         free(out);
         return nullptr;
     }
+    g_last_error.clear();
     return out;
 }
 

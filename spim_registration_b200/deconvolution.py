@@ -111,6 +111,12 @@ class Session:
         native.check(self.lib, self.lib.mvd_upload_region(self._h, int(v), int(which), a.ctypes.data, native.int3(lo),
                                                           native.int3(a.shape)), "mvd_upload_region")
 
+    def upload_region_ptr(self, v: int, which: int, ptr: int, lo: Sequence[int], ext: Sequence[int]):
+        """Same from a raw pointer to a tightly packed [z, y, x] cell -- host memory, or device memory (a cell generated or
+        fused on a GPU; mvd_upload_region copies with unified addressing)."""
+        native.check(self.lib, self.lib.mvd_upload_region(self._h, int(v), int(which), C.c_void_p(int(ptr)), native.int3(lo),
+                                                          native.int3(ext)), "mvd_upload_region")
+
     def init(self):
         native.check(self.lib, self.lib.mvd_init(self._h), "mvd_init")
 
@@ -344,10 +350,19 @@ class _ViewFFT:
         bs = self.blockSize
         block = np.empty((bs[2], bs[1], bs[0]), dtype=np.float32)
         kdim = kernel.shape
+        def conv_block(buf, dev):
+            # the JNA entry is void and leaves the buffer untouched on failure (the reference's contract); this host layer
+            # must not paste an un-convolved block back as if it were the result, so it reads the error string the call left
+            # behind (cleared by the library on success, thread-local like the call)
+            cuda.convolution3DfftCUDAInPlace(buf, buf.shape, kernel, kdim, dev)
+            err = cuda.last_error()
+            if err:
+                raise RuntimeError(f"convolution3DfftCUDAInPlace failed on device {dev}: {err}")
+
         if len(self.deviceList) == 1:
             for b in self.blocks:
                 b.copyBlock(image, block, ext, value)
-                cuda.convolution3DfftCUDAInPlace(block, block.shape, kernel, kdim, self.device0)
+                conv_block(block, self.device0)
                 b.pasteBlock(result, block)
             return result
         # multi-device mode (LRFFT.java:499-522, MVDeconFFT.java:447-469): one host thread per entry of deviceList, each
@@ -367,7 +382,7 @@ class _ViewFFT:
                         return
                     b = self.blocks[i]
                     b.copyBlock(image, mine, ext, value)
-                    cuda.convolution3DfftCUDAInPlace(mine, mine.shape, kernel, kdim, dev)
+                    conv_block(mine, dev)
                     b.pasteBlock(result, mine)
             except BaseException as e:      # noqa: BLE001
                 errors.append(e)

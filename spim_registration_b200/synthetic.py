@@ -170,3 +170,53 @@ def make_dataset(shape: Sequence[int], num_views: int, psf_size: int, kind: str 
     psfs = make_psfs(num_views, psf_size)
     imgs, ws = make_views(truth, psfs, seed=seed, weight_mode=weight_mode, blur=blur)
     return truth, imgs, ws, psfs
+
+
+# --------------------------------------------------------------------------------------------------
+# position-deterministic noise volumes for the full-size multi-GPU runs
+# --------------------------------------------------------------------------------------------------
+# Every voxel's value is a hash of its GLOBAL linear index and a seed, so that (a) each rank generates its own brick on
+# its own GPU (torch twin below) without any host memory or PCIe traffic, and (b) a test can regenerate any crop of the
+# global volume on the CPU (numpy twin), bit for bit, and hand it to the oracle.
+_M32 = 0xFFFFFFFF
+
+
+def _hash_u24(idx, seed: int, xp):
+    """idx: int64 array (numpy or torch) of global linear indices -> 24-bit integers, identical in both libraries
+    (64-bit two's-complement products, masked to 32 bits after every step)."""
+    h = (idx * 0x9E3779B1 + (int(seed) * 0x85EBCA6B & _M32)) & _M32
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & _M32
+    h = h ^ (h >> 12)
+    h = (h * 0x297A2D39) & _M32
+    h = h ^ (h >> 15)
+    return h >> 8
+
+
+def hash_volume_numpy(gshape: Sequence[int], lo: Sequence[int], ext: Sequence[int], seed: int, a: float, b: float) -> np.ndarray:
+    """a + b * u, u in [0, 1) hashed from the global index, for the box [lo, lo + ext) of a volume of shape gshape."""
+    z = np.arange(lo[0], lo[0] + ext[0], dtype=np.int64)[:, None, None]
+    y = np.arange(lo[1], lo[1] + ext[1], dtype=np.int64)[None, :, None]
+    x = np.arange(lo[2], lo[2] + ext[2], dtype=np.int64)[None, None, :]
+    idx = (z * int(gshape[1]) + y) * int(gshape[2]) + x
+    u = _hash_u24(idx, seed, np).astype(np.float32) * np.float32(2.0 ** -24)
+    return (np.float32(a) + np.float32(b) * u).astype(np.float32)
+
+
+def hash_volume_torch(gshape: Sequence[int], lo: Sequence[int], ext: Sequence[int], seed: int, a: float, b: float, device):
+    """The same values as hash_volume_numpy, computed on `device` (a float32 torch tensor of shape ext)."""
+    import torch
+    z = torch.arange(lo[0], lo[0] + ext[0], dtype=torch.int64, device=device)[:, None, None]
+    y = torch.arange(lo[1], lo[1] + ext[1], dtype=torch.int64, device=device)[None, :, None]
+    x = torch.arange(lo[2], lo[2] + ext[2], dtype=torch.int64, device=device)[None, None, :]
+    idx = (z * int(gshape[1]) + y) * int(gshape[2]) + x
+    u = _hash_u24(idx, seed, torch).to(torch.float32) * (2.0 ** -24)
+    return (u * b + a).contiguous()      # one rounding for the product, one for the sum, like the numpy twin
+
+
+def hash_view(gshape, lo, ext, view: int, num_views: int, xp="numpy", device=None):
+    """(image, weight) of one view of the hash dataset: image in [0.05, 1), weight in [0.25, 1) / num_views."""
+    f = hash_volume_numpy if xp == "numpy" else (lambda *a_: hash_volume_torch(*a_, device))
+    img = f(gshape, lo, ext, 1000 + view, 0.05, 0.95)
+    w = f(gshape, lo, ext, 5000 + view, 0.25 / num_views, 0.75 / num_views)
+    return img, w
