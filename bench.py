@@ -2,20 +2,26 @@
 """bench.py -- multi-view deconvolution throughput (voxel-view-iterations/s) on N B200s.
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
-prints ONE JSON line on rank 0.
+prints ONE JSON line on rank 0 (the LAST line of stdout; reported extras are printed before it, one short JSON line
+each, and the complete record is also written to gpurun_out/bench_full_N<N>.json when that directory exists).
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): per GPU a
 512x512x256 fp32 volume, 7 views, 31^3 PSFs, Efficient-Bayesian, Tikhonov lambda 0.006,
 synthetic specimen data.  One step = one full iteration (7 view-steps = 14 FFT convolutions with
 their fused ratio / update epilogues).  At N > 1 the global volume is N bricks of that size
 (2 -> 1024x512x256, 4 -> 1024x1024x256, 8 -> 1024x1024x512 = the size of configs[2]) with the
-PSF/2-wide halos exchanged over NCCL every convolution: weak scaling.
+PSF/2-wide halos pushed over NVLink peer memory every convolution: weak scaling.
 
 value    = N_voxels(global) * views * K / device time of K iterations, inputs resident in HBM.
-e2e      = the same metric through the reference-facing call (the MVDeconvolution constructor
-           equivalent: session create + upload of all views from pinned host memory + init +
-           K iterations + mask + download of psi), host<->device copies inside the timed region.
+e2e      = the same metric through the reference-facing call -- at N = 1 literally the plugin's call
+           `MVDeconvolution(views, PSFTYPE, numIterations, lambda, ...)` of spim_registration_b200/deconvolution.py
+           (MVDeconvolution.java:94-211) on pinned host arrays: upload of all views, init, K iterations with their
+           statistics, mask, download of psi; at N > 1 the brick runner (one such call per rank) -- host<->device copies
+           inside the timed region.
 roofline = dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json.
+At N > 1 two more objects: `strong_scaling` (BASELINE configs[2]: ONE fixed 6-view 1024x1024x512 Optimization-II volume
+split over the N GPUs, against the same volume on one GPU of the same box) and, at N = 8, `configs4` (BASELINE
+configs[4]: 8 views, 2048x2048x1024, bricks of 1024x1024x512, 10 iterations).
 """
 from __future__ import annotations
 
@@ -47,6 +53,47 @@ KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor *
 # the x-inverse launch also carries the fused pointwise traffic of SURVEY 8d (16 B per voxel-view-iteration):
 # ratio epilogue reads img (4 N), update epilogue reads weight + psi (8 N); their writes are the sweep's own write
 XINV_POINTWISE_BYTES_PER_VOXEL = 6     # average of the two launches of a view-step
+
+
+def usable_cores():
+    """cores this process may really use: the affinity mask, capped by the cgroup CPU quota (os.cpu_count() reports the
+    whole host on shared multi-GPU boxes, and oversubscribed pocketfft pools halve the CPU baseline)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def config_dict(n_gpus):
+    """the `config` object -- built the same way by both arms (ours and --impl reference) from host-side information only"""
+    from spim_registration_b200 import bricks, native
+    grid = bricks.grid_for(n_gpus)
+    try:
+        lib = native.load_library()
+        fd = [int(lib.mvd_fft_size(BRICK[d] + PSF - 1, 1 if d == 2 else 0)) for d in range(3)]
+    except Exception:
+        fd = None
+    return {"workload": workload_string(n_gpus)[0], "fft_dims_zyx": fd,
+            "np_voxels_per_brick": int(np.prod([b + PSF - 1 for b in BRICK])),
+            "parallelism": (f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), PSF/2 halos pushed over NVLink peer memory (NCCL batch as "
+                            "fallback)") if n_gpus > 1 else "single GPU",
+            "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"}
 
 
 def workload_string(n_gpus):
@@ -149,12 +196,15 @@ def cpu_reference_step(imgs, ws, psfs, psi, k1, k2, v):
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement, all host threads, one view-step per step."""
+    """--impl reference: the CPU restatement of the reference's path on the host cores this process may use; each timed
+    step is a bounded sample (ONE view-step = 1/VIEWS of an iteration of one brick), value normalised to the metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import mvdecon_oracle as O
     from spim_registration_b200 import synthetic
+    cores = usable_cores()
+    O.WORKERS = cores
     shape = BRICK
     truth = synthetic.specimen_truth(shape)
     psfs = synthetic.make_psfs(VIEWS, PSF)
@@ -170,19 +220,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     nvox = int(np.prod(shape))
     value = nvox * args.steps / dt                   # one view-step = N voxel-view-iterations
-    cores = os.cpu_count()
+    sample = (f"each timed step = ONE view-step (1/{VIEWS} of an iteration) of one {BRICK[2]}x{BRICK[1]}x{BRICK[0]} brick on the host "
+              f"CPU, {args.steps} steps; CPU restatement of the reference (NumPy + SciPy pocketfft, {cores} threads); the "
+              "reference JVM is not available")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(args.gpus)[0],
-                   "reference_step": "each timed step of this arm is ONE view-step (1/%d of an iteration) of one "
-                                     "%dx%dx%d brick on the host CPU; value is normalised to voxel-view-iterations/s" % (
-                                         VIEWS, BRICK[2], BRICK[1], BRICK[0]),
-                   "l2": "inputs (256 MiB per volume) larger than any cache"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} view-steps of one {BRICK[2]}x{BRICK[1]}x{BRICK[0]} brick, CPU restatement of the "
-                                   "reference (NumPy + SciPy pocketfft, workers = all cores); reference JVM unavailable"},
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,32 +281,10 @@ def fusion_prestep_leg(shape, views, peak, lib=None, timed=None, stack_planes=No
 # CUDA events).  The first entry is the control: the default configuration in the very same harness.
 VARIANTS = [
     ("default", {}),
+    ("x_kernels_without_tma", {"SPIM_XFWD_TMA": "0", "SPIM_XINV_TMA": "0"}),   # the round-1 x kernels (plain loads, one tile per block)
     ("ieee_epilogue", {"SPIM_FAST_EPI": "0"}),                     # IEEE division / sqrt instead of the branch-free refinement
-    ("lean_z_pass", {"SPIM_COL_LEAN": "1"}),                       # z pass (288 = 8*6*6) compiled for radices <= 8: 80 registers, 24 warps
-    ("xinv_lean_update", {"SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),   # x plan 5*7*8 + update kernel for stage-0 radix <= 5: 24 warps
-    ("pdl", {"SPIM_PDL": "1"}),                                    # programmatic dependent launch
-    ("serpentine", {"SPIM_SERPENTINE": "1"}),                      # y-forward / x-inverse sweeps start on what is still in L2
-    ("y_tiles_3x192_threads", {"SPIM_REGCAP": "2"}),               # 18 resident warps on the y passes instead of 12 (96 registers)
-    ("x_kernels_160_threads", {"SPIM_THREADS_XFWD": "160", "SPIM_THREADS_XINV": "160", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1"}),
-                                                                   # item counts per phase fit 160 threads: 5 blocks of 160 per SM
-    ("combined", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_THREADS_XFWD": "160",
-                  "SPIM_THREADS_XINV": "160", "SPIM_SERPENTINE": "1", "SPIM_REGCAP": "2"}),   # are the gains additive?
-    ("combined_pdl", {"SPIM_COL_LEAN": "1", "SPIM_XPLAN_ASC": "1", "SPIM_XINV_R0": "1", "SPIM_THREADS_XFWD": "160",
-                      "SPIM_THREADS_XINV": "160", "SPIM_SERPENTINE": "1", "SPIM_REGCAP": "2", "SPIM_PDL": "1"}),
-    ("narrow_tiles", {"SPIM_COL_NARROW": "1"}),                    # 8-column tiles on every column pass
-    ("tma_y_passes", {"SPIM_COLP_Y": "3"}),                        # warp-specialised TMA pipeline for the y passes
-    ("xplan_ascending", {"SPIM_XPLAN_ASC": "1"}),                  # the plan order alone
-    ("z_tiles_6x128_threads", {"SPIM_REGCAP": "3"}),               # general kernel capped to 80 registers (spills) on the z pass
-    ("pdl_serpentine", {"SPIM_PDL": "1", "SPIM_SERPENTINE": "1"}),
-    ("col_160_threads", {"SPIM_THREADS_COL": "160"}),
-    ("xinv_update_5_blocks", {"SPIM_XINV_CAP": "5"}),              # general update kernel capped to 96 registers (spills)
-    ("xinv_192_threads", {"SPIM_THREADS_XINV": "192"}),
-    ("xfwd_256_threads", {"SPIM_THREADS_XFWD": "256"}),
-    ("xfwd_128_threads", {"SPIM_THREADS_XFWD": "128"}),
-    ("col_regcap_256_threads", {"SPIM_REGCAP": "1", "SPIM_THREADS_COL": "256"}),
-    ("pdl_tma_y", {"SPIM_PDL": "1", "SPIM_COLP_Y": "3"}),
-    ("warp_private_columns_z", {"SPIM_COLP_Z": "4"}),
-    ("kernel_spectrum_staged", {"SPIM_KSTAGE": "1"}),
+    ("y_passes_cp_async", {"SPIM_COLP_Y": "2"}),                   # y passes with one-shot cp.async staging instead of the TMA pipeline
+    ("no_pdl", {"SPIM_PDL": "0"}),                                 # without programmatic dependent launch
 ]
 
 
@@ -337,46 +361,79 @@ def variants_leg(budget_s=120.0, per_child_s=30.0):
     return out
 
 
-def p2p_flag_path():
-    """host-side signal "the direct-push child job is over" from rank 0 to the other ranks of this job"""
-    return os.path.join("/tmp", "spim_bench_p2p_%s_%s" % (os.environ.get("MASTER_PORT", "0"),
-                                                          os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))))
-
-
-def p2p_variant_leg(n, steps, limit_s=240.0):
-    """Rank 0, N > 1: run this very benchmark once more as a child torchrun job with SPIM_BRICK_P2P=1 (noise inputs, no
-    extras) and return its throughput.  The child is its own process group and is killed as a group at the time limit."""
-    import signal
-    import socket
-    sk = socket.socket()
-    sk.bind(("127.0.0.1", 0))
-    port = sk.getsockname()[1]
-    sk.close()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.abspath(__file__), "--gpus", str(n), "--steps", str(max(3, min(steps, 10))),
-           "--warmup", "3", "--no-cpu-baseline", "--no-fusion-leg", "--no-cufft-leg", "--no-variants", "--no-p2p-variant",
-           "--fast-inputs", "--skip-e2e", "--brick", str(BRICK[0]), str(BRICK[1]), str(BRICK[2]), "--views", str(VIEWS)]
-    drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_NAME",
-            "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")
-    env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC_")}
-    env.update(SPIM_BRICK_P2P="1", SPIM_P2P_TIMEOUT_S="10")
-    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+def emit_extra(name, obj):
+    """a reported extra as its own short line BEFORE the final line (the final line stays small enough to survive any tail)"""
     try:
-        out, err = p.communicate(timeout=limit_s)
-    except subprocess.TimeoutExpired:
+        print(json.dumps({"extra": name, "data": obj}), flush=True)
+    except Exception:
+        pass
+
+
+def strong_scaling_leg(rank, N, local, dist, iters=5):
+    """BASELINE configs[2]: ONE fixed 6-view 1024x1024x512 volume, 31^3 PSFs, Optimization II, split over the N GPUs (hash
+    inputs generated on the devices), against the same volume on one GPU of the same box (rank 0 alone, the others wait)."""
+    import torch
+    from spim_registration_b200 import bigvolume, bricks
+    G = (512, 1024, 1024)
+    grid = bricks.grid_for(N)
+    brick = tuple(G[d] // grid[d] for d in range(3))
+    out = {"workload": "6-view 1024x1024x512 fp32, 31^3 PSFs, Optimization II (BASELINE configs[2]), hash-noise inputs generated on the "
+                       "devices, %d iterations timed after one warm-up" % iters, "n_gpus": N, "brick_zyx": list(brick)}
+    r, meta = bigvolume.setup_runner(brick, 6, 0, rank, N, local, dist)
+    ms = bigvolume.time_iterations(r, iters, dist)
+    out["ms_per_iteration"] = ms
+    out["value"] = int(np.prod(G)) * 6 / (ms * 1e-3)
+    out["exchange"] = meta["exchange"]
+    out["peak_device_bytes_per_gpu"] = bigvolume.peak_device_bytes(dist, N)
+    r.close()
+    del r
+    torch.cuda.empty_cache()
+    dist.barrier()
+    one = torch.zeros(2, dtype=torch.float64, device="cuda")
+    if rank == 0:
         try:
-            os.killpg(p.pid, signal.SIGKILL)      # exactly the process group started above
-        except OSError:
-            pass
-        p.communicate()
-        return {"error": f"child job exceeded {limit_s:.0f} s and was stopped"}
-    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
-    if p.returncode != 0 or not lines:
-        return {"error": f"child job exit {p.returncode}: {(err or '').strip()[-300:]}"}
-    d = json.loads(lines[-1])
-    return {"value": d.get("value"), "ms_per_step": d.get("ms_per_step"), "steps": d.get("steps"),
-            "exchange": (d.get("config") or {}).get("parallelism"), "data": "noise inputs (timing only)",
-            "per_kernel_ms": {k: v.get("avg_ms") for k, v in ((d.get("roofline_conv_pass") or {}).get("per_kernel") or {}).items()}}
+            r1, meta1 = bigvolume.setup_runner(G, 6, 0, 0, 1, local, None)
+            ms1 = bigvolume.time_iterations(r1, max(2, iters // 2), None)
+            one[0] = ms1
+            per = bigvolume.kernel_times(r1, 1)
+            tot = sum(per.values())
+            one[1] = 44 * meta1["np_voxels_per_brick"] / (tot * 1e-3) / 1e9 / peaks()[0]
+            r1.close()
+            del r1
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            out["one_gpu_error"] = f"{type(e).__name__}: {e}"
+    dist.all_reduce(one)            # doubles as the barrier the other ranks wait in
+    ms1 = float(one[0].item())
+    if ms1 > 0:
+        out["one_gpu_ms_per_iteration"] = ms1
+        out["one_gpu_value"] = int(np.prod(G)) * 6 / (ms1 * 1e-3)
+        out["one_gpu_conv_pass_frac"] = float(one[1].item())
+        out["speedup_vs_one_gpu"] = ms1 / ms
+        out["efficiency"] = ms1 / ms / N
+    return out
+
+
+def configs4_leg(rank, N, local, dist, iters=10):
+    """BASELINE configs[4]: 8 views, 2048x2048x1024, 31^3 PSFs, Efficient-Bayesian, bricks of 1024x1024x512 on 8 GPUs, views
+    handed over cell by cell with mvd_upload_region from device memory, 10 iterations (oracle spot check of the same run:
+    tests/run_bricks_fullsize.py --config c5, log under profiles/)."""
+    import torch
+    from spim_registration_b200 import bigvolume
+    brick = (512, 1024, 1024)
+    r, meta = bigvolume.setup_runner(brick, 8, ITER_TYPE, rank, N, local, dist)
+    ms = bigvolume.time_iterations(r, iters, dist)
+    G = meta["global_zyx"]
+    out = {"workload": "8-view 2048x2048x1024 fp32, 31^3 PSFs, Efficient-Bayesian, bricks of 1024x1024x512 (BASELINE configs[4]), "
+                       "hash-noise inputs generated on the devices and handed over with mvd_upload_region",
+           "iterations": iters, "ms_per_iteration": ms, "value": int(np.prod(G)) * 8 / (ms * 1e-3), "unit": UNIT,
+           "fft_dims_zyx": meta["fft_dims_zyx"], "exchange": meta["exchange"],
+           "peak_device_bytes_per_gpu": bigvolume.peak_device_bytes(dist, N), "session_device_bytes": meta["session_device_bytes"],
+           "t_generate_upload_s": meta["t_generate_upload_s"], "t_init_s": meta["t_init_s"]}
+    r.close()
+    del r
+    torch.cuda.empty_cache()
+    return out
 
 
 _T0 = time.perf_counter()
@@ -399,7 +456,7 @@ def main():
     ap.add_argument("--no-cufft-leg", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the A/B matrix of kernel variants (an extra of the default run)")
     ap.add_argument("--variant-child", action="store_true", help="internal: one configuration of the A/B matrix")
-    ap.add_argument("--no-p2p-variant", action="store_true", help="N > 1: skip the child job that times the direct halo push")
+    ap.add_argument("--no-big-legs", action="store_true", help="N > 1: skip the strong-scaling (configs[2]) and configs[4] legs")
     ap.add_argument("--fast-inputs", action="store_true", help="internal: noise inputs instead of the synthetic specimen")
     ap.add_argument("--skip-e2e", action="store_true", help="internal: timing-only child runs")
     ap.add_argument("--fusion-leg-only", action="store_true", help="internal: run the fusion pre-step leg and print its JSON")
@@ -446,11 +503,6 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        if rank == 0:       # a flag file left behind by an aborted earlier run must not release the other ranks early (see below)
-            try:
-                os.remove(p2p_flag_path())
-            except OSError:
-                pass
         dist.barrier()
         tlog("process group up")
     if world != args.gpus:
@@ -576,50 +628,62 @@ def main():
 
     # ---------------- end to end through the reference-facing call -------------------------------------
     barrier()
-    t_e2e, e2e_value = None, None
+    t_e2e, e2e_value, e2e_note = None, None, None
     if not args.skip_e2e:
-        t0 = time.perf_counter()
-        r2 = new_runner()
-        upload(r2)
-        r2.init()
-        r2.run(args.steps)
-        r2.finish()
-        r2.session.get_psi_ptr(pin_out.data_ptr())
-        torch.cuda.synchronize()
-        t_e2e = max_over_ranks(time.perf_counter() - t0)
-        r2.close()
+        if N == 1:
+            # the plugin's own call: MVDeconInput.add(new MVDeconFFT(image, weight, kernel, ...)) per view, then the
+            # MVDeconvolution constructor, which runs all iterations (MVDeconvolution.java:94-211), then getPsi()
+            from spim_registration_b200.deconvolution import MVDeconFFT, MVDeconInput, MVDeconvolution, PSFTYPE
+            out_np = pin_out.numpy()
+            t0 = time.perf_counter()
+            views = MVDeconInput()
+            for v in range(VIEWS):
+                views.add(MVDeconFFT(pin_img[v].numpy(), pin_w[v].numpy(), psfs[v], None, (local,), False, None, False))
+            decon = MVDeconvolution(views, PSFTYPE(ITER_TYPE), args.steps, LAMBDA, 1.0, 0, "bench")
+            decon.getPsi(out_np)
+            torch.cuda.synchronize()
+            t_e2e = time.perf_counter() - t0
+            del decon, views
+            e2e_note = ("MVDeconInput.add(MVDeconFFT(...)) x views + MVDeconvolution(views, PSFTYPE, K, lambda, ...) + getPsi(): upload of "
+                        "all views from pinned memory, init, K iterations with per-view statistics, mask, download of psi")
+        else:
+            t0 = time.perf_counter()
+            r2 = new_runner()
+            upload(r2)
+            r2.init()
+            r2.run(args.steps)
+            r2.finish()
+            r2.session.get_psi_ptr(pin_out.data_ptr())
+            torch.cuda.synchronize()
+            t_e2e = max_over_ranks(time.perf_counter() - t0)
+            r2.close()
+            e2e_note = ("per rank: brick session create + upload of all views from pinned memory + init (average all-reduced, peers "
+                        "connected) + K iterations + mask + download of the brick of psi")
         e2e_value = nvox_global * VIEWS * args.steps / t_e2e
         tlog("e2e done")
 
-    # ---------------- reported extra at N > 1: the same job with the direct halo push (SPIM_BRICK_P2P=1) -------------------
-    # A separate torchrun job started by rank 0 (own process group, own NCCL communicator, hard time limit), so that the
-    # opt-in exchange path is timed on real links in every scaling run without being able to take this line with it.
-    # The other ranks wait on the host (a flag file), not in a collective, so no NCCL kernel spins on their GPUs meanwhile.
-    p2p_variant = None
-    if N > 1 and not args.no_p2p_variant and os.environ.get("SPIM_BRICK_P2P", "0") != "1":
-        flag = p2p_flag_path()
-        if rank == 0:
-            try:
-                p2p_variant = p2p_variant_leg(N, args.steps)
-            except Exception as e:      # noqa: BLE001
-                p2p_variant = {"error": f"{type(e).__name__}: {e}"}
-            open(flag, "w").close()
-            tlog("p2p variant done")
-        else:
-            t_wait = time.perf_counter()
-            while not os.path.exists(flag) and time.perf_counter() - t_wait < 400:
-                time.sleep(0.2)
+    # ---------------- N > 1: strong scaling on the configs[2] volume, configs[4] at N = 8 ----------------------------------
+    strong, configs4 = None, None
+    if N > 1 and not args.no_big_legs and tuple(BRICK) == (256, 512, 512):
+        try:
+            strong = strong_scaling_leg(rank, N, local, dist)
+        except Exception as e:      # noqa: BLE001
+            strong = {"error": f"{type(e).__name__}: {e}"}
         barrier()
-        if rank == 0:
+        tlog("strong-scaling leg done")
+        if N == 8:
             try:
-                os.remove(flag)
-            except OSError:
-                pass
+                configs4 = configs4_leg(rank, N, local, dist)
+            except Exception as e:      # noqa: BLE001
+                configs4 = {"error": f"{type(e).__name__}: {e}"}
+            barrier()
+            tlog("configs[4] leg done")
 
     # ---------------- CPU baseline: the oracle on a bounded sample (rank 0, N = 1 only) --------------------
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         from oracle import mvdecon_oracle as O
+        O.WORKERS = usable_cores()
         k1, k2 = O.init_kernels(psfs, ITER_TYPE)
         psi = np.full(BRICK, np.float32(info.avg), np.float32)
         nsteps = 2
@@ -627,9 +691,9 @@ def main():
         for v in range(nsteps):
             psi = cpu_reference_step(imgs, ws, psfs, psi, k1, k2, v)
         dt = time.perf_counter() - t0
-        cpu = {"value": nvox_brick * nsteps / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": nvox_brick * nsteps / dt, "unit": UNIT, "cores": usable_cores(), "kind": "port",
                "sample": f"{nsteps} view-steps (of {VIEWS * args.steps}) of the same {BRICK[2]}x{BRICK[1]}x{BRICK[0]} "
-                         "workload; CPU restatement of the reference (NumPy + SciPy pocketfft, all cores); "
+                         "workload; CPU restatement of the reference (NumPy + SciPy pocketfft, all usable cores); "
                          "reference JVM unavailable"}
 
     # ---------------- reported extras (rank 0, N = 1; child processes, so that none of them can take the line with it) ------
@@ -699,31 +763,45 @@ def main():
         tlog("fusion leg done")
 
     if rank == 0:
+        extras = {"fusion_prestep": fusion_leg, "cufft_comparison": cufft_leg, "variants": variants,
+                  "configs2_one_gpu": config2_leg, "roofline_conv_pass_per_kernel": (conv_pass or {}).get("per_kernel"),
+                  "strong_scaling": strong, "configs4": configs4}
+        for k, v in extras.items():
+            if v is not None:
+                emit_extra(k, v)
+        cfg = config_dict(N)
+        cfg["fft_dims_zyx"] = [int(x) for x in info.fft_dims]
+        cfg["np_voxels_per_brick"] = np_brick
+        brief = lambda d, keys: None if not isinstance(d, dict) else {k: d.get(k) for k in keys if k in d}      # noqa: E731
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_string(N)[0],
-                       "fft_dims_zyx": list(info.fft_dims), "np_voxels_per_brick": np_brick,
-                       "parallelism": f"bricks {grid[2]}x{grid[1]}x{grid[0]} (x,y,z), halo exchange: {exchange_path}" if N > 1 else "single GPU",
-                       "l2": "working set per convolution (>= 256 MiB real + 370 MiB spectrum) exceeds the 126 MB L2"},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": None if e2e_value is None else {
                 "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / args.steps,
-                "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e,
-                "note": "whole call: create + upload all views from pinned memory + init + K iterations + mask + download psi"},
+                "d2h_bytes_per_step": d2h_bytes / args.steps, "seconds": t_e2e, "note": e2e_note},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "roofline_conv_pass": conv_pass,
+            "roofline_conv_pass": None if not conv_pass else {k: v for k, v in conv_pass.items() if k != "per_kernel"},
             "roofline_view_step": view_step if dom else None,
             "cpu_baseline": cpu,
-            "fusion_prestep": fusion_leg,
-            "cufft_comparison": cufft_leg,
-            "variants": variants,
-            "p2p_variant": p2p_variant,
-            "configs2_one_gpu": config2_leg,
+            "exchange_path": exchange_path,
+            "strong_scaling": brief(strong, ("value", "ms_per_iteration", "one_gpu_value", "one_gpu_ms_per_iteration",
+                                             "one_gpu_conv_pass_frac", "speedup_vs_one_gpu", "efficiency", "exchange", "error")),
+            "configs4": brief(configs4, ("value", "ms_per_iteration", "iterations", "peak_device_bytes_per_gpu", "exchange", "error")),
+            "configs2_one_gpu": brief(config2_leg, ("value", "ms_per_step", "ms_per_conv", "conv_pass_frac", "per_kernel_ms", "error", "skipped")),
+            "extras_printed_before_this_line": [k for k, v in extras.items() if v is not None],
         }
-        print(json.dumps(line))
+        text = json.dumps(line)
+        try:
+            d_ = os.path.join(ROOT, "gpurun_out")
+            if os.path.isdir(d_):
+                with open(os.path.join(d_, f"bench_full_N{N}.json"), "w") as f:
+                    f.write(json.dumps(dict(line, extras=extras)) + "\n")
+        except Exception:
+            pass
+        print(text)
     sys.stdout.flush()
     sys.stderr.flush()
     if dist is not None:

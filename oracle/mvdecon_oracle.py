@@ -116,8 +116,11 @@ def _halos(kshape: Sequence[int]) -> Tuple[List[int], List[int]]:
     return lo, hi
 
 
+WORKERS = -1        # pocketfft threads when a call does not say (-1 = os.cpu_count()); bench.py pins it to the usable cores
+
+
 def convolve(img: np.ndarray, kernel: np.ndarray, ext: int, value: float = 0.0,
-             dtype=np.float32, workers: int = -1) -> np.ndarray:
+             dtype=np.float32, workers: Optional[int] = None) -> np.ndarray:
     """Linear convolution of ``img`` (extended by rule ``ext``) with ``kernel`` whose origin is
     element ``dim//2``; output has ``img``'s shape.  True convolution, not correlation
     (``setComputeComplexConjugate(false)``, FD/MVDeconFFT.java:395,416,488,509).
@@ -126,6 +129,8 @@ def convolve(img: np.ndarray, kernel: np.ndarray, ext: int, value: float = 0.0,
     tree; see module docstring): pad by the kernel, real-to-complex FFT in ``dtype`` precision,
     multiply, inverse, crop.  The result is independent of the padded FFT size."""
     dtype = np.dtype(dtype)
+    if workers is None:
+        workers = WORKERS
     img = np.asarray(img, dtype=dtype)
     kernel = np.asarray(kernel, dtype=dtype)
     lo, hi = _halos(kernel.shape)

@@ -596,8 +596,10 @@ class _Deconvolution(Deconvolver):
     def getCurrentIteration(self) -> int:
         return self.i
 
-    def getPsi(self) -> np.ndarray:
-        return self._session.get_psi()
+    def getPsi(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """psi as a host array; `out` (optional, C-contiguous float32 of the volume's shape -- e.g. pinned memory) receives
+        the download instead of a freshly allocated array"""
+        return self._session.get_psi(out)
 
     def runIteration(self) -> None:
         r = self._session.run(1, stats=type(self).collectStatistics)

@@ -1,26 +1,24 @@
-"""Full-size multi-GPU brick runs, launched by torchrun (one rank per GPU):
+"""Full-size multi-GPU brick runs with oracle checks, launched by torchrun (one rank per GPU):
 
-  --config c3   BASELINE configs[2] geometry: world bricks of 512x512x256 (8 ranks = 1024x1024x512), 31^3 PSFs.  ONE full
-                iteration over --views views, then sub-bricks of psi that straddle brick faces, the brick corner in the
-                middle of the volume and a volume corner are recomputed by the oracle from a crop of the global inputs.
+  --config c3   BASELINE configs[2] geometry: bricks of 512x512x256 (8 ranks = 1024x1024x512), 31^3 PSFs, Optimization II.
+                ONE full iteration over --views views (default 3), then sub-bricks of psi that straddle brick faces, the
+                brick corner in the middle of the volume and a volume corner are recomputed by the oracle from a crop of
+                the global inputs.
   --config c5   BASELINE configs[4]: 8 views, 2048x2048x1024 over 8 ranks (bricks of 1024x1024x512), Efficient-Bayesian,
                 views handed over cell by cell with mvd_upload_region from device memory.  The first --check-steps
-                view-steps are verified against the oracle on straddling sub-bricks (the dependency cone of a whole
-                8-view iteration would need a 512^3 oracle run), then psi is reset and --iters iterations are timed.
+                view-steps (default 2) are verified against the oracle on the same kind of straddling sub-bricks (the
+                dependency cone of a whole 8-view iteration would need a 512^3 oracle run), then psi is reset and --iters
+                iterations (default 10) are timed.
 
-Inputs are hash noise of the global voxel index (spim_registration_b200/synthetic.py: hash_view), generated by every rank
-for its own brick on its own GPU and regenerated by rank 0 for any crop on the CPU, bit for bit.
+Set-up and timing are spim_registration_b200/bigvolume.py (shared with bench.py); this file adds the oracle.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 \
       tests/run_bricks_fullsize.py --config c5 --json gpurun_out/c5.json
-The oracle is only imported when a check is requested (--check-steps > 0); bench.py's configs[4] leg runs this file with
---check-steps 0, i.e. timing only.
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,12 +27,10 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-PSF = 31
 
-
-def regions_for(gshape, grid, brick, n=32):
-    """Sub-bricks (lo, n^3) to verify: the brick corner nearest the volume centre (straddles up to 8 bricks), one face
-    centre per split axis (straddles 2), and the volume corner (boundary rule + no neighbour)."""
+def regions_for(gshape, grid, brick, n):
+    """Sub-bricks (name, lo) to verify: the brick corner nearest the volume centre (straddles up to 8 bricks), one face
+    centre per split axis (straddles 2), and the volume corner (boundary rule, no neighbour)."""
     out = []
     c = [brick[d] * (grid[d] // 2) if grid[d] > 1 else gshape[d] // 2 for d in range(3)]
     out.append(("corner_of_bricks", [max(0, min(gshape[d] - n, c[d] - n // 2)) for d in range(3)]))
@@ -52,7 +48,7 @@ def main():
     ap.add_argument("--brick", type=int, nargs=3, default=None, help="per-rank brick (z y x)")
     ap.add_argument("--views", type=int, default=None)
     ap.add_argument("--iter-type", type=int, default=None)
-    ap.add_argument("--psf", type=int, default=PSF)
+    ap.add_argument("--psf", type=int, default=31)
     ap.add_argument("--check-steps", type=int, default=None, help="view-steps verified against the oracle (0 = none)")
     ap.add_argument("--iters", type=int, default=None, help="timed iterations after the check")
     ap.add_argument("--json", default=None)
@@ -66,71 +62,29 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from spim_registration_b200 import bricks, synthetic
+    from spim_registration_b200 import bigvolume, bricks, synthetic
     from spim_registration_b200.deconvolution import PSFTYPE
 
     if args.config == "c3":
-        brick, V, typ = (256, 512, 512), 3, int(PSFTYPE.OPTIMIZATION_II)
-        check_steps, iters = None, 0
+        brick, V, typ, check_steps, iters = (256, 512, 512), 3, int(PSFTYPE.OPTIMIZATION_II), None, 0
     elif args.config == "c5":
-        brick, V, typ = (512, 1024, 1024), 8, int(PSFTYPE.EFFICIENT_BAYESIAN)
-        check_steps, iters = 2, 10
+        brick, V, typ, check_steps, iters = (512, 1024, 1024), 8, int(PSFTYPE.EFFICIENT_BAYESIAN), 2, 10
     else:
-        brick, V, typ = (64, 64, 64), 3, int(PSFTYPE.EFFICIENT_BAYESIAN)
-        check_steps, iters = None, 0
-    if args.brick:
-        brick = tuple(args.brick)
-    if args.views:
-        V = args.views
-    if args.iter_type is not None:
-        typ = args.iter_type
-    if args.check_steps is not None:
-        check_steps = args.check_steps
-    if args.iters is not None:
-        iters = args.iters
+        brick, V, typ, check_steps, iters = (64, 64, 64), 3, int(PSFTYPE.EFFICIENT_BAYESIAN), None, 0
+    brick = tuple(args.brick) if args.brick else brick
+    V = args.views or V
+    typ = args.iter_type if args.iter_type is not None else typ
+    check_steps = args.check_steps if args.check_steps is not None else check_steps
+    iters = args.iters if args.iters is not None else iters
     if check_steps is None:
         check_steps = V                     # one full iteration
     ks = args.psf
-    grid = bricks.grid_for(world)
-    coords = bricks.rank_coords(rank, grid)
-    gshape = tuple(brick[d] * grid[d] for d in range(3))
-    origin = tuple(coords[d] * brick[d] for d in range(3))
-    psfs = synthetic.make_psfs(V, ks)
 
-    t_start = time.perf_counter()
-    free0, total = torch.cuda.mem_get_info()
-    r = bricks.BrickRunner(brick, V, typ, generation=2, lam=0.006, device=local, rank=rank, world=world, grid=grid,
-                           dist=dist if world > 1 else None)
+    r, meta = bigvolume.setup_runner(brick, V, typ, rank, world, local, dist if world > 1 else None, psf_size=ks)
     s = r.session
-    # views: generated on this GPU, cell by cell along z, and handed over with mvd_upload_region (device pointers)
-    from spim_registration_b200 import fusion
-    cell = max(1, min(brick[0], (1 << 27) // (brick[1] * brick[2])))      # <= 512 MiB per cell
-    for v in range(V):
-        for z0 in range(0, brick[0], cell):
-            ext = (min(cell, brick[0] - z0), brick[1], brick[2])
-            lo = (origin[0] + z0, origin[1], origin[2])
-            img, w = synthetic.hash_view(gshape, lo, ext, v, V, xp="torch", device=dev)
-            torch.cuda.synchronize()
-            s.upload_region_ptr(v, 0, img.data_ptr(), (z0, 0, 0), ext)
-            s.upload_region_ptr(v, 1, w.data_ptr(), (z0, 0, 0), ext)
-            del img, w
-        fusion.set_psf(s, v, psfs[v])
-    torch.cuda.empty_cache()
-    t_gen = time.perf_counter() - t_start
-    r.init()
-    t_init = time.perf_counter() - t_start - t_gen
-    info = s.info()
-    path = "p2p" if r.use_p2p else ("pack" if r.use_pack else ("slab" if world > 1 else "single"))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    result = {"config": args.config, "world": world, "grid_zyx": list(grid), "brick_zyx": list(brick), "global_zyx": list(gshape),
-              "views": V, "iteration_type": int(typ), "psf": ks, "fft_dims_zyx": [int(x) for x in info.fft_dims],
-              "exchange": path, "t_generate_upload_s": t_gen, "t_init_s": t_init, "avg": float(getattr(r, "avg", info.avg))}
+    psfs = meta.pop("psfs")
+    gshape, grid = tuple(meta["global_zyx"]), tuple(meta["grid_zyx"])
+    result = dict(meta, config=args.config)
 
     # ---------------- oracle check of the first view-steps on straddling sub-bricks ----------------------
     ok = True
@@ -139,92 +93,52 @@ def main():
         for v in range(check_steps):          # view-steps in view order, exactly BrickRunner._iteration
             if world > 1:
                 r.exchange(0)
-                s.view_phase(v, 0)
+            s.view_phase(v, 0)
+            if world > 1:
                 r.exchange(1)
-                s.view_phase(v, 1)
-            else:
-                s.view_phase(v, 0)
-                s.view_phase(v, 1)
-        full_iteration = (check_steps == V)
-        if full_iteration:
+            s.view_phase(v, 1)
+        if check_steps == V:
             r.finish()
         s.sync()
-        ptr, dims, org = s.device_buffer(0)
-        psi_t = r._wrap(ptr, dims) if world > 1 else None
-        if psi_t is None:
-            psi_host = s.get_psi()
         checks = []
         for name, lo in regions_for(gshape, grid, brick, n):
-            # my part of the region -> a zero n^3 box, summed over ranks (supports are disjoint)
-            box = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
-            a = [max(lo[d], origin[d]) for d in range(3)]
-            b = [min(lo[d] + n, origin[d] + brick[d]) for d in range(3)]
-            if all(b[d] > a[d] for d in range(3)):
-                dst = tuple(slice(a[d] - lo[d], b[d] - lo[d]) for d in range(3))
-                if psi_t is not None:
-                    src = tuple(slice(a[d] - origin[d] + org[d], b[d] - origin[d] + org[d]) for d in range(3))
-                    box[dst] = psi_t[src]
-                else:
-                    src = tuple(slice(a[d] - origin[d], b[d] - origin[d]) for d in range(3))
-                    box[dst] = torch.from_numpy(np.ascontiguousarray(psi_host[src])).to(dev)
-            if world > 1:
-                dist.all_reduce(box)
+            box = bigvolume.gather_region(r, meta, lo, n, dist if world > 1 else None)
             if rank == 0:
                 from oracle import mvdecon_oracle as O
                 h = (ks // 2) * 2 * check_steps          # every view-step reaches 2 * (k // 2) voxels further
                 clo = [max(0, lo[d] - h) for d in range(3)]
                 chi = [min(gshape[d], lo[d] + n + h) for d in range(3)]
                 ext = [chi[d] - clo[d] for d in range(3)]
-                imgs, ws = [], []
-                for v in range(check_steps):
-                    im, w = synthetic.hash_view(gshape, clo, ext, v, V, xp="numpy")
-                    imgs.append(im)
-                    ws.append(w)
                 k1, k2 = O.init_kernels(psfs, typ)
                 p = O.DeconParams(iteration_type=typ, lam=0.006, gen=O.GEN2)
-                psi = np.full(ext, np.float32(result["avg"]), np.float32)
+                psi = np.full(ext, np.float32(meta["avg"]), np.float32)
                 for v in range(check_steps):
-                    psi, _, _ = O.view_step(psi, imgs[v], ws[v], k1[v], k2[v], p)
+                    im, w = synthetic.hash_view(gshape, clo, ext, v, V, xp="numpy")
+                    psi, _, _ = O.view_step(psi, im, w, k1[v], k2[v], p)
                 rs = tuple(slice(lo[d] - clo[d], lo[d] - clo[d] + n) for d in range(3))
-                per, l2 = O.parity_errors(box.cpu().numpy(), psi[rs])
+                per, l2 = O.parity_errors(box, psi[rs])
                 good = bool(per <= 1e-3 and l2 <= 1e-4)
                 ok = ok and good
-                checks.append({"region": name, "lo_zyx": [int(x) for x in lo], "size": n, "per_voxel": float(per), "rel_l2": float(l2), "ok": good})
+                checks.append({"region": name, "lo_zyx": [int(x) for x in lo], "size": n, "per_voxel": float(per),
+                               "rel_l2": float(l2), "ok": good})
                 print(f"[fullsize {args.config}] {name} at {lo}: per-voxel {per:.3e} L2 {l2:.3e} {'ok' if good else 'FAIL'}", flush=True)
         result["oracle_check"] = {"view_steps": check_steps, "regions": checks,
                                   "tolerance": "per-voxel <= 1e-3, relative L2 <= 1e-4 (BASELINE north_star)"}
-        # back to the initial estimate for the timed part
-        if iters > 0:
-            s.set_avg(result["avg"], float(getattr(r, "osem", 1.0)))
+        if iters > 0:                           # back to the initial estimate for the timed part
+            s.set_avg(meta["avg"], float(getattr(r, "osem", 1.0)))
             r._p2p_last = None
-            barrier()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
 
     # ---------------- timed iterations --------------------------------------------------------------------
     if iters > 0:
-        stream = torch.cuda.ExternalStream(s.stream(), device=dev)
-        r.run(1)                                # warm-up (captures the CUDA graph in brick mode)
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        r.run(iters)
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
-        nvox = int(np.prod(gshape))
-        result.update({"iterations": iters, "ms_per_iteration": ms / iters,
-                       "value": nvox * V * iters / (ms * 1e-3), "unit": "voxel-view-iters/s",
+        ms = bigvolume.time_iterations(r, iters, dist if world > 1 else None)
+        result.update({"iterations": iters, "ms_per_iteration": ms,
+                       "value": int(np.prod(gshape)) * V / (ms * 1e-3), "unit": "voxel-view-iters/s",
                        "timing": "CUDA events on the session stream, max over ranks, one warm-up iteration before"})
-    free1, _ = torch.cuda.mem_get_info()
-    used = torch.tensor([float(total - free1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(used, op=dist.ReduceOp.MAX)
-    result["peak_device_bytes_per_gpu"] = float(used.item())
-    result["session_device_bytes"] = int(info.device_bytes)
-    result["hbm_total_bytes"] = int(total)
+    result["peak_device_bytes_per_gpu"] = bigvolume.peak_device_bytes(dist if world > 1 else None, world)
+    result["hbm_total_bytes"] = int(torch.cuda.mem_get_info()[1])
     result["ok"] = bool(ok)
     if rank == 0:
         line = json.dumps(result)
