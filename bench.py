@@ -50,6 +50,17 @@ METRIC = "MV deconvolution voxel-view-iters/s"      # BASELINE.json: "MV deconvo
 UNIT = "voxel-view-iters/s"
 KERNEL_NAMES = ["x_fwd_r2c", "y_fwd", "z_fwd_mul_inv", "y_inv", "x_inv_c2r_epilogue"]
 KERNEL_ALG_FACTOR = [8, 8, 12, 8, 8]   # algorithmic bytes per launch = factor * Np
+# the library times the x-inverse launches per epilogue: timer slot 4 = ratio (conv1), slot 7 = update (conv2)
+XINV_SLOTS = {"x_inv_c2r_ratio": 4, "x_inv_c2r_update": 7}
+
+
+def merge_xinv(kms, kcnt):
+    """per-kernel (ms, launches) lists of the library -> the five sweep kernels (x-inverse = both epilogues together) plus
+    the two epilogues separately"""
+    kms, kcnt = list(kms), list(kcnt)
+    sep = {n: (kms[i] / kcnt[i]) for n, i in XINV_SLOTS.items() if kcnt[i] > 0}
+    kms[4], kcnt[4] = kms[4] + kms[7], kcnt[4] + kcnt[7]
+    return kms, kcnt, sep
 # the x-inverse launch also carries the fused pointwise traffic of SURVEY 8d (16 B per voxel-view-iteration):
 # ratio epilogue reads img (4 N), update epilogue reads weight + psi (8 N); their writes are the sweep's own write
 XINV_POINTWISE_BYTES_PER_VOXEL = 6     # average of the two launches of a view-step
@@ -307,7 +318,7 @@ def variant_child():
         dt = time.perf_counter() - t0
         s.set_timing(True)
         s.run(2, stats=False)
-        kms, kcnt = s.get_timing()
+        kms, kcnt, xinv_sep = merge_xinv(*s.get_timing())
         info = s.info()
         sample = s.get_psi()[::8, ::16, ::16].astype(np.float64)
         psi_ok = bool(np.isfinite(sample).all())
@@ -316,7 +327,7 @@ def variant_child():
     gbs = 44 * int(info.np_voxels) / (ms_conv * 1e-3) / 1e9 if ms_conv > 0 else None
     print(json.dumps({"value": int(np.prod(BRICK)) * VIEWS * iters / dt, "ms_per_step": 1e3 * dt / iters,
                       "ms_per_conv": ms_conv, "conv_pass_gbs": gbs, "conv_pass_frac": (gbs / peaks()[0]) if gbs else None,
-                      "per_kernel_ms": per, "fft_dims_zyx": list(info.fft_dims), "finite": psi_ok,
+                      "per_kernel_ms": per, "x_inv_by_epilogue_ms": xinv_sep, "fft_dims_zyx": list(info.fft_dims), "finite": psi_ok,
                       "psi_checksum": float(sample.sum())}))
 
 
@@ -588,7 +599,7 @@ def main():
     runner.session.set_timing(True)
     runner.use_graph = False          # brick mode: eager launches here, so that every kernel is bracketed by its events
     runner.run(max(2, min(args.steps, 5)))
-    kms, kcnt = runner.session.get_timing()
+    kms, kcnt, xinv_sep = merge_xinv(*runner.session.get_timing())
     runner.session.set_timing(False)
     peak, peak_src = peaks()
     per_kernel = {}
@@ -615,7 +626,7 @@ def main():
                     "alg_bytes_per_launch": per_kernel[dom]["alg_bytes"], "avg_ms": per_kernel[dom]["avg_ms"]}
         tot_ms = sum(per_kernel[k]["avg_ms"] for k in per_kernel)
         a2 = 44 * np_brick / (tot_ms * 1e-3) / 1e9
-        conv_pass = {"achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "ms_per_conv": tot_ms,
+        conv_pass = {"achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "ms_per_conv": tot_ms, "x_inv_by_epilogue_ms": xinv_sep,
                      "alg_bytes": 44 * np_brick, "per_kernel": per_kernel,
                      "note": "44*Np per FFT-convolution pass (SURVEY 8d), Np = prod(n + k - 1); sum of the five kernels' average durations"}
         # whole view-step: two passes + 16 B/voxel pointwise = B_vvi * N

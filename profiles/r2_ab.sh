@@ -15,7 +15,7 @@ run() {  # name, size args, env...
     python - "$name" "$line" <<'PY'
 import json, sys
 d = json.loads(sys.argv[2])
-print(sys.argv[1], "frac", d.get("conv_pass_frac"), {k: round(v, 4) for k, v in (d.get("per_kernel_ms") or {}).items()}, d.get("psi_checksum"), d.get("error"))
+print(sys.argv[1], "frac", round(d.get("conv_pass_frac") or 0, 4), {k[:6]: round(v, 4) for k, v in (d.get("per_kernel_ms") or {}).items()}, {k[10:]: round(v, 4) for k, v in (d.get("x_inv_by_epilogue_ms") or {}).items()}, d.get("psi_checksum"), d.get("error"))
 PY
 }
 C1="--views 7 --brick 256 512 512"

@@ -17,7 +17,8 @@ namespace spim {
 // host-side launch counters (mvd_debug_counter): [0] column passes launched with narrow tiles
 inline std::atomic<long long>& debug_counter(int i) { static std::atomic<long long> c[4]; return c[i & 3]; }
 
-enum KernelId { K_XFWD = 0, K_YFWD, K_ZMID, K_YINV, K_XINV, K_ZFWD, K_MISC, K_COUNT };
+// x-inverse launches are timed per epilogue: K_XINV = ratio (conv1), K_XINV_UPDATE = update (conv2), K_XINV_STORE = plain store
+enum KernelId { K_XFWD = 0, K_YFWD, K_ZMID, K_YINV, K_XINV, K_ZFWD, K_XINV_STORE, K_XINV_UPDATE, K_COUNT };
 
 // ------------------------------------------------------------------------------------------
 // stage planning
@@ -166,10 +167,15 @@ inline int use_serpentine() { return env_int_now("SPIM_SERPENTINE", 0); }
 inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
 
 // per-axis override for A/B runs: SPIM_COLP_Y / SPIM_COLP_Z (e.g. the TMA pipeline for the 72 KB y tiles only)
+// Defaults (measured on B200, profiles/): the y passes (72 KB tiles at the bench size) run the persistent TMA / mbarrier
+// pipeline, the z pass (36 KB tiles, five blocks per SM) the one-shot cp.async staging.
 inline int use_colp_for(int axis) {
     static int y = env_int("SPIM_COLP_Y", -1), z = env_int("SPIM_COLP_Z", -1);
+    static int all = env_int("SPIM_COLP", -1);
     const int v = axis == 1 ? y : z;
-    return v >= 0 ? v : use_colp();
+    if (v >= 0) return v;
+    if (all >= 0) return all;
+    return axis == 1 ? 3 : 2;
 }
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
@@ -381,7 +387,9 @@ public:
             q.LS = (std::max(p.sx, p.ox + P[2]) + 3) & ~3;
             q.row_bytes = (unsigned)p.sx * 4u;
             const size_t slot_bytes = (size_t)TC * q.LS * sizeof(float);
-            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t);
+            const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
+            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
+                                 (size_t)std::max(1, fx_.n) * sizeof(int2);
             const size_t lim = rt::max_smem();
             // blocks per SM / slots per block: three blocks with one slot each where that fits (tiles up to ~36 KB), else two
             // blocks with one slot, else one block with as many slots as fit
@@ -392,8 +400,8 @@ public:
             const size_t sm = fixed + nslot * slot_bytes;
             if (sm + 1024 <= lim) {
                 bps = (int)std::min<size_t>(3, lim / (sm + 1024));
-                const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
                 q.fix = fx_.d; q.nfix = fx_.n;
+                q.magic_nfix = magic_for(std::max(1, fx_.n));
                 q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
                 q.const_row = const_row(p.sx, q.cval, st);
                 q.nslot = nslot;
@@ -429,10 +437,12 @@ public:
         // (FFT lengths above ~880, e.g. the 1080-long axes of a 1024^2 x 512 volume on one GPU); SPIM_COL_NARROW=0/1 forces
         const size_t lim = rt::max_smem();
         const int narrow_env = env_int_now("SPIM_COL_NARROW", -1);
-        const bool narrow = use_colp_for(axis) == 2 &&
+        int colp = use_colp_for(axis);
+        // the TMA pipeline keeps three tiles per block: axes too long for that (FFT lengths above ~590) fall back to cp.async staging
+        if (colp == 3 && 3 * ((size_t)Pa * TC * sizeof(float2)) + 64 > lim) colp = 2;
+        const bool narrow = colp == 2 &&
                             (narrow_env >= 0 ? narrow_env != 0 : 2 * ((size_t)Pa * TC * sizeof(float2) + 1024) > lim);
         const int tcols = narrow ? TC / 2 : TC;
-        const int colp = use_colp_for(axis);
         p.ntx = pitch / tcols;
         if (axis == 1) { p.row_stride = pitch; p.outer_stride = (long long)pitch * P[1]; }
         else { p.row_stride = (long long)pitch * P[1]; p.outer_stride = pitch; }
@@ -548,6 +558,7 @@ public:
         auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; };
         p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);
         const long long grid = (p.nlines + TC - 1) / TC;
+        const int xinv_id = e.epi == EPI_UPDATE ? K_XINV_UPDATE : (e.epi == EPI_RATIO ? K_XINV : K_XINV_STORE);
         p.nblocks = (int)grid;
         p.reverse = (use_serpentine() && e.epi != EPI_STORE && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
@@ -569,7 +580,7 @@ public:
                 q.nslot = nslot;
                 q.ntiles = (int)grid;
                 const int T = env_int_now("SPIM_THREADS_XINVP", 0);
-                if (timer) timer->begin(K_XINV, st);
+                if (timer) timer->begin(xinv_id, st);
                 const bool hot = p.fast_epilogue && !e.exact_tikhonov && e.epi != EPI_STORE;
                 if (hot && bps >= 3) {
                     q.nctas = (int)std::min<long long>(grid, 3LL * rt::sm_count());
@@ -595,11 +606,11 @@ public:
                     else if (p.fast_epilogue) rt::launch<XInvPUpdateFast, 256, 2>(q, q.nctas, T2, sm, st);
                     else rt::launch<XInvPUpdateIeee, 256, 2>(q, q.nctas, T2, sm, st);
                 }
-                if (timer) timer->end(K_XINV, st);
+                if (timer) timer->end(xinv_id, st);
                 return;
             }
         }
-        if (timer) timer->begin(K_XINV, st);
+        if (timer) timer->begin(xinv_id, st);
         const int T = threads_xinv();
         // 36 KB tiles: six 128-thread blocks fit per SM as long as the ratio kernel stays within 85 registers
         const bool cap6 = T <= 128 && smem <= 37 * 1024;
@@ -632,7 +643,7 @@ public:
             else rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
         }
         else rt::launch<XInvT<EPI_UPDATE, MATH_IEEE>>(p, grid, T, smem, st);
-        if (timer) timer->end(K_XINV, st);
+        if (timer) timer->end(xinv_id, st);
     }
 
     // spectrum of a (host) kernel, pre-scaled by 1/(4 Px Py Pz), in the layout the mid pass expects

@@ -956,6 +956,7 @@ struct XFwdTParams {
     float cval;                // that constant
     const int2* fix;           // fix-up list: staging[fix.x] = fix.y >= 0 ? staging[fix.y] : (fix.y == -1 ? 0 : cval)
     int nfix;
+    uint32_t magic_nfix;       // for item / nfix
 };
 
 // source row of padded line l (nullptr beyond the last line) and its destination offset in the spectrum
@@ -1046,7 +1047,8 @@ struct XFwdT {
         float* stg = reinterpret_cast<float*>(smem2 + (size_t)N2 * TC);
         long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * q.LS);     // [nslot][TC]
         long long* dcur = dsto + MAXSLOT * TC;                                                 // [TC], the tile in work
-        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC);                               // [nslot]
+        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC);                               // [MAXSLOT]
+        int2* fixs = reinterpret_cast<int2*>(full + MAXSLOT);                                  // [nfix], the fix-up list
         const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
 #if !defined(SPIM_HOST_EMU)
         if (threadIdx.x == 0) {
@@ -1056,6 +1058,7 @@ struct XFwdT {
         __syncthreads();
 #endif
         for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, bid + j * q.nctas, j, stg, dsto, full);
+        SPIM_FOR_ITEMS(j, q.nfix) fixs[j] = spim_ldg(q.fix + j);
         SPIM_BARRIER();
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
@@ -1067,10 +1070,10 @@ struct XFwdT {
 #endif
             // fix-ups: halo before the image, out-of-bounds values, zero gap
             SPIM_FOR_ITEMS(it, TC * q.nfix) {
-                const int b = it / q.nfix;
+                const int b = q.nfix > 1 ? fastdiv(it, q.magic_nfix) : it;
                 const int j = it - b * q.nfix;
                 if (dsto[slot * TC + b] < 0) continue;
-                const int2 f = spim_ldg(q.fix + j);
+                const int2 f = fixs[j];
                 float* ln = sl + b * q.LS;
                 ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
             }
@@ -1113,6 +1116,28 @@ struct HaloFuse {
 };
 constexpr int kFuseCombos = 4;         // (dz, dy) in {0, dzs} x {0, dys} per line
 constexpr int kFuseSlots = 3;          // per combo: whole line, x-low part, x-high part
+// bytes of shared memory a FUSE instantiation needs behind its other arrays: [TC][kFuseCombos][kFuseSlots] pointers + [TC] counts
+constexpr size_t kFuseSmemBytes = TC * kFuseCombos * kFuseSlots * sizeof(float2*) + TC * sizeof(int);
+
+// where line (z, y) of the brick goes besides the local buffer: for (dz, dy) in {0, dzs} x {0, dys} the whole line (except
+// (0, 0)), its first cells for the x neighbour below and its last cells for the one above.  d_o = offset of the line's first
+// voxel in the local buffer; f = this line's [kFuseCombos][kFuseSlots] pointers.  Returns the number of combos in use.
+SPIM_DEV int fuse_line_targets(const HaloFuse& h, int z, int y, long long d_o, float2** f) {
+    const int dzs = (z < h.whi[0] && (h.has_lo & 1)) ? -1 : ((z >= h.n[0] - h.wlo[0] && (h.has_hi & 1)) ? 1 : 0);
+    const int dys = (y < h.whi[1] && (h.has_lo & 2)) ? -1 : ((y >= h.n[1] - h.wlo[1] && (h.has_hi & 2)) ? 1 : 0);
+    int nc = 0;
+    for (int iz = 0; iz < (dzs ? 2 : 1); ++iz)
+        for (int iy = 0; iy < (dys ? 2 : 1); ++iy) {
+            const int cz = iz ? dzs : 0, cy = iy ? dys : 0;
+            const int dir = (cz + 1) * 9 + (cy + 1) * 3 + 1;
+            f[0] = (cz || cy) ? reinterpret_cast<float2*>(h.peer[dir] + (d_o - h.shift[dir])) : nullptr;
+            f[1] = ((h.has_lo & 4) && h.peer[dir - 1]) ? reinterpret_cast<float2*>(h.peer[dir - 1] + (d_o - h.shift[dir - 1])) : nullptr;
+            f[2] = ((h.has_hi & 4) && h.peer[dir + 1]) ? reinterpret_cast<float2*>(h.peer[dir + 1] + (d_o - h.shift[dir + 1])) : nullptr;
+            f += kFuseSlots;
+            ++nc;
+        }
+    return nc;
+}
 
 struct XInvParams {
     const HaloFuse* fuse;      // device pointer, FUSE instantiations only
@@ -1391,9 +1416,8 @@ SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* 
 // R0MAX: largest radix the register-resident last stage (plan.radix[0]) is compiled for.  The epilogue keeps 8 R floats per
 // item in registers (spectrum row, two prefetched inputs, twiddles), so an instantiation for R0MAX = 5 is much leaner than
 // the general one; the host only selects it when the x plan starts with a radix <= R0MAX (SPIM_XPLAN_ASC orders it so).
-// bytes of shared memory a FUSE instantiation needs behind the tile and the three line-offset arrays
-constexpr size_t kFuseSmemBytes = TC * kFuseCombos * kFuseSlots * sizeof(float2*) + TC * sizeof(int);
-
+// FUSE: brick mode with connected peers -- the epilogue also stores every voxel a neighbour's halo needs straight into that
+// neighbour's buffer (HaloFuse above); the host selects it only when the vectorised epilogue applies.
 template <int EPI, int MATH, int R0MAX = 16, bool FUSE = false>
 struct XInvT {
     typedef XInvParams Params;
@@ -1419,21 +1443,7 @@ struct XInvT {
                 so = ((long long)z * p.Py + y) * (long long)p.pitch;
                 d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
                 a_o = ((long long)z * p.ny + y) * (long long)p.nx;
-                if (FUSE) {
-                    const HaloFuse& h = *p.fuse;
-                    const int dzs = (z < h.whi[0] && (h.has_lo & 1)) ? -1 : ((z >= h.n[0] - h.wlo[0] && (h.has_hi & 1)) ? 1 : 0);
-                    const int dys = (y < h.whi[1] && (h.has_lo & 2)) ? -1 : ((y >= h.n[1] - h.wlo[1] && (h.has_hi & 2)) ? 1 : 0);
-                    for (int iz = 0; iz < (dzs ? 2 : 1); ++iz)
-                        for (int iy = 0; iy < (dys ? 2 : 1); ++iy) {
-                            const int cz = iz ? dzs : 0, cy = iy ? dys : 0;
-                            const int dir = (cz + 1) * 9 + (cy + 1) * 3 + 1;
-                            float2** f = fptr + (b * kFuseCombos + nc) * kFuseSlots;
-                            f[0] = (cz || cy) ? reinterpret_cast<float2*>(h.peer[dir] + (d_o - h.shift[dir])) : nullptr;
-                            f[1] = ((h.has_lo & 4) && h.peer[dir - 1]) ? reinterpret_cast<float2*>(h.peer[dir - 1] + (d_o - h.shift[dir - 1])) : nullptr;
-                            f[2] = ((h.has_hi & 4) && h.peer[dir + 1]) ? reinterpret_cast<float2*>(h.peer[dir + 1] + (d_o - h.shift[dir + 1])) : nullptr;
-                            ++nc;
-                        }
-                }
+                if (FUSE) nc = fuse_line_targets(*p.fuse, z, y, d_o, fptr + b * kFuseCombos * kFuseSlots);
             }
             srcoff[b] = so; dstoff[b] = d_o; auxoff[b] = a_o;
             if (FUSE) fnc[b] = nc;
@@ -1446,7 +1456,7 @@ struct XInvT {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        if (FUSE) {        // the host only selects a FUSE instantiation when the vectorised path applies
+        if (FUSE) {
             const int nlo2 = (p.fuse->whi[2] + 1) >> 1;              // pairs (2n, 2n+1) that reach into x < whi
             const int nhi2 = (p.nx - p.fuse->wlo[2]) >> 1;           // ... into x >= nx - wlo
             SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
@@ -1499,7 +1509,9 @@ SPIM_DEV void xinvp_presplit(const XInvParams& p, float4* tile, const float2* st
     }
 }
 
-template <int EPI, int MATH, int R0MAX = 16>
+// FUSE: brick mode with connected peers -- the epilogue also stores every voxel a neighbour's halo needs straight into that
+// neighbour's buffer (HaloFuse above); the host selects it only when the vectorised epilogue applies
+template <int EPI, int MATH, int R0MAX = 16, bool FUSE = false>
 struct XInvP {
     typedef XInvPParams Params;
     static constexpr bool kEmuThreads = true;
@@ -1546,7 +1558,7 @@ struct XInvP {
     // stage-0 twiddles once were for M > 1, keeps its registers live around the whole persistent loop -- for every radix path
     // at once, 255 registers and spills instead of 80.)
     SPIM_DEV static void tile_body(const Params& q, int t, int nxt, int slot, unsigned parity, float2* tile2, float2* stg,
-                                     long long* dstoff, long long* auxoff, uint64_t* full, EpiAcc& acc_out) {
+                                     long long* dstoff, long long* auxoff, uint64_t* full, EpiAcc& acc_out, float2** fptr, int* fnc) {
         const XInvParams& p = q.x;
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
@@ -1557,13 +1569,16 @@ struct XInvP {
         SPIM_FOR_ITEMS(b, TC) {
             const long long l = (long long)t * TC + b;
             long long d_o = -1, a_o = -1;
+            int nc = 0;
             if (l < p.nlines) {
                 const int z = (int)(l / p.ny);
                 const int y = (int)(l - (long long)z * p.ny);
                 d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
                 a_o = ((long long)z * p.ny + y) * (long long)p.nx;
+                if (FUSE) nc = fuse_line_targets(*p.fuse, z, y, d_o, fptr + b * kFuseCombos * kFuseSlots);
             }
             dstoff[b] = d_o; auxoff[b] = a_o;
+            if (FUSE) fnc[b] = nc;
         }
 #if !defined(SPIM_HOST_EMU)
         mbar_wait(full + slot, parity);
@@ -1579,7 +1594,12 @@ struct XInvP {
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
-        if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        if (FUSE) {
+            const int nlo2 = (p.fuse->whi[2] + 1) >> 1;              // pairs (2n, 2n+1) that reach into x < whi
+            const int nhi2 = (p.nx - p.fuse->wlo[2]) >> 1;           // ... into x >= nx - wlo
+            SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
+        }
+        else if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
         else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
         if (EPI == EPI_UPDATE) { acc_out.sum += acc.sum; acc_out.mx = fmaxf(acc_out.mx, acc.mx); }
         SPIM_BARRIER();            // the tile and the offset arrays are free for the next round
@@ -1592,6 +1612,8 @@ struct XInvP {
         long long* dstoff = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * p.pitch);
         long long* auxoff = dstoff + TC;
         uint64_t* full = reinterpret_cast<uint64_t*>(auxoff + TC);
+        float2** fptr = reinterpret_cast<float2**>(full + MAXSLOT);                // FUSE: [TC][kFuseCombos][kFuseSlots]
+        int* fnc = reinterpret_cast<int*>(fptr + TC * kFuseCombos * kFuseSlots);   // FUSE: combos in use per line
         const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
 #if !defined(SPIM_HOST_EMU)
         if (threadIdx.x == 0) {
@@ -1611,7 +1633,7 @@ struct XInvP {
         for (int i = 0; i < ntl; ++i) {
             const int slot = i % q.nslot;
             const int nxt = (i + q.nslot < ntl) ? tile_at(i + q.nslot) : -1;
-            tile_body(q, tile_at(i), nxt, slot, (unsigned)((i / q.nslot) & 1), tile2, stg, dstoff, auxoff, full, acc);
+            tile_body(q, tile_at(i), nxt, slot, (unsigned)((i / q.nslot) & 1), tile2, stg, dstoff, auxoff, full, acc, fptr, fnc);
         }
 #undef tile_at
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);

@@ -133,10 +133,10 @@ inline int sm_count() {
     return v;
 }
 
-// Programmatic dependent launch (opt-in, SPIM_PDL=1): every block first lets the NEXT kernel of the stream start launching
+// Programmatic dependent launch (the default; SPIM_PDL=0 launches plainly): every block first lets the NEXT kernel of the stream start launching
 // and then waits for the PREVIOUS kernel to complete and flush.  The next kernel's blocks become resident in the slots the
 // last wave of this one frees, parked at their own wait, so the tail of one sweep and the ramp-up of the next overlap instead
-// of adding up.  Both instructions are no-ops for a kernel launched without the attribute (the default).
+// of adding up.  Both instructions are no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) kernel_entry_capped(const __grid_c
 }
 
 inline bool use_pdl() {
-    static int v = [] { const char* e = getenv("SPIM_PDL"); return (e && *e == '1') ? 1 : 0; }();
+    static int v = [] { const char* e = getenv("SPIM_PDL"); return (e && *e == '0') ? 0 : 1; }();
     return v != 0;
 }
 template <class K, class P>

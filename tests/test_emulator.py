@@ -146,8 +146,14 @@ def test_limits_and_argument_validation(emu_lib):
         s.init()                                                     # x axis: Px/2 ~ 1512 rows of 128 B -> fits in 227 KB
     with Session((1, 2000, 4), 1, 3, lib=emu_lib) as s:
         s.set_view(0, np.ones((1, 2000, 4), np.float32), None, np.ones((1, 3, 1), np.float32))
+        s.init()                                                     # y axis: 2016 rows -> narrow (8-column) tiles of 129 KB
+        s.run(1, stats=False)
+        want = 2.0 / (1.0 + np.sqrt(1.0 + 2 * 0.006))               # all-ones views: psi stays 1 up to the Tikhonov step
+        assert np.abs(s.get_psi() - want).max() < 1e-5
+    with Session((1, 4000, 4), 1, 3, lib=emu_lib) as s:
+        s.set_view(0, np.ones((1, 4000, 4), np.float32), None, np.ones((1, 3, 1), np.float32))
         with pytest.raises(native.NativeError, match="too long"):
-            s.init()
+            s.init()                                                 # not even a narrow tile fits: refused with a message
     # struct_size guards the ABI
     p = native.MvdParams()
     emu_lib.mvd_params_default(ctypes.byref(p))
