@@ -89,11 +89,8 @@ struct FftPlanHost {
     std::vector<int> radices;
     std::vector<unsigned short> pos;   // pos[k]: row that holds frequency k after the DIF stages
 
-    // ascending: smallest radix first.  Stage 0 is the register-resident stage of the x kernels (first from global memory in
-    // x-forward, last with the fused epilogue in x-inverse); a small radix there keeps the epilogue's per-item state small
-    void create(int n, bool ascending = false) {
+    void create(int n) {
         if (!plan_radices(n, radices)) throw rt::Error("unsupported FFT length " + std::to_string(n));
-        if (ascending) std::reverse(radices.begin(), radices.end());
         memset(&dev, 0, sizeof(dev));
         dev.n = n;
         dev.nstages = (int)radices.size();
@@ -136,46 +133,24 @@ struct FftPlanHost {
     void destroy() { rt::dfree(d_tw); d_tw = nullptr; }
 };
 
-// block sizes (tunable through the environment for experiments; defaults chosen from ncu runs)
+// The few switches that remain after the round-2 A/B runs (profiles/README.md has the numbers behind every default):
+//   SPIM_XFWD_TMA=0   x-forward from the plain-load kernel (XFwd) instead of the TMA-fed pipeline (XFwdT)
+//   SPIM_COLP=0|2|3   column passes: 0 first stage straight from global memory, 2 one-shot cp.async staging, 3 persistent
+//                     TMA / mbarrier pipeline; unset = 3 for large tiles (y passes of the bench volume), 2 for small ones
+//   SPIM_COL_NARROW=0|1  force 16- / 8-column tiles (unset: narrow where a 16-column tile leaves one block per SM)
+//   SPIM_FAST_EPI=0|1    override mvd_params.fast_epilogue
+//   SPIM_PDL=0           plain launches instead of programmatic dependent launch (runtime.h)
 inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
     const int r = atoi(v);
     return (r >= 0 && r <= 1024) ? r : dflt;
 }
-// the same, read on every call (switches the tests flip inside one process)
-inline int env_int_now(const char* name, int dflt) { return env_int(name, dflt); }
-inline int threads_xfwd() { static int t = env_int("SPIM_THREADS_XFWD", 192); return t; }
-inline int threads_col() { static int t = env_int("SPIM_THREADS_COL", 128); return t; }
 // Column tiles larger than a third of the shared memory leave room for only two / one block per SM: scale the block
-// so that ~384 threads stay resident (2 x 192, 1 x 384).  SPIM_THREADS_COL, when set, wins.
+// so that ~384 threads stay resident (2 x 192, 1 x 384).
 inline int threads_col_for(size_t smem_bytes, size_t smem_limit) {
-    static int user = env_int("SPIM_THREADS_COL", 0);
-    if (user > 0) return user;
     const size_t blocks = smem_limit / (smem_bytes + 1024);   // 1 KB per block is reserved by the driver
     return blocks >= 3 ? 128 : (blocks == 2 ? 192 : 384);
-}
-inline int threads_xinv() { static int t = env_int("SPIM_THREADS_XINV", 128); return t; }
-inline int threads_colt() { static int t = env_int("SPIM_THREADS_COLT", 480); return t; }
-// SPIM_REGCAP (experiments): 1 = column passes from an instantiation capped at 85 registers (3 x 256 threads per SM),
-// 2 = y tiles with 3 x 192 threads (<= 113 registers), 3 = z tiles with 6 x 128 threads (<= 85 registers)
-inline int use_regcap() { static int t = env_int("SPIM_REGCAP", 0); return t; }
-// SPIM_SERPENTINE=1 (experiment): the y-forward pass and the x-inverse pass walk their tiles from the last to the first, so
-// that each starts on the ~100 MB its predecessor (x-forward / y-inverse, which end at the high planes) has just left in
-// the 126 MB L2, and the next x-forward pass (ascending) starts on what the x-inverse pass wrote last
-inline int use_serpentine() { return env_int_now("SPIM_SERPENTINE", 0); }
-inline int use_colp() { static int t = env_int("SPIM_COLP", 2); return t; }   // 0 direct loads in the first stage, 2 one-shot cp.async tile staging (default), 3 experimental TMA pipeline, 4 experimental warp-private columns
-
-// per-axis override for A/B runs: SPIM_COLP_Y / SPIM_COLP_Z (e.g. the TMA pipeline for the 72 KB y tiles only)
-// Defaults (measured on B200, profiles/): the y passes (72 KB tiles at the bench size) run the persistent TMA / mbarrier
-// pipeline, the z pass (36 KB tiles, five blocks per SM) the one-shot cp.async staging.
-inline int use_colp_for(int axis) {
-    static int y = env_int("SPIM_COLP_Y", -1), z = env_int("SPIM_COLP_Z", -1);
-    static int all = env_int("SPIM_COLP", -1);
-    const int v = axis == 1 ? y : z;
-    if (v >= 0) return v;
-    if (all >= 0) return all;
-    return axis == 1 ? 3 : 2;
 }
 
 inline uint32_t magic_for(int d) { return d > 1 ? (uint32_t)((0x100000000ull / (uint64_t)d) + 1ull) : 0u; }
@@ -241,7 +216,7 @@ public:
         }
         N2 = P[2] / 2;
         pitch = ((N2 + 1 + TC - 1) / TC) * TC;
-        fx.create(N2, env_int_now("SPIM_XPLAN_ASC", 0) != 0); fy.create(P[1]); fz.create(P[0]);
+        fx.create(N2); fy.create(P[1]); fz.create(P[0]);
         // one tile per block: [N2][16] float2 along x, [P][16] -- or, for long axes, the narrow [P][8] -- along y / z
         const size_t need_x = (size_t)N2 * TC * sizeof(float2) + 512;
         const size_t need_c = (size_t)std::max(P[1], P[0]) * (TC / 2) * sizeof(float2) + 512;
@@ -379,8 +354,7 @@ public:
         const long long grid = (p.nlines + TC - 1) / TC;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long);
         // TMA-fed persistent pipeline (XFwdT, the default): needs 16-byte aligned source rows and an even x origin
-        const int tma = env_int_now("SPIM_XFWD_TMA", 1);
-        if (tma && (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && p.sx % 4 == 0 && p.ox % 2 == 0 && grid <= 0x7fffffff) {
+        if (env_int("SPIM_XFWD_TMA", 1) && (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && p.sx % 4 == 0 && p.ox % 2 == 0 && grid <= 0x7fffffff) {
             XFwdTParams q;
             memset(&q, 0, sizeof(q));
             q.x = p;
@@ -388,41 +362,32 @@ public:
             q.row_bytes = (unsigned)p.sx * 4u;
             const size_t slot_bytes = (size_t)TC * q.LS * sizeof(float);
             const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
-            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
-                                 (size_t)std::max(1, fx_.n) * sizeof(int2);
+            const size_t sm = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
+                              (size_t)std::max(1, fx_.n) * sizeof(int2) + slot_bytes;
             const size_t lim = rt::max_smem();
-            // blocks per SM / slots per block: three blocks with one slot each where that fits (tiles up to ~36 KB), else two
-            // blocks with one slot, else one block with as many slots as fit
-            int nslot = env_int_now("SPIM_XFWD_SLOTS", 0), bps = 0;
-            if (nslot <= 0) nslot = 1;
-            nslot = std::min(nslot, (int)XFwdT::MAXSLOT);
-            while (nslot > 1 && fixed + nslot * slot_bytes + 1024 > lim) --nslot;
-            const size_t sm = fixed + nslot * slot_bytes;
             if (sm + 1024 <= lim) {
-                bps = (int)std::min<size_t>(3, lim / (sm + 1024));
+                // one staging slot per block; three blocks per SM where that fits (tiles up to ~36 KB), else two, else one
+                const int bps = (int)std::min<size_t>(3, lim / (sm + 1024));
                 q.fix = fx_.d; q.nfix = fx_.n;
                 q.magic_nfix = magic_for(std::max(1, fx_.n));
                 q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
                 q.const_row = const_row(p.sx, q.cval, st);
-                q.nslot = nslot;
+                q.nslot = 1;
                 q.ntiles = (int)grid;
                 q.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count() * bps);
                 if (timer) timer->begin(K_XFWD, st);
-                const int T = env_int_now("SPIM_THREADS_XFWDT", 0);
-                if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, T > 0 ? T : 256, sm, st);
-                else if (bps == 2) rt::launch<XFwdT, 384, 2>(q, q.nctas, T > 0 ? T : 384, sm, st);
-                else rt::launch<XFwdT, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
+                // three blocks per SM: 160 threads each -- the phases of a tile hold (N2 / R) * 8 items (280 / 320 / 448 for the
+                // 280-point plan 8 * 7 * 5, 282 for the split step), which 160 threads cover in 2 + 2 + 3 + 2 rounds at 92 % lane
+                // use where 256 threads need 2 + 2 + 2 + 2 at 65 % (measured 0.197 vs 0.208 ms, profiles/r2)
+                if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, 160, sm, st);
+                else if (bps == 2) rt::launch<XFwdT, 384, 2>(q, q.nctas, 384, sm, st);
+                else rt::launch<XFwdT, 512, 1>(q, q.nctas, 512, sm, st);
                 if (timer) timer->end(K_XFWD, st);
                 return;
             }
         }
         if (timer) timer->begin(K_XFWD, st);
-        // four 192-thread blocks per SM (the measured round-1 configuration) need <= 85 registers
-        // SPIM_THREADS_XFWD=160 (experiment): the phases of a 280-point tile hold 280 / 320 / 448 / 282 items -- 160 threads need
-        // the same 2 + 2 + 3 + 2 rounds as 192 do, so five blocks of 160 (72 registers) replace four of 192
-        if (threads_xfwd() == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XFwd, 160, 5>(p, grid, 160, smem, st);
-        else if (threads_xfwd() <= 192) rt::launch<XFwd, 192, 4>(p, grid, threads_xfwd(), smem, st);
-        else rt::launch<XFwd>(p, grid, threads_xfwd(), smem, st);
+        rt::launch<XFwd, 192, 4>(p, grid, 192, smem, st);       // four 192-thread blocks per SM (<= 85 registers)
         if (timer) timer->end(K_XFWD, st);
     }
 
@@ -436,12 +401,15 @@ public:
         // narrow tiles (8 columns, 64-byte rows): automatically where a 16-column tile would leave one block per SM
         // (FFT lengths above ~880, e.g. the 1080-long axes of a 1024^2 x 512 volume on one GPU); SPIM_COL_NARROW=0/1 forces
         const size_t lim = rt::max_smem();
-        const int narrow_env = env_int_now("SPIM_COL_NARROW", -1);
-        int colp = use_colp_for(axis);
-        // the TMA pipeline keeps three tiles per block: axes too long for that (FFT lengths above ~590) fall back to cp.async staging
-        if (colp == 3 && 3 * ((size_t)Pa * TC * sizeof(float2)) + 64 > lim) colp = 2;
-        const bool narrow = colp == 2 &&
-                            (narrow_env >= 0 ? narrow_env != 0 : 2 * ((size_t)Pa * TC * sizeof(float2) + 1024) > lim);
+        const int narrow_env = env_int("SPIM_COL_NARROW", -1);
+        // staging: the persistent TMA / mbarrier pipeline where three tiles fit (FFT lengths up to ~590: the 72 KB y tiles of
+        // the bench volume run 0.136 / 0.126 ms instead of 0.161 / 0.148), but not for small tiles (<= 40 KB: five or six
+        // blocks per SM with one-shot cp.async staging are faster, 0.247 vs 0.300 ms on the z pass)
+        const size_t tile16 = (size_t)Pa * TC * sizeof(float2);
+        int colp = env_int("SPIM_COLP", -1);
+        if (colp < 0) colp = tile16 > 40 * 1024 ? 3 : 2;
+        if (colp == 3 && 3 * tile16 + 64 > lim) colp = 2;
+        const bool narrow = colp == 2 && (narrow_env >= 0 ? narrow_env != 0 : 2 * (tile16 + 1024) > lim);
         const int tcols = narrow ? TC / 2 : TC;
         p.ntx = pitch / tcols;
         if (axis == 1) { p.row_stride = pitch; p.outer_stride = (long long)pitch * P[1]; }
@@ -454,83 +422,56 @@ public:
         p.sa = out_rows;
         p.mode = mode;
         const long long grid = (long long)p.ntx * outer_count;
-        p.nblocks = (int)grid;
-        p.reverse = (use_serpentine() && axis == 1 && mode == COL_FWD && colp == 2 && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)Pa * tcols * sizeof(float2);
         if (timer) timer->begin(id, st);
         if (narrow) {
             debug_counter(0) += 1;
             p.ntiles = -1;    // async mode flag
-            p.kstage = 0;
             const int T = threads_col_for(smem, lim);
             // 36 KB tiles and smaller: keep five 128-thread blocks per SM, like the 16-column small-tile instantiation
             if (smem <= 40 * 1024 && T <= 128) rt::launch<ColPassNarrow, 128, 5>(p, grid, T, smem, st);
             else rt::launch<ColPassNarrow>(p, grid, T, smem, st);
-        } else if (colp == 3 && 3 * smem + 64 <= lim && grid <= 0x7fffffff) {
-            // experimental TMA / mbarrier pipeline: correct, but slower than the default in round 1 (see kernels.h)
-            p.kstage = 0;
+        } else if (colp == 3 && grid <= 0x7fffffff) {
+            // persistent, warp-specialised: one CTA per SM, a producer warp and two consumer groups over a ring of three tiles
             p.ntiles = (int)grid;
             p.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
-            int T = threads_colt();
-            if (T < 96) T = 96;
-            // tensor-map producer (SPIM_TMAP=1): one request per box of box_rows rows instead of one per row
-            static int want_tmap = env_int("SPIM_TMAP", 1);
+            // tensor-map producer: one request per box of box_rows rows instead of one bulk copy per row
             p.use_tmap = 0;
-            if (want_tmap) {
-                int br = 0;
-                for (int d = std::min(Pa, 256); d >= 1; --d) if (Pa % d == 0) { br = d; break; }
-                const unsigned long long fl = 2ull * pitch;                      // floats per row
-                bool ok = br >= 8 && Pa / br <= 32;
-                if (ok && axis == 1) {
-                    const unsigned long long dims[2] = {fl, (unsigned long long)P[1] * P[0]};
-                    const unsigned long long str[1] = {fl * 4};
-                    const unsigned int box[2] = {2 * TC, (unsigned)br};
-                    ok = rt::encode_tensor_map(&p.tmap, data, 2, dims, str, box);
-                    p.tmap_rank = 2;
-                } else if (ok) {
-                    const unsigned long long dims[3] = {fl, (unsigned long long)P[1], (unsigned long long)P[0]};
-                    const unsigned long long str[2] = {fl * 4, fl * 4 * P[1]};
-                    const unsigned int box[3] = {2 * TC, 1, (unsigned)br};
-                    ok = rt::encode_tensor_map(&p.tmap, data, 3, dims, str, box);
-                    p.tmap_rank = 3;
-                }
-                if (ok) { p.use_tmap = 1; p.box_rows = br; }
+            int br = 0;
+            for (int d = std::min(Pa, 256); d >= 1; --d) if (Pa % d == 0) { br = d; break; }
+            const unsigned long long fl = 2ull * pitch;                      // floats per row
+            bool ok = br >= 8 && Pa / br <= 32;
+            if (ok && axis == 1) {
+                const unsigned long long dims[2] = {fl, (unsigned long long)P[1] * P[0]};
+                const unsigned long long str[1] = {fl * 4};
+                const unsigned int box[2] = {2 * TC, (unsigned)br};
+                ok = rt::encode_tensor_map(&p.tmap, data, 2, dims, str, box);
+                p.tmap_rank = 2;
+            } else if (ok) {
+                const unsigned long long dims[3] = {fl, (unsigned long long)P[1], (unsigned long long)P[0]};
+                const unsigned long long str[2] = {fl * 4, fl * 4 * P[1]};
+                const unsigned int box[3] = {2 * TC, 1, (unsigned)br};
+                ok = rt::encode_tensor_map(&p.tmap, data, 3, dims, str, box);
+                p.tmap_rank = 3;
             }
-            rt::launch<ColPassT, 512>(p, p.nctas, T, 3 * smem + 64, st);
-        } else if (colp == 4) {
-            // experimental warp-private-column variant: 4 warps per tile, no CTA barriers between stages
-            rt::launch<ColPassW>(p, grid, 128, smem, st);
-        } else if (colp >= 2) {
-            p.ntiles = -1;    // async mode flag
-            static int ks = env_int("SPIM_KSTAGE", 0);
-            p.kstage = (ks && mode == COL_MID && 2 * smem <= 76 * 1024) ? 1 : 0;
-            const int rc = use_regcap();
-            // SPIM_COL_LEAN=1 (experiment): plans without radices 9 / 10 (288 = 8*6*6, the z axis of the bench volume) run from
-            // an instantiation compiled for radices <= 8 only: 80 registers without spills instead of 127 (96 when capped), so
-            // six 128-thread blocks of a 36 KB tile are resident per SM instead of five
+            if (ok) { p.use_tmap = 1; p.box_rows = br; }
+            rt::launch<ColPassT, 512>(p, p.nctas, 480, 3 * smem + 64, st);
+        } else {
+            p.ntiles = colp >= 2 ? -1 : 0;    // -1: async mode (whole tile staged by cp.async)
             int rmax = 0;
             for (int s_ = 0; s_ < p.plan.nstages; ++s_) rmax = std::max(rmax, p.plan.radix[s_]);
-            if (env_int_now("SPIM_COL_LEAN", 0) && rmax <= 8 && !p.kstage) {
-                if (smem <= 37 * 1024) rt::launch<ColPassR8, 128, 6>(p, grid, 128, smem, st);
-                else rt::launch<ColPassR8, 256, 1>(p, grid, threads_col_for(smem, lim), smem, st);
-            }
-            else if (rc == 1) rt::launch<ColPass, 256, 3>(p, grid, threads_col(), (p.kstage ? 2 : 1) * smem, st);
-            // SPIM_REGCAP=2: large tiles (three 72 KB y tiles per SM) with 192 threads each, <= 113 registers: 18 warps
-            else if (rc == 2 && smem > 40 * 1024 && 3 * (smem + 1024) <= lim && !p.kstage) rt::launch<ColPass, 192, 3>(p, grid, 192, smem, st);
-            // SPIM_REGCAP=3: small tiles (36 KB z tiles) as six blocks of 128 threads per SM, <= 85 registers: 24 warps
-            else if (rc == 3 && smem <= 37 * 1024 && !p.kstage) rt::launch<ColPass, 128, 6>(p, grid, 128, smem, st);
-            else if (smem <= 40 * 1024 && threads_col() <= 128 && !p.kstage)
-                // small tiles (z pass of the 512x512x256 brick: 36 KB): registers, not shared memory, limit the resident
-                // blocks -- keep 5 blocks of 128 threads per SM (<= 102 registers) as in the measured round-1 binary
-                rt::launch<ColPass, 128, 5>(p, grid, threads_col(), smem, st);
+            if (smem <= 37 * 1024 && rmax <= 8)
+                // small tiles of plans without radices 9 / 10 (288 = 8 * 6 * 6, the z axis of the bench volume): the instantiation
+                // compiled for radices <= 8 needs 80 registers -- six 128-thread blocks per SM (0.2445 vs 0.2467 ms)
+                rt::launch<ColPassR8, 128, 6>(p, grid, 128, smem, st);
+            else if (smem <= 40 * 1024)
+                // small tiles: registers, not shared memory, limit the resident blocks -- five blocks of 128 threads (96 registers)
+                rt::launch<ColPass, 128, 5>(p, grid, 128, smem, st);
             else {
-                const size_t sm = (p.kstage ? 2 : 1) * smem;
-                const int T = threads_col_for(sm, lim);
-                if (T > 256) rt::launch<ColPass, 384>(p, grid, T, sm, st);     // one 1080-row tile per SM
-                else rt::launch<ColPass>(p, grid, T, sm, st);
+                const int T = threads_col_for(smem, lim);
+                if (T > 256) rt::launch<ColPass, 384>(p, grid, T, smem, st);     // one 1080-row tile per SM
+                else rt::launch<ColPass>(p, grid, T, smem, st);
             }
-        } else {
-            rt::launch<ColPass>(p, grid, threads_col(), smem, st);
         }
         if (timer) timer->end(id, st);
     }
@@ -559,90 +500,31 @@ public:
         p.vec_ok = al8(e.dst) && (p.dsx % 2 == 0) && (p.dox % 2 == 0) && (n[2] % 2 == 0) && al8(e.img) && al8(e.weight);
         const long long grid = (p.nlines + TC - 1) / TC;
         const int xinv_id = e.epi == EPI_UPDATE ? K_XINV_UPDATE : (e.epi == EPI_RATIO ? K_XINV : K_XINV_STORE);
-        p.nblocks = (int)grid;
-        p.reverse = (use_serpentine() && e.epi != EPI_STORE && grid <= 0x7fffffff) ? 1 : 0;
         const size_t smem = (size_t)N2 * TC * sizeof(float2) + 3 * TC * sizeof(long long);
-        // TMA-fed persistent pipeline (XInvP, the default): spectrum rows are always 16-byte aligned
-        if (env_int_now("SPIM_XINV_TMA", 1) && grid <= 0x7fffffff) {
-            XInvPParams q;
-            memset(&q, 0, sizeof(q));
-            q.x = p;
-            q.row_bytes = (unsigned)pitch * (unsigned)sizeof(float2);
-            q.prefetch = env_int_now("SPIM_XINV_PREFETCH", 1);
-            const size_t slot_bytes = (size_t)TC * pitch * sizeof(float2);
-            const size_t fixed = (size_t)N2 * TC * sizeof(float2) + 2 * TC * sizeof(long long) + 3 * sizeof(uint64_t);
-            const size_t lim = rt::max_smem();
-            int nslot = std::max(1, std::min(3, env_int_now("SPIM_XINV_SLOTS", 1)));
-            while (nslot > 1 && fixed + nslot * slot_bytes + 1024 > lim) --nslot;
-            const size_t sm = fixed + nslot * slot_bytes;
-            if (sm + 1024 <= lim) {
-                const int bps = (int)std::min<size_t>(3, lim / (sm + 1024));
-                q.nslot = nslot;
-                q.ntiles = (int)grid;
-                const int T = env_int_now("SPIM_THREADS_XINVP", 0);
-                if (timer) timer->begin(xinv_id, st);
-                const bool hot = p.fast_epilogue && !e.exact_tikhonov && e.epi != EPI_STORE;
-                if (hot && bps >= 3) {
-                    q.nctas = (int)std::min<long long>(grid, 3LL * rt::sm_count());
-                    // ratio: 80 registers, three blocks of 256 threads; update: 128 registers uncapped -- 160 threads run it
-                    // without spills, 192 threads (one round less per tile) cap it at 96 registers with ~130 bytes of spills
-                    if (e.epi == EPI_RATIO) rt::launch<XInvPRatioFast, 256, 3>(q, q.nctas, T > 0 ? T : 256, sm, st);
-                    else if (T > 0 && T <= 160) rt::launch<XInvPUpdateFast, 160, 3>(q, q.nctas, T, sm, st);
-                    else rt::launch<XInvPUpdateFast, 192, 3>(q, q.nctas, T > 0 ? T : 192, sm, st);
-                } else if (hot && bps == 1) {
-                    q.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count());
-                    if (e.epi == EPI_RATIO) rt::launch<XInvPRatioFast, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
-                    else rt::launch<XInvPUpdateFast, 512, 1>(q, q.nctas, T > 0 ? T : 512, sm, st);
-                } else {
-                    const int b2 = std::min(bps, 2);
-                    q.nctas = (int)std::min<long long>(grid, (long long)b2 * rt::sm_count());
-                    const int T2 = T > 0 ? T : 256;
-                    if (e.epi == EPI_STORE) rt::launch<XInvPStore, 256, 2>(q, q.nctas, T2, sm, st);
-                    else if (e.epi == EPI_RATIO) {
-                        if (p.fast_epilogue) rt::launch<XInvPRatioFast, 256, 2>(q, q.nctas, T2, sm, st);
-                        else rt::launch<XInvPRatioIeee, 256, 2>(q, q.nctas, T2, sm, st);
-                    }
-                    else if (e.exact_tikhonov) rt::launch<XInvPUpdateExact64, 256, 2>(q, q.nctas, T2, sm, st);
-                    else if (p.fast_epilogue) rt::launch<XInvPUpdateFast, 256, 2>(q, q.nctas, T2, sm, st);
-                    else rt::launch<XInvPUpdateIeee, 256, 2>(q, q.nctas, T2, sm, st);
-                }
-                if (timer) timer->end(xinv_id, st);
-                return;
-            }
-        }
         if (timer) timer->begin(xinv_id, st);
-        const int T = threads_xinv();
-        // 36 KB tiles: six 128-thread blocks fit per SM as long as the ratio kernel stays within 85 registers
-        const bool cap6 = T <= 128 && smem <= 37 * 1024;
-        if (e.epi == EPI_STORE) rt::launch<XInvT<EPI_STORE, MATH_IEEE>>(p, grid, T, smem, st);
+        // Block size: small tiles (<= 36 KB: five / six blocks per SM) run 128 threads, larger ones (three or fewer blocks per
+        // SM) 256 -- measured on the 540-point lines of the 1024^2 x 512 volume: 2.16 ms with 256 threads, 2.41 with 128.
+        // The register-capped instantiations keep six (ratio, 80 registers) / five (update, 96 registers) 128-thread blocks
+        // resident on the small tiles (update: 0.300 vs 0.336 ms uncapped).  A TMA-fed persistent variant of this kernel was
+        // built and measured in round 2 (0.325 vs 0.300 ms average) and removed again: its staging slot halves the resident blocks.
+        const bool small = smem <= 37 * 1024;
+        const int T = small ? 128 : 256;
+        if (e.epi == EPI_STORE) rt::launch<XInvStore>(p, grid, T, smem, st);
         else if (e.epi == EPI_RATIO) {
             if (p.fast_epilogue) {
-                // SPIM_THREADS_XINV=160 (experiment): 11 rounds per tile instead of 15 with 128 threads, five blocks per SM
-                if (T == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvRatioFast, 160, 5>(p, grid, 160, smem, st);
-                else if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_FAST>, 128, 6>(p, grid, T, smem, st);
-                else rt::launch<XInvT<EPI_RATIO, MATH_FAST>>(p, grid, T, smem, st);
+                if (small) rt::launch<XInvRatioFast, 128, 6>(p, grid, T, smem, st);
+                else rt::launch<XInvRatioFast>(p, grid, T, smem, st);
             } else {
-                if (cap6) rt::launch<XInvT<EPI_RATIO, MATH_IEEE>, 128, 6>(p, grid, T, smem, st);
-                else rt::launch<XInvT<EPI_RATIO, MATH_IEEE>>(p, grid, T, smem, st);
+                if (small) rt::launch<XInvRatioIeee, 128, 6>(p, grid, T, smem, st);
+                else rt::launch<XInvRatioIeee>(p, grid, T, smem, st);
             }
         }
-        else if (e.exact_tikhonov) rt::launch<XInvT<EPI_UPDATE, MATH_EXACT64>>(p, grid, T, smem, st);
+        else if (e.exact_tikhonov) rt::launch<XInvUpdateExact64>(p, grid, T, smem, st);
         else if (p.fast_epilogue) {
-            // SPIM_XINV_CAP=5 (experiment): five 128-thread blocks of the update kernel per SM (96 registers, ~270 bytes of
-            // spills) instead of four at 128 registers
-            static int cap = env_int("SPIM_XINV_CAP", 0);
-            // SPIM_XINV_R0=1 (experiment, with SPIM_XPLAN_ASC=1): when the x plan starts with a small radix, run the update
-            // from an instantiation compiled for stage-0 radices <= 5 (80 registers, six 128-thread blocks per SM, no spills)
-            // or <= 7 (96 registers, five blocks) instead of the general one (128 registers, four blocks)
-            const int lean = env_int_now("SPIM_XINV_R0", 0);
-            const int r0 = fx.dev.radix[0];
-            if (lean && r0 <= 5 && T == 160 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 160, 5>(p, grid, 160, smem, st);
-            else if (lean && r0 <= 5 && T <= 128 && 6 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR5, 128, 6>(p, grid, T, smem, st);
-            else if (lean && r0 <= 7 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFastR7, 128, 5>(p, grid, T, smem, st);
-            else if (cap == 5 && T <= 128 && 5 * (smem + 1024) <= rt::max_smem()) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
-            else rt::launch<XInvT<EPI_UPDATE, MATH_FAST>>(p, grid, T, smem, st);
+            if (small) rt::launch<XInvUpdateFast, 128, 5>(p, grid, T, smem, st);
+            else rt::launch<XInvUpdateFast>(p, grid, T, smem, st);
         }
-        else rt::launch<XInvT<EPI_UPDATE, MATH_IEEE>>(p, grid, T, smem, st);
+        else rt::launch<XInvUpdateIeee>(p, grid, T, smem, st);
         if (timer) timer->end(xinv_id, st);
     }
 

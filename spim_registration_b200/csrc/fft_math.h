@@ -238,4 +238,194 @@ template <int R, bool INV> struct Dft {
     }
 };
 
+
+// =========================================================================================
+// Packed pairs (Blackwell FADD2 / FMUL2 / FFMA2): the TWO columns (or lines) of a work item go through identical
+// arithmetic, so their real parts travel in one 64-bit register pair and their imaginary parts in another, and every
+// butterfly operation is ONE packed instruction for both columns -- half the floating-point issue slots of the scalar
+// form.  Scalar operands (compile-time twiddle constants, per-row twiddles) are broadcast by the instruction itself.
+// The host / emulator build evaluates the same expressions component-wise.
+// =========================================================================================
+struct C2 { float2 re, im; };      // re = (re_a, re_b), im = (im_a, im_b)
+
+#if defined(__CUDA_ARCH__) && !defined(SPIM_HOST_EMU)
+SPIM_HD float2 p2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SPIM_HD float2 p2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+SPIM_HD float2 p2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+SPIM_HD float2 p2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+SPIM_HD float2 p2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SPIM_HD float2 p2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+SPIM_HD float2 p2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+SPIM_HD float2 p2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+SPIM_HD float2 p2neg(float2 a) { return make_float2(-a.x, -a.y); }
+SPIM_HD float2 p2bc(float s) { return make_float2(s, s); }       // scalar broadcast (an operand modifier on the GPU)
+
+SPIM_HD C2 cadd(C2 a, C2 b) { C2 r; r.re = p2add(a.re, b.re); r.im = p2add(a.im, b.im); return r; }
+SPIM_HD C2 csub(C2 a, C2 b) { C2 r; r.re = p2sub(a.re, b.re); r.im = p2sub(a.im, b.im); return r; }
+// a + i b  /  a - i b
+SPIM_HD C2 caddi(C2 a, C2 b) { C2 r; r.re = p2sub(a.re, b.im); r.im = p2add(a.im, b.re); return r; }
+SPIM_HD C2 csubi(C2 a, C2 b) { C2 r; r.re = p2add(a.re, b.im); r.im = p2sub(a.im, b.re); return r; }
+// a * (c + i s) and a * (c - i s) with scalar c, s (broadcast)
+SPIM_HD C2 cmul_s(C2 a, float c, float s) {
+    C2 r;
+    r.re = p2fma(p2neg(a.im), p2bc(s), p2mul(a.re, p2bc(c)));
+    r.im = p2fma(a.re, p2bc(s), p2mul(a.im, p2bc(c)));
+    return r;
+}
+SPIM_HD C2 cmulc_s(C2 a, float c, float s) {
+    C2 r;
+    r.re = p2fma(a.im, p2bc(s), p2mul(a.re, p2bc(c)));
+    r.im = p2fma(p2neg(a.re), p2bc(s), p2mul(a.im, p2bc(c)));
+    return r;
+}
+// a * b with b = two different complex numbers (the kernel-spectrum multiply)
+SPIM_HD C2 cmul(C2 a, C2 b) {
+    C2 r;
+    r.re = p2fma(p2neg(a.im), b.im, p2mul(a.re, b.re));
+    r.im = p2fma(a.re, b.im, p2mul(a.im, b.re));
+    return r;
+}
+// interleaved float4 (re_a, im_a, re_b, im_b) <-> packed pair
+SPIM_HD C2 c2_from_il(float4 v) { C2 r; r.re = make_float2(v.x, v.z); r.im = make_float2(v.y, v.w); return r; }
+SPIM_HD float4 c2_to_il(C2 a) { return make_float4(a.re.x, a.im.x, a.re.y, a.im.y); }
+// packed float4 (re_a, re_b, im_a, im_b): the layout of shared-memory tiles between stages
+SPIM_HD C2 c2_from_pk(float4 v) { C2 r; r.re = make_float2(v.x, v.y); r.im = make_float2(v.z, v.w); return r; }
+SPIM_HD float4 c2_to_pk(C2 a) { return make_float4(a.re.x, a.re.y, a.im.x, a.im.y); }
+SPIM_HD C2 c2_from_ab(float2 a, float2 b) { C2 r; r.re = make_float2(a.x, b.x); r.im = make_float2(a.y, b.y); return r; }
+SPIM_HD float2 c2_a(C2 v) { return make_float2(v.re.x, v.im.x); }
+SPIM_HD float2 c2_b(C2 v) { return make_float2(v.re.y, v.im.y); }
+
+template <bool INV> SPIM_HD C2 rot90(C2 a) {        // multiply by -i (forward) or +i (inverse)
+    C2 r;
+    if (INV) { r.re = p2neg(a.im); r.im = a.re; } else { r.re = a.im; r.im = p2neg(a.re); }
+    return r;
+}
+template <int NUM, int DEN, bool INV> SPIM_HD C2 ctw(C2 a) {
+    constexpr int n = ((NUM % DEN) + DEN) % DEN;
+    if constexpr (n == 0) {
+        return a;
+    } else if constexpr (4 * n == DEN) {
+        return rot90<INV>(a);
+    } else if constexpr (2 * n == DEN) {
+        C2 r; r.re = p2neg(a.re); r.im = p2neg(a.im); return r;
+    } else if constexpr (4 * n == 3 * DEN) {
+        return rot90<!INV>(a);
+    } else {
+        constexpr float c = Tw<n, DEN>::c;
+        constexpr float s = INV ? -Tw<n, DEN>::s : Tw<n, DEN>::s;  // w = c - i*s (fwd)
+        return cmulc_s(a, c, s);
+    }
+}
+
+template <int R, bool INV> struct Dft2;
+template <int R, bool INV> SPIM_HD void dft(C2 (&a)[R]) { Dft2<R, INV>::run(a); }
+
+template <bool INV> struct Dft2<1, INV> { SPIM_HD static void run(C2 (&)[1]) {} };
+template <bool INV> struct Dft2<2, INV> {
+    SPIM_HD static void run(C2 (&a)[2]) {
+        C2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    }
+};
+template <bool INV> struct Dft2<4, INV> {
+    SPIM_HD static void run(C2 (&a)[4]) {
+        C2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+        C2 t2 = cadd(a[1], a[3]), d = csub(a[1], a[3]);
+        a[0] = cadd(t0, t2);
+        a[2] = csub(t0, t2);
+        // t1 -+ i d (forward: a[1] = t1 - i d)
+        a[1] = INV ? caddi(t1, d) : csubi(t1, d);
+        a[3] = INV ? csubi(t1, d) : caddi(t1, d);
+    }
+};
+template <int P, bool INV> struct Dft2Prime {
+    SPIM_HD static void run(C2 (&a)[P]) {
+        constexpr int H = (P - 1) / 2;
+        C2 s[H], d[H];
+        static_for<H>([&](auto qi) {
+            constexpr int q = decltype(qi)::value + 1;
+            s[q - 1] = cadd(a[q], a[P - q]);
+            d[q - 1] = csub(a[q], a[P - q]);
+        });
+        const C2 a0 = a[0];
+        C2 x0 = a0;
+        static_for<H>([&](auto qi) { x0 = cadd(x0, s[decltype(qi)::value]); });
+        a[0] = x0;
+        static_for<H>([&](auto ki) {
+            constexpr int k = decltype(ki)::value + 1;
+            C2 t = a0, u;
+            static_for<H>([&](auto qi) {
+                constexpr int q = decltype(qi)::value + 1;
+                constexpr float c = Tw<(k * q) % P, P>::c;
+                constexpr float sn = Tw<(k * q) % P, P>::s;
+                t.re = p2fma(s[q - 1].re, p2bc(c), t.re);
+                t.im = p2fma(s[q - 1].im, p2bc(c), t.im);
+                if constexpr (q == 1) { u.re = p2mul(d[0].re, p2bc(sn)); u.im = p2mul(d[0].im, p2bc(sn)); }
+                else { u.re = p2fma(d[q - 1].re, p2bc(sn), u.re); u.im = p2fma(d[q - 1].im, p2bc(sn), u.im); }
+            });
+            // forward: X_k = t - i u ; X_{P-k} = t + i u   (inverse swaps the two)
+            const C2 lo = csubi(t, u), hi = caddi(t, u);
+            a[k] = INV ? hi : lo;
+            a[P - k] = INV ? lo : hi;
+        });
+    }
+};
+template <int R, bool INV> struct Dft2Composite {
+    SPIM_HD static void run(C2 (&a)[R]) {
+        constexpr int R1 = split_factor(R);
+        constexpr int R2 = R / R1;
+        C2 y[R];
+        static_for<R2>([&](auto n2i) {
+            constexpr int n2 = decltype(n2i)::value;
+            C2 t[R1];
+            static_for<R1>([&](auto n1i) { constexpr int n1 = decltype(n1i)::value; t[n1] = a[R2 * n1 + n2]; });
+            dft<R1, INV>(t);
+            static_for<R1>([&](auto k1i) {
+                constexpr int k1 = decltype(k1i)::value;
+                y[k1 * R2 + n2] = ctw<n2 * k1, R, INV>(t[k1]);
+            });
+        });
+        static_for<R1>([&](auto k1i) {
+            constexpr int k1 = decltype(k1i)::value;
+            C2 u[R2];
+            static_for<R2>([&](auto n2i) { constexpr int n2 = decltype(n2i)::value; u[n2] = y[k1 * R2 + n2]; });
+            dft<R2, INV>(u);
+            static_for<R2>([&](auto k2i) { constexpr int k2 = decltype(k2i)::value; a[k1 + R1 * k2] = u[k2]; });
+        });
+    }
+};
+template <int R, bool INV> struct Dft2PFA {
+    SPIM_HD static void run(C2 (&a)[R]) {
+        constexpr int R1 = pfa_factor(R);
+        constexpr int R2 = R / R1;
+        constexpr int E1 = R2 * cmodinv(R2 % R1, R1);
+        constexpr int E2 = R1 * cmodinv(R1 % R2, R2);
+        C2 y[R];
+        static_for<R2>([&](auto n2i) {
+            constexpr int n2 = decltype(n2i)::value;
+            C2 t[R1];
+            static_for<R1>([&](auto n1i) { constexpr int n1 = decltype(n1i)::value; t[n1] = a[(R2 * n1 + R1 * n2) % R]; });
+            dft<R1, INV>(t);
+            static_for<R1>([&](auto k1i) { constexpr int k1 = decltype(k1i)::value; y[k1 * R2 + n2] = t[k1]; });
+        });
+        static_for<R1>([&](auto k1i) {
+            constexpr int k1 = decltype(k1i)::value;
+            C2 u[R2];
+            static_for<R2>([&](auto n2i) { constexpr int n2 = decltype(n2i)::value; u[n2] = y[k1 * R2 + n2]; });
+            dft<R2, INV>(u);
+            static_for<R2>([&](auto k2i) { constexpr int k2 = decltype(k2i)::value; a[(k1 * E1 + k2 * E2) % R] = u[k2]; });
+        });
+    }
+};
+template <int R, bool INV> struct Dft2 {
+    SPIM_HD static void run(C2 (&a)[R]) {
+        if constexpr (is_prime(R)) Dft2Prime<R, INV>::run(a);
+        else if constexpr (pfa_factor(R) != 0) Dft2PFA<R, INV>::run(a);
+        else Dft2Composite<R, INV>::run(a);
+    }
+};
+
 }  // namespace spim

@@ -146,10 +146,31 @@ SPIM_DEV void mul_twiddles1(float2 (&a)[R], const float2 (&w)[R]) {
 // transposing first / last phases are conflict-free)
 SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
 
+// twiddle multiply of a packed pair: x[p] *= w[p] (forward) or conj(w[p]) (inverse), w broadcast to both columns
+template <int R, bool INV>
+SPIM_DEV void mul_twiddles_c2(C2 (&x)[R], const float2 (&w)[R]) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) x[p] = INV ? cmulc_s(x[p], w[p].x, w[p].y) : cmul_s(x[p], w[p].x, w[p].y);
+}
+
+template <int R, bool INV>
+SPIM_DEV void apply_twiddles_c2(C2 (&x)[R], const float2* tw) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) {
+        const float2 w = spim_ldg(tw + (p - 1));
+        x[p] = INV ? cmulc_s(x[p], w.x, w.y) : cmul_s(x[p], w.x, w.y);
+    }
+}
+
 // W = float4 column pairs per tile row: TP (16 columns, 128-byte rows) or TP / 2 (narrow tiles: 8 columns, 64-byte rows, for
-// axes so long that a 16-column tile would leave one block per SM)
+// axes so long that a 16-column tile would leave one block per SM).
+// The butterflies run on packed pairs (fft_math.h, C2).  Global memory and freshly staged tiles hold the two columns
+// interleaved (re_a, im_a, re_b, im_b); between the stages of one kernel the shared-memory tile holds them packed
+// (re_a, re_b, im_a, im_b), so only a kernel's first load and last store pay the register shuffle.
+// src_p / dst_p: the shared-memory source / destination of this stage is in the packed layout.
 template <int R, bool INV, bool TW, int W = TP>
-SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
+SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g,
+                         int src_p = 0, int dst_p = 0) {
     const int M = pl.M[s];
     const int L = M * R;
     const int nb = pl.n / R;
@@ -165,56 +186,74 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
         const int blk = (M == 1) ? m : fastdiv(m, magic);
         const int j = m - blk * M;
         const int base = blk * L + j;
-        float2 a[R], b[R], w[R];
+        C2 x[R];
+        float2 w[R];
         if (TW) load_twiddles<R>(w, twp + j * (R - 1));
         if (src_g) {
             const float4* gp = reinterpret_cast<const float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q * M;
-                const float4 v = ldg_stream(gp + q * gstep);   // gap rows hold stale data: load anyway, select zero
+                float4 v = ldg_stream(gp + q * gstep);   // gap rows hold stale data: load anyway, select zero
                 const bool ok = (row < g.va) || (row >= g.vb);
-                a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
-                b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
+                if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                x[q] = c2_from_il(v);
             }
-        } else if (W != TP || !swz) {
-            const float4* sp = tile + base * W + c2;
-#pragma unroll
-            for (int q = 0; q < R; ++q) { const float4 v = sp[q * M * W]; a[q] = lo2(v); b[q] = hi2(v); }
         } else {
+            float4 v[R];
+            if (W != TP || !swz) {
+                const float4* sp = tile + base * W + c2;
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q * M;
-                const float4 v = tile[row * TP + ((c2 + row) & (TP - 1))];
-                a[q] = lo2(v); b[q] = hi2(v);
+                for (int q = 0; q < R; ++q) v[q] = sp[q * M * W];
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int row = base + q * M;
+                    v[q] = tile[row * TP + ((c2 + row) & (TP - 1))];
+                }
+            }
+            if (src_p) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) x[q] = c2_from_pk(v[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) x[q] = c2_from_il(v[q]);
             }
         }
         if (!INV) {
-            dft<R, false>(a);
-            dft<R, false>(b);
-            if (TW) mul_twiddles2<R, false>(a, b, w);
+            dft<R, false>(x);
+            if (TW) mul_twiddles_c2<R, false>(x, w);
         } else {
-            if (TW) mul_twiddles2<R, true>(a, b, w);
-            dft<R, true>(a);
-            dft<R, true>(b);
+            if (TW) mul_twiddles_c2<R, true>(x, w);
+            dft<R, true>(x);
         }
         if (dst_g) {
             // predicated streaming stores, the row pointer advanced by one 64-bit add per row
             float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                stg_stream_if(gp, pack4(a[q], b[q]), base + q * M < g.sa);
+                stg_stream_if(gp, c2_to_il(x[q]), base + q * M < g.sa);
                 gp += gstep;
             }
-        } else if (W != TP || !swz) {
-            float4* sp = tile + base * W + c2;
-#pragma unroll
-            for (int q = 0; q < R; ++q) sp[q * M * W] = pack4(a[q], b[q]);
         } else {
+            float4 v[R];
+            if (dst_p) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q * M;
-                tile[row * TP + ((c2 + row) & (TP - 1))] = pack4(a[q], b[q]);
+                for (int q = 0; q < R; ++q) v[q] = c2_to_pk(x[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) v[q] = c2_to_il(x[q]);
+            }
+            if (W != TP || !swz) {
+                float4* sp = tile + base * W + c2;
+#pragma unroll
+                for (int q = 0; q < R; ++q) sp[q * M * W] = v[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int row = base + q * M;
+                    tile[row * TP + ((c2 + row) & (TP - 1))] = v[q];
+                }
             }
         }
     }
@@ -223,22 +262,20 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
 #endif
 }
 
-// last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers
+// last forward stage + kernel-spectrum multiply + first inverse stage, fused in registers (packed pairs; the kernel
+// spectrum arrives interleaved from global memory or its staged copy).  src_p / dst_p as in stage_tile.
 template <int R, int W = TP>
-SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
+SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, long long ks4,
+                       int src_p = 0, int dst_p = 0) {
     const int nb = pl.n / R;
     const long long gs4 = g.stride >> 1;
     constexpr int LW = (W == 8) ? 3 : 2;
     SPIM_FOR_ITEMS_TG(tg, i, nb * W) {
         const int c2 = i & (W - 1);
         const int base = (i >> LW) * R;
-        float2 a[R], b[R];
+        C2 x[R];
         float4 kv[R];
-        if (ks) {      // kernel-spectrum tile staged in shared memory
-            const float4* kp = ks + base * W + c2;
-#pragma unroll
-            for (int q = 0; q < R; ++q) kv[q] = kp[q * W];
-        } else {
+        {
             const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * ks4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) kv[q] = ldg_stream(kp + q * ks4);
@@ -248,33 +285,41 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int row = base + q;
-                const float4 v = ldg_stream(gp + q * gs4);
+                float4 v = ldg_stream(gp + q * gs4);
                 const bool ok = (row < g.va) || (row >= g.vb);
-                a[q] = ok ? lo2(v) : make_float2(0.f, 0.f);
-                b[q] = ok ? hi2(v) : make_float2(0.f, 0.f);
+                if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                x[q] = c2_from_il(v);
             }
         } else {
             const float4* sp = tile + base * W + c2;
+            if (src_p) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) { const float4 v = sp[q * W]; a[q] = lo2(v); b[q] = hi2(v); }
+                for (int q = 0; q < R; ++q) x[q] = c2_from_pk(sp[q * W]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) x[q] = c2_from_il(sp[q * W]);
+            }
         }
-        dft<R, false>(a);
-        dft<R, false>(b);
+        dft<R, false>(x);
 #pragma unroll
-        for (int q = 0; q < R; ++q) { a[q] = cmul(a[q], lo2(kv[q])); b[q] = cmul(b[q], hi2(kv[q])); }
-        dft<R, true>(a);
-        dft<R, true>(b);
+        for (int q = 0; q < R; ++q) x[q] = cmul(x[q], c2_from_il(kv[q]));
+        dft<R, true>(x);
         if (dst_g) {
             float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                stg_stream_if(gp, pack4(a[q], b[q]), base + q < g.sa);
+                stg_stream_if(gp, c2_to_il(x[q]), base + q < g.sa);
                 gp += gs4;
             }
         } else {
             float4* sp = tile + base * W + c2;
+            if (dst_p) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) sp[q * W] = pack4(a[q], b[q]);
+                for (int q = 0; q < R; ++q) sp[q * W] = c2_to_pk(x[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) sp[q * W] = c2_to_il(x[q]);
+            }
         }
     }
     tg_barrier(tg);
@@ -309,13 +354,15 @@ SPIM_DEV void mid_tile(const TG& tg, const FftPlanDev& pl, float4* tile, int src
 
 // RMAX: largest radix the instantiation is compiled for (register-lean variants for plans without large radices)
 template <bool INV, int W = TP, int RMAX = 16>
-SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g) {
-    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, true, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
-    else { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, false, W>(tg, pl, s, tile, swz, src_g, dst_g, g))) }
+SPIM_DEV void stage_dispatch(const TG& tg, const FftPlanDev& pl, int s, float4* tile, int swz, int src_g, int dst_g, const GRows& g,
+                             int src_p = 0, int dst_p = 0) {
+    if (pl.M[s] > 1) { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, true, W>(tg, pl, s, tile, swz, src_g, dst_g, g, src_p, dst_p))) }
+    else { SPIM_RADIX_SWITCH_MAX(pl.radix[s], RMAX, (stage_tile<RR, INV, false, W>(tg, pl, s, tile, swz, src_g, dst_g, g, src_p, dst_p))) }
 }
 template <int W = TP, int RMAX = 16>
-SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, const float4* ks, long long ks4) {
-    SPIM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], RMAX, (mid_tile<RR, W>(tg, pl, tile, src_g, dst_g, g, kh, ks, ks4)))
+SPIM_DEV void mid_dispatch(const TG& tg, const FftPlanDev& pl, float4* tile, int src_g, int dst_g, const GRows& g, const float2* kh, long long ks4,
+                           int src_p = 0, int dst_p = 0) {
+    SPIM_RADIX_SWITCH_MAX(pl.radix[pl.nstages - 1], RMAX, (mid_tile<RR, W>(tg, pl, tile, src_g, dst_g, g, kh, ks4, src_p, dst_p)))
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,9 +379,6 @@ struct ColPassParams {
     int va, vb, sa;
     int mode;
     int ntiles, nctas;         // ColPassT (persistent): tiles in total / CTAs launched; ntiles < 0 selects the async mode of ColPass
-    int kstage;                // COL_MID: kernel-spectrum tile staged in shared memory too
-    int reverse;               // ColPassN: tiles taken from the last to the first (serpentine sweep order, SPIM_SERPENTINE)
-    int nblocks;               // grid size, for the reversed order
     // ColPassT with tensor maps (use_tmap): y pass = 2-D map {2*pitch floats, Py*Pz rows}, box {32, box_rows};
     // z pass = 3-D map {2*pitch, Py, Pz}, box {32, 1, box_rows}; box_rows divides the FFT length
     int use_tmap, box_rows, tmap_rank;
@@ -378,7 +422,6 @@ struct ColPassN {
     SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
         const TG tg = tg_cta();
         float4* tile = reinterpret_cast<float4*>(tile2);
-        if (p.reverse) bid = p.nblocks - 1 - bid;
         const int o = bid / p.ntx;
         const int tx = bid - o * p.ntx;
         const int outer = o < p.outer_split ? o : o + p.outer_shift;
@@ -390,7 +433,6 @@ struct ColPassN {
         const FftPlanDev& pl = p.plan;
         const int S = pl.nstages;
         int sg = 1;                       // first stage reads global memory directly ...
-        const float4* ks = nullptr;
         if (p.ntiles < 0) {               // ... or (async mode) the whole tile is staged with one burst of cp.async
             const int P = pl.n;
             const long long gs4 = p.row_stride >> 1;
@@ -401,11 +443,6 @@ struct ColPassN {
             } else {
                 async_rows<W>(tile, gp, gs4, 0, P);
             }
-            if (p.mode == COL_MID && p.kstage) {
-                float4* kb = tile + (size_t)P * W;
-                async_rows<W>(kb, reinterpret_cast<const float4*>(p.khat + base), gs4, 0, P);
-                ks = kb;
-            }
             cp_async_commit();
             if (p.va < p.vb) {
                 SPIM_FOR_ITEMS(i, (p.vb - p.va) * W) tile[p.va * W + i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -415,14 +452,15 @@ struct ColPassN {
             sg = 0;
             g.va = P; g.vb = P;
         }
+        // the tile is interleaved as loaded and packed between the stages (stage_tile)
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, s == S - 1, g, s > 0, 1);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, sg && s == S - 1, s == 0, g, s < S - 1, 1);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, 0, g);
-            mid_dispatch<W, RMAX>(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, ks, p.row_stride >> 1);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, 0, s == 0, g);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false, W, RMAX>(tg, pl, s, tile, 0, sg && s == 0, 0, g, s > 0, 1);
+            mid_dispatch<W, RMAX>(tg, pl, tile, sg && S == 1, S == 1, g, p.khat + base, p.row_stride >> 1, S > 1, 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true, W, RMAX>(tg, pl, s, tile, 0, 0, s == 0, g, 1, 1);
         }
     }
 };
@@ -462,13 +500,13 @@ struct ColPassT {
         g.stride = p.row_stride;
         g.va = P; g.vb = P; g.sa = p.sa;
         if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g);
+            for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g, s > 0, 1);
         } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
+            for (int s = S - 1; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g, s < S - 1, 1);
         } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, 0, g);
-            mid_dispatch(tg, pl, tile, 0, S == 1, g, p.khat + base, nullptr, p.row_stride >> 1);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g);
+            for (int s = 0; s < S - 1; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, 0, g, s > 0, 1);
+            mid_dispatch(tg, pl, tile, 0, S == 1, g, p.khat + base, p.row_stride >> 1, S > 1, 1);
+            for (int s = S - 2; s >= 0; --s) stage_dispatch<true>(tg, pl, s, tile, 0, 0, s == 0, g, 1, 1);
         }
     }
     SPIM_DEV static void run(const Params& p, int bid, float2* smem2) {
@@ -556,175 +594,6 @@ struct ColPassT {
 };
 
 // ---------------------------------------------------------------------------------------------
-// ColPassW (EXPERIMENTAL, SPIM_COLP=4, not yet timed on hardware): warp-private columns.
-// The 16 columns of a tile are dealt out to the 4 warps of the CTA, two column pairs each.  A column's FFT
-// only ever touches that column, so after the cooperative tile load (one CTA barrier) every warp runs all its
-// stages with warp-level synchronisation only: no CTA barriers between stages, and the warps of an SM drift
-// out of phase instead of stalling together.  Rows are stored rotated (pair c2 of row r sits in 16-byte slot
-// (c2 + 2 r) & 7) so that the 8 lanes of a quarter warp -- 4 consecutive rows x 2 pairs -- hit 8 different slots.
-// ---------------------------------------------------------------------------------------------
-constexpr int WP = 2;                       // column pairs per warp
-SPIM_HD int wslot(int c2, int row) { return (c2 + WP * row) & (TP - 1); }
-
-template <int R, bool INV>
-SPIM_DEV void stage_tile_w(int lane, int nlanes, int c0, const FftPlanDev& pl, int s, float4* tile, int dst_g, const GRows& g) {
-    const int M = pl.M[s];
-    const int L = M * R;
-    const int nb = pl.n / R;
-    const uint32_t magic = pl.magicM[s];
-    const float2* twp = pl.tws + pl.tw_off[s];
-    const long long gs4 = g.stride >> 1;
-    const long long gstep = (long long)M * gs4;
-    for (int i = lane; i < nb * WP; i += nlanes) {
-        const int c2 = c0 + (i & (WP - 1));
-        const int m = i >> 1;
-        const int blk = (M == 1) ? m : fastdiv(m, magic);
-        const int j = m - blk * M;
-        const int base = blk * L + j;
-        float2 a[R], b[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int row = base + q * M;
-            const float4 v = tile[row * TP + wslot(c2, row)];
-            a[q] = lo2(v); b[q] = hi2(v);
-        }
-        if (!INV) {
-            dft<R, false>(a);
-            dft<R, false>(b);
-            if (M > 1) apply_twiddles2<R, false>(a, b, twp + j * (R - 1));
-        } else {
-            if (M > 1) apply_twiddles2<R, true>(a, b, twp + j * (R - 1));
-            dft<R, true>(a);
-            dft<R, true>(b);
-        }
-        if (dst_g) {
-            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q * M;
-                if (row < g.sa) stg_stream(gp + q * gstep, pack4(a[q], b[q]));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q * M;
-                tile[row * TP + wslot(c2, row)] = pack4(a[q], b[q]);
-            }
-        }
-    }
-    spim_syncwarp();
-}
-
-template <int R>
-SPIM_DEV void mid_tile_w(int lane, int nlanes, int c0, const FftPlanDev& pl, float4* tile, int dst_g, const GRows& g, const float2* kh) {
-    const int nb = pl.n / R;
-    const long long gs4 = g.stride >> 1;
-    for (int i = lane; i < nb * WP; i += nlanes) {
-        const int c2 = c0 + (i & (WP - 1));
-        const int base = (i >> 1) * R;
-        float2 a[R], b[R];
-        float4 kv[R];
-        const float4* kp = reinterpret_cast<const float4*>(kh) + (long long)base * gs4 + c2;
-#pragma unroll
-        for (int q = 0; q < R; ++q) kv[q] = ldg_stream(kp + q * gs4);
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int row = base + q;
-            const float4 v = tile[row * TP + wslot(c2, row)];
-            a[q] = lo2(v); b[q] = hi2(v);
-        }
-        dft<R, false>(a);
-        dft<R, false>(b);
-#pragma unroll
-        for (int q = 0; q < R; ++q) { a[q] = cmul(a[q], lo2(kv[q])); b[q] = cmul(b[q], hi2(kv[q])); }
-        dft<R, true>(a);
-        dft<R, true>(b);
-        if (dst_g) {
-            float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q;
-                if (row < g.sa) stg_stream(gp + q * gs4, pack4(a[q], b[q]));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = base + q;
-                tile[row * TP + wslot(c2, row)] = pack4(a[q], b[q]);
-            }
-        }
-    }
-    spim_syncwarp();
-}
-
-template <bool INV>
-SPIM_DEV void stage_dispatch_w(int lane, int nlanes, int c0, const FftPlanDev& pl, int s, float4* tile, int dst_g, const GRows& g) {
-    SPIM_RADIX_SWITCH(pl.radix[s], (stage_tile_w<RR, INV>(lane, nlanes, c0, pl, s, tile, dst_g, g)))
-}
-SPIM_DEV void mid_dispatch_w(int lane, int nlanes, int c0, const FftPlanDev& pl, float4* tile, int dst_g, const GRows& g, const float2* kh) {
-    SPIM_RADIX_SWITCH(pl.radix[pl.nstages - 1], (mid_tile_w<RR>(lane, nlanes, c0, pl, tile, dst_g, g, kh)))
-}
-
-// cooperative async load of tile rows into the rotated layout
-SPIM_DEV void async_rows_w(float4* buf, const float4* gp, long long gs4, int row_lo, int row_hi) {
-#if defined(SPIM_HOST_EMU)
-    for (int row = row_lo; row < row_hi; ++row)
-        for (int c2 = 0; c2 < TP; ++c2) cp_async16(buf + row * TP + wslot(c2, row), gp + (long long)row * gs4 + c2);
-#else
-    const int c2 = threadIdx.x & (TP - 1);
-    const int rstep = blockDim.x >> 3;
-    for (int row = row_lo + (threadIdx.x >> 3); row < row_hi; row += rstep)
-        cp_async16(buf + row * TP + wslot(c2, row), gp + (long long)row * gs4 + c2);
-#endif
-}
-
-struct ColPassW {
-    typedef ColPassParams Params;
-    static constexpr bool kEmuThreads = false;
-    SPIM_DEV static void warp_work(const Params& p, int lane, int nlanes, int c0, float4* tile, const GRows& g, long long base) {
-        const FftPlanDev& pl = p.plan;
-        const int S = pl.nstages;
-        if (p.mode == COL_FWD) {
-            for (int s = 0; s < S; ++s) stage_dispatch_w<false>(lane, nlanes, c0, pl, s, tile, s == S - 1, g);
-        } else if (p.mode == COL_INV) {
-            for (int s = S - 1; s >= 0; --s) stage_dispatch_w<true>(lane, nlanes, c0, pl, s, tile, s == 0, g);
-        } else {
-            for (int s = 0; s < S - 1; ++s) stage_dispatch_w<false>(lane, nlanes, c0, pl, s, tile, 0, g);
-            mid_dispatch_w(lane, nlanes, c0, pl, tile, S == 1, g, p.khat + base);
-            for (int s = S - 2; s >= 0; --s) stage_dispatch_w<true>(lane, nlanes, c0, pl, s, tile, s == 0, g);
-        }
-    }
-    SPIM_DEV static void run(const Params& p, int bid, float2* tile2) {
-        float4* tile = reinterpret_cast<float4*>(tile2);
-        const int P = p.plan.n;
-        long long base;
-        col_tile_base(p, bid, base);
-        GRows g;
-        g.p = p.data + base;
-        g.stride = p.row_stride;
-        g.va = P; g.vb = P; g.sa = p.sa;
-        const long long gs4 = p.row_stride >> 1;
-        const float4* gp = reinterpret_cast<const float4*>(g.p);
-        if (p.va < p.vb) {
-            async_rows_w(tile, gp, gs4, 0, p.va);
-            async_rows_w(tile, gp, gs4, p.vb, P);
-            SPIM_FOR_ITEMS(i, (p.vb - p.va) * TP) tile[p.va * TP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            async_rows_w(tile, gp, gs4, 0, P);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        SPIM_BARRIER();          // the only CTA-wide barrier of the tile
-#if defined(SPIM_HOST_EMU)
-        for (int w = 0; w < TP / WP; ++w) warp_work(p, 0, 1, w * WP, tile, g, base);
-#else
-        const int warp = threadIdx.x >> 5;
-        if (warp < TP / WP) warp_work(p, threadIdx.x & 31, 32, warp * WP, tile, g, base);
-#endif
-    }
-};
-
-// ---------------------------------------------------------------------------------------------
 // XFwd: real lines -> half spectrum (R2C via one complex FFT of length Px/2 + split step)
 // Tile = [Px/2 rows][16 lines]; line pair bp of row r lives in float4 slot (bp + r) & 7.
 // ---------------------------------------------------------------------------------------------
@@ -802,14 +671,16 @@ SPIM_DEV void xfwd_stage0(const XFwdParams& p, float4* tile, const long long* sr
                 a[q] = lo2(v); b[q] = hi2(v);
             }
         }
-        dft<R, false>(a);
-        dft<R, false>(b);
+        C2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = c2_from_ab(a[q], b[q]);
+        dft<R, false>(x);
         // twiddles are fetched on use here: holding them across the loads and the butterfly costs the fourth resident block
-        apply_twiddles2<R, false>(a, b, twp + m * (R - 1));     // M == 1: a table of ones
+        apply_twiddles_c2<R, false>(x, twp + m * (R - 1));     // M == 1: a table of ones
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
-            tile[row * TP + ((bp + row) & (TP - 1))] = pack4(a[q], b[q]);
+            tile[row * TP + ((bp + row) & (TP - 1))] = c2_to_pk(x[q]);      // packed tile (stage_tile)
         }
     }
     SPIM_BARRIER();
@@ -837,6 +708,24 @@ SPIM_DEV void split_inv(float2 A, float2 B, float2 w, float2& zk, float2& zm) {
     zm = make_float2(s.x + t.y, -s.y + t.x);
 }
 
+// the same two steps on a packed pair (both lines of a pair share w)
+SPIM_DEV void split_fwd(C2 zk, C2 zm, float2 w, C2& xk, C2& xm) {
+    C2 s, d;
+    s.re = p2add(zk.re, zm.re); s.im = p2sub(zk.im, zm.im);
+    d.re = p2sub(zk.re, zm.re); d.im = p2add(zk.im, zm.im);
+    const C2 t = cmul_s(d, w.x, w.y);
+    xk.re = p2add(s.re, t.im); xk.im = p2sub(s.im, t.re);
+    xm.re = p2sub(s.re, t.im); xm.im = p2sub(p2neg(s.im), t.re);
+}
+SPIM_DEV void split_inv(C2 A, C2 B, float2 w, C2& zk, C2& zm) {
+    C2 s, d;
+    s.re = p2add(A.re, B.re); s.im = p2sub(A.im, B.im);
+    d.re = p2sub(A.re, B.re); d.im = p2add(A.im, B.im);
+    const C2 t = cmulc_s(d, w.x, w.y);
+    zk.re = p2sub(s.re, t.im); zk.im = p2add(s.im, t.re);
+    zm.re = p2add(s.re, t.im); zm.im = p2sub(t.re, s.im);
+}
+
 // forward split step of one tile: half spectrum of 16 real lines from the 8 complex transforms of their pairs (factor
 // 1/2 folded into the kernel scale).  One item = one frequency pair (k, N2 - k) of FOUR line pairs, see xinv_presplit.
 SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2) {
@@ -860,16 +749,15 @@ SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long lon
         for (int g = 0; g < 4; ++g) {
             const int bp = h * 4 + g;
             const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
-            float2 xk, xm;
+            C2 xk, xm;
+            split_fwd(c2_from_pk(zk[g]), c2_from_pk(zm[g]), w, xk, xm);      // the tile is packed (stage_tile)
             if (d0 >= 0) {
-                split_fwd(lo2(zk[g]), lo2(zm[g]), w, xk, xm);
-                p.spec[d0 + k] = xk;
-                if (two) p.spec[d0 + km] = xm;
+                p.spec[d0 + k] = c2_a(xk);
+                if (two) p.spec[d0 + km] = c2_a(xm);
             }
             if (d1 >= 0) {
-                split_fwd(hi2(zk[g]), hi2(zm[g]), w, xk, xm);
-                p.spec[d1 + k] = xk;
-                if (two) p.spec[d1 + km] = xm;
+                p.spec[d1 + k] = c2_b(xk);
+                if (two) p.spec[d1 + km] = c2_b(xm);
             }
         }
     }
@@ -917,7 +805,7 @@ struct XFwd {
         else { SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR, false>(p, tile, srcoff))) }
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
-        for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
+        for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
         xfwd_split(p, tile, dstoff, N2);
         // zero the pad columns [N2+1, pitch)
         const int npad = p.pitch - (N2 + 1);
@@ -997,13 +885,15 @@ SPIM_DEV void xfwdt_stage0(const XFwdParams& p, float4* tile, const float* stg, 
         float2 a[R], b[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) { a[q] = l0[q * M]; b[q] = l1[q * M]; }
-        dft<R, false>(a);
-        dft<R, false>(b);
-        apply_twiddles2<R, false>(a, b, twp + m * (R - 1));     // M == 1: a table of ones
+        C2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = c2_from_ab(a[q], b[q]);
+        dft<R, false>(x);
+        apply_twiddles_c2<R, false>(x, twp + m * (R - 1));     // M == 1: a table of ones
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
-            tile[row * TP + ((bp + row) & (TP - 1))] = pack4(a[q], b[q]);
+            tile[row * TP + ((bp + row) & (TP - 1))] = c2_to_pk(x[q]);      // packed tile (stage_tile)
         }
     }
 }
@@ -1085,7 +975,7 @@ struct XFwdT {
 #endif
             SPIM_BARRIER();
             if (i + q.nslot < ntl) issue(q, bid + (i + q.nslot) * q.nctas, slot, stg, dsto, full);
-            for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g);
+            for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
             xfwd_split(p, tile, dcur, N2);
             const int npad = p.pitch - (N2 + 1);
             SPIM_FOR_ITEMS(k, npad * TC) {
@@ -1168,8 +1058,6 @@ struct XInvParams {
     double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
     unsigned int* stat_max;    // max |change| as float bits
     int vec_ok;                // float2 accesses to dst / img / weight allowed and nx even
-    int reverse;               // tiles of lines taken from the last to the first (serpentine sweep order, SPIM_SERPENTINE)
-    int nblocks;
 };
 
 struct EpiAcc { double sum; float mx; };
@@ -1382,7 +1270,8 @@ SPIM_DEV void stats_commit(const XInvParams& p, float2* tile, EpiAcc& acc) {
 // One item = one frequency pair (k, N2 - k) of FOUR line pairs: the table lookups (pos[], twiddle) and the index split
 // are paid once per item, and 16 spectrum loads per thread are in flight before the first is consumed.
 constexpr int XG = 4;     // line pairs per split-step item
-SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* srcoff, int N2) {
+// dst_p: the tile is written packed (further stages follow) or interleaved (single-stage plan: stage 0 reads it directly)
+SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* srcoff, int N2, int dst_p) {
     const int nk = p.nk;
     SPIM_FOR_ITEMS(i, nk * (TP / XG)) {
         const int h = fastdiv(i, p.magic_nk);
@@ -1404,21 +1293,17 @@ SPIM_DEV void xinv_presplit(const XInvParams& p, float4* tile, const long long* 
 #pragma unroll
         for (int g = 0; g < XG; ++g) {
             const int bp = h * XG + g;
-            float2 zk0, zm0, zk1, zm1;
-            split_inv(A0[g], B0[g], w, zk0, zm0);
-            split_inv(A1[g], B1[g], w, zk1, zm1);
-            tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
-            if (two) tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
+            C2 zk, zm;
+            split_inv(c2_from_ab(A0[g], A1[g]), c2_from_ab(B0[g], B1[g]), w, zk, zm);
+            tile[rk * TP + ((bp + rk) & (TP - 1))] = dst_p ? c2_to_pk(zk) : c2_to_il(zk);
+            if (two) tile[rm * TP + ((bp + rm) & (TP - 1))] = dst_p ? c2_to_pk(zm) : c2_to_il(zm);
         }
     }
 }
 
-// R0MAX: largest radix the register-resident last stage (plan.radix[0]) is compiled for.  The epilogue keeps 8 R floats per
-// item in registers (spectrum row, two prefetched inputs, twiddles), so an instantiation for R0MAX = 5 is much leaner than
-// the general one; the host only selects it when the x plan starts with a radix <= R0MAX (SPIM_XPLAN_ASC orders it so).
 // FUSE: brick mode with connected peers -- the epilogue also stores every voxel a neighbour's halo needs straight into that
 // neighbour's buffer (HaloFuse above); the host selects it only when the vectorised epilogue applies.
-template <int EPI, int MATH, int R0MAX = 16, bool FUSE = false>
+template <int EPI, int MATH, bool FUSE = false>
 struct XInvT {
     typedef XInvParams Params;
     static constexpr bool kEmuThreads = true;
@@ -1432,7 +1317,6 @@ struct XInvT {
         long long* auxoff = dstoff + TC;
         float2** fptr = reinterpret_cast<float2**>(auxoff + TC);                   // FUSE: [TC][kFuseCombos][kFuseSlots]
         int* fnc = reinterpret_cast<int*>(fptr + TC * kFuseCombos * kFuseSlots);   // FUSE: combos in use per line
-        if (p.reverse) bid = p.nblocks - 1 - bid;
         SPIM_FOR_ITEMS(b, TC) {
             const long long l = (long long)bid * TC + b;
             long long so = -1, d_o = -1, a_o = -1;
@@ -1449,193 +1333,20 @@ struct XInvT {
             if (FUSE) fnc[b] = nc;
         }
         SPIM_BARRIER();
-        xinv_presplit(p, tile, srcoff, N2);
+        xinv_presplit(p, tile, srcoff, N2, pl.nstages > 1);
         SPIM_BARRIER();
         GRows g;
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
-        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
+        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g, 1, s > 1);   // stage 0 reads single lines: interleaved
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;
         if (FUSE) {
             const int nlo2 = (p.fuse->whi[2] + 1) >> 1;              // pairs (2n, 2n+1) that reach into x < whi
             const int nhi2 = (p.nx - p.fuse->wlo[2]) >> 1;           // ... into x >= nx - wlo
-            SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
+            SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
         }
-        else if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
-        else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
-        if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
-    }
-};
-
-// ---------------------------------------------------------------------------------------------
-// XInvP: the x-inverse pass as a persistent, TMA-fed pipeline (the default; XInvT remains for unaligned buffers and brick
-// sessions with the fused halo push).  The 16 spectrum lines of a tile are whole contiguous rows of `pitch` float2: each is
-// fetched by one bulk copy (UBLKCP) into a line-major staging slot while the previous tile is still being transformed; the
-// C2R pre-step reads the slot (conflict-free 8-byte accesses along k) instead of issuing 16 global loads per item, and the
-// rows of the epilogue inputs (observed image, or psi and weight) are pulled into L2 by bulk prefetches issued when the tile
-// starts, three shared-memory stages before the epilogue loads them.  Change statistics are accumulated over all tiles of a
-// CTA and committed once.
-// ---------------------------------------------------------------------------------------------
-struct XInvPParams {
-    XInvParams x;
-    int ntiles, nctas, nslot;
-    unsigned row_bytes;        // pitch * 8
-    int prefetch;              // bulk L2 prefetch of the epilogue input rows
-};
-
-SPIM_DEV void xinvp_presplit(const XInvParams& p, float4* tile, const float2* stg, int N2) {
-    const int nk = p.nk;
-    const int LSP = p.pitch;
-    SPIM_FOR_ITEMS(i, nk * (TP / XG)) {
-        const int h = fastdiv(i, p.magic_nk);
-        const int k = i - h * nk;
-        const int km = N2 - k;
-        const float2 w = spim_ldg(p.wx + k);
-        const int rk = spim_ldg(p.pos + k);
-        const int rm = spim_ldg(p.pos + (k == 0 ? 0 : km));
-        const bool two = (k != 0) && (km != k);
-        const float2* l = stg + (size_t)(h * XG * 2) * LSP;
-#pragma unroll
-        for (int g = 0; g < XG; ++g) {
-            const int bp = h * XG + g;
-            const float2 A0 = l[k], B0 = l[km], A1 = l[LSP + k], B1 = l[LSP + km];
-            l += 2 * LSP;
-            float2 zk0, zm0, zk1, zm1;
-            split_inv(A0, B0, w, zk0, zm0);
-            split_inv(A1, B1, w, zk1, zm1);
-            tile[rk * TP + ((bp + rk) & (TP - 1))] = pack4(zk0, zk1);
-            if (two) tile[rm * TP + ((bp + rm) & (TP - 1))] = pack4(zm0, zm1);
-        }
-    }
-}
-
-// FUSE: brick mode with connected peers -- the epilogue also stores every voxel a neighbour's halo needs straight into that
-// neighbour's buffer (HaloFuse above); the host selects it only when the vectorised epilogue applies
-template <int EPI, int MATH, int R0MAX = 16, bool FUSE = false>
-struct XInvP {
-    typedef XInvPParams Params;
-    static constexpr bool kEmuThreads = true;
-    static constexpr int MAXSLOT = 3;
-    SPIM_DEV static void issue(const Params& q, int t, int slot, float2* stg, uint64_t* full) {
-        const XInvParams& p = q.x;
-#if defined(SPIM_HOST_EMU)
-        (void)full;
-        SPIM_FOR_ITEMS(b, TC) {
-            const long long l = (long long)t * TC + b;
-            if (l < p.nlines) {
-                const int z = (int)(l / p.ny);
-                const int y = (int)(l - (long long)z * p.ny);
-                memcpy(stg + ((size_t)slot * TC + b) * p.pitch, p.spec + ((long long)z * p.Py + y) * (long long)p.pitch, q.row_bytes);
-            }
-        }
-#else
-        if (threadIdx.x < 32) {
-            const int b = (int)threadIdx.x;
-            const long long l = (long long)t * TC + b;
-            const bool live1 = b < TC && l < p.nlines;
-            const unsigned live = __ballot_sync(0xffffffffu, live1);
-            if (b == 0) mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes);
-            __syncwarp();
-            if (live1) {
-                const int z = (int)(l / p.ny);
-                const int y = (int)(l - (long long)z * p.ny);
-                bulk_g2s(stg + ((size_t)slot * TC + b) * p.pitch, p.spec + ((long long)z * p.Py + y) * (long long)p.pitch, q.row_bytes, full + slot);
-                if (q.prefetch && EPI != EPI_STORE) {
-                    // epilogue inputs of the same tile -> L2 (rows of nx floats)
-                    const long long d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
-                    const long long a_o = ((long long)z * p.ny + y) * (long long)p.nx;
-                    if (EPI == EPI_RATIO) bulk_prefetch_l2(p.img + a_o, p.nx);
-                    else {
-                        bulk_prefetch_l2(p.dst + d_o, p.nx);
-                        if (p.weight) bulk_prefetch_l2(p.weight + a_o, p.nx);
-                    }
-                }
-            }
-        }
-#endif
-    }
-    // One tile.  (Every register array of a phase must be defined unconditionally: a definition under a predicate, like the
-    // stage-0 twiddles once were for M > 1, keeps its registers live around the whole persistent loop -- for every radix path
-    // at once, 255 registers and spills instead of 80.)
-    SPIM_DEV static void tile_body(const Params& q, int t, int nxt, int slot, unsigned parity, float2* tile2, float2* stg,
-                                     long long* dstoff, long long* auxoff, uint64_t* full, EpiAcc& acc_out, float2** fptr, int* fnc) {
-        const XInvParams& p = q.x;
-        const TG tg = tg_cta();
-        float4* tile = reinterpret_cast<float4*>(tile2);
-        const FftPlanDev& pl = p.plan;
-        const int N2 = pl.n;
-        GRows g;
-        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
-        SPIM_FOR_ITEMS(b, TC) {
-            const long long l = (long long)t * TC + b;
-            long long d_o = -1, a_o = -1;
-            int nc = 0;
-            if (l < p.nlines) {
-                const int z = (int)(l / p.ny);
-                const int y = (int)(l - (long long)z * p.ny);
-                d_o = ((long long)(z + p.doz) * p.dsy + (y + p.doy)) * (long long)p.dsx + p.dox;
-                a_o = ((long long)z * p.ny + y) * (long long)p.nx;
-                if (FUSE) nc = fuse_line_targets(*p.fuse, z, y, d_o, fptr + b * kFuseCombos * kFuseSlots);
-            }
-            dstoff[b] = d_o; auxoff[b] = a_o;
-            if (FUSE) fnc[b] = nc;
-        }
-#if !defined(SPIM_HOST_EMU)
-        mbar_wait(full + slot, parity);
-#else
-        (void)parity;
-#endif
-        xinvp_presplit(p, tile, stg + (size_t)slot * TC * p.pitch, N2);
-#if !defined(SPIM_HOST_EMU)
-        fence_proxy_async();
-#endif
-        SPIM_BARRIER();
-        if (nxt >= 0) issue(q, nxt, slot, stg, full);
-        for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g);
-        EpiAcc acc;
-        acc.sum = 0.0; acc.mx = 0.f;
-        if (FUSE) {
-            const int nlo2 = (p.fuse->whi[2] + 1) >> 1;              // pairs (2n, 2n+1) that reach into x < whi
-            const int nhi2 = (p.nx - p.fuse->wlo[2]) >> 1;           // ... into x >= nx - wlo
-            SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true, true>(p, tile2, auxoff, dstoff, acc, fptr, fnc, nlo2, nhi2)))
-        }
-        else if (p.vec_ok) { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
-        else { SPIM_RADIX_SWITCH_MAX(pl.radix[0], R0MAX, (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
-        if (EPI == EPI_UPDATE) { acc_out.sum += acc.sum; acc_out.mx = fmaxf(acc_out.mx, acc.mx); }
-        SPIM_BARRIER();            // the tile and the offset arrays are free for the next round
-    }
-    SPIM_DEV static void run(const Params& q, int bid, float2* tile2) {
-        const XInvParams& p = q.x;
-        const FftPlanDev& pl = p.plan;
-        const int N2 = pl.n;
-        float2* stg = tile2 + (size_t)N2 * TC;                                                   // [nslot][TC][pitch]
-        long long* dstoff = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * p.pitch);
-        long long* auxoff = dstoff + TC;
-        uint64_t* full = reinterpret_cast<uint64_t*>(auxoff + TC);
-        float2** fptr = reinterpret_cast<float2**>(full + MAXSLOT);                // FUSE: [TC][kFuseCombos][kFuseSlots]
-        int* fnc = reinterpret_cast<int*>(fptr + TC * kFuseCombos * kFuseSlots);   // FUSE: combos in use per line
-        const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
-#if !defined(SPIM_HOST_EMU)
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < q.nslot; ++s) mbar_init(full + s, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-#endif
-        // tile of round i: bid, bid + nctas, ... (from the last tile downwards in the serpentine order)
-        const int t0 = p.reverse ? q.ntiles - 1 - bid : bid;
-        const int dt = p.reverse ? -q.nctas : q.nctas;
-#define tile_at(i) (t0 + (i) * dt)
-        for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, tile_at(j), j, stg, full);
-        SPIM_BARRIER();
-        EpiAcc acc;
-        acc.sum = 0.0; acc.mx = 0.f;
-        for (int i = 0; i < ntl; ++i) {
-            const int slot = i % q.nslot;
-            const int nxt = (i + q.nslot < ntl) ? tile_at(i + q.nslot) : -1;
-            tile_body(q, tile_at(i), nxt, slot, (unsigned)((i / q.nslot) & 1), tile2, stg, dstoff, auxoff, full, acc, fptr, fnc);
-        }
-#undef tile_at
+        else if (p.vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, true>(p, tile2, auxoff, dstoff, acc))) }
+        else { SPIM_RADIX_SWITCH(pl.radix[0], (xinv_stage0<RR, EPI, MATH, false>(p, tile2, auxoff, dstoff, acc))) }
         if (EPI == EPI_UPDATE) stats_commit(p, tile2, acc);
     }
 };

@@ -327,15 +327,17 @@ def test_multi_device_block_queue_of_the_view_classes(emu_lib):
         _ViewFFT.cuda = saved
 
 
-def test_serpentine_sweep_order(emu_lib, monkeypatch):
-    """SPIM_SERPENTINE=1: the y-forward and x-inverse passes take their tiles from the last to the first (L2 reuse between
-    consecutive sweeps); the order of independent tiles must not change a single bit of the result."""
+def test_column_staging_modes_are_bit_identical(emu_lib, monkeypatch):
+    """SPIM_COLP selects how a column tile reaches shared memory (0 first stage from global memory, 2 one-shot staging,
+    3 persistent pipeline) and SPIM_COL_NARROW its width: none of them may change a single bit of the result."""
     shape = (14, 18, 22)
     _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
     a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    monkeypatch.setenv("SPIM_SERPENTINE", "1")
-    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    assert np.array_equal(a, b)
+    for colp in ("0", "2", "3"):
+        monkeypatch.setenv("SPIM_COLP", colp)
+        b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+        assert np.array_equal(a, b), colp
+    monkeypatch.delenv("SPIM_COLP")
     P.conv_case(emu_lib, (9, 7, 11), (3, 5, 3), 2)
     P.golden_case(emu_lib, 1, 1)
     monkeypatch.setenv("SPIM_COL_NARROW", "1")
@@ -343,35 +345,9 @@ def test_serpentine_sweep_order(emu_lib, monkeypatch):
     assert np.array_equal(a, c)
 
 
-def test_ascending_x_plan_and_lean_update_kernel(emu_lib, monkeypatch):
-    """SPIM_XPLAN_ASC=1 orders the x plan smallest radix first (stage 0 is the register-resident stage of the x kernels);
-    SPIM_XINV_R0=1 then runs the update from the instantiation compiled for small stage-0 radices.  Same arithmetic per
-    butterfly, different factor order: results agree with the default to round-off and meet the same parity bar."""
-    shape = (14, 18, 22)
-    _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
-    a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    monkeypatch.setenv("SPIM_XPLAN_ASC", "1")
-    monkeypatch.setenv("SPIM_XINV_R0", "1")
-    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    per, l2 = O.parity_errors(b, a)
-    assert per <= 2e-5 and l2 <= 2e-6, (per, l2)
-    P.decon_case(emu_lib, (14, 18, 22), 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
-    P.decon_case(emu_lib, (9, 11, 13), 2, 3, O.INDEPENDENT, 2, 2, lam=0.0, use_weights=False)
-    for n in (20, 30, 42, 56, 60, 70, 84, 100, 120, 140):          # x plans with several stages: 10 = 2*5 ... 70 = 2*5*7
-        P.legacy_case(emu_lib, (4, 4, n), (3, 3, 3), seed=n)
-    for ext in range(5):
-        P.conv_case(emu_lib, (5, 30, 33), (1, 7, 9), ext)
-
-
-def test_lean_column_pass_for_small_radix_plans(emu_lib, monkeypatch):
-    """SPIM_COL_LEAN=1: column plans without radices 9 / 10 run from the instantiation compiled for radices <= 8 (same
-    butterflies, fewer registers); plans that do need them keep the general kernel.  Bit-identical results."""
-    shape = (14, 18, 22)
-    _, imgs, ws, psfs = __import__("spim_registration_b200").synthetic.make_dataset(shape, 3, 5, kind="beads")
-    a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    monkeypatch.setenv("SPIM_COL_LEAN", "1")
-    b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    assert np.array_equal(a, b)
+def test_lean_column_pass_for_small_radix_plans(emu_lib):
+    """Small column tiles of plans without radices 9 / 10 run from the instantiation compiled for radices <= 8 (same
+    butterflies, fewer registers); plans that do need them keep the general kernel."""
     for n in (16, 24, 28, 36, 48, 56, 64, 72, 84, 96, 112, 128, 144, 288,      # radices <= 8 only
               18, 20, 30, 50, 90, 100, 560):                                   # plans with 9 / 10: general kernel
         for shp in ((n, 4, 8), (4, n, 8)):

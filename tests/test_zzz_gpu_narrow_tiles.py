@@ -68,41 +68,32 @@ def test_configs2_size_on_one_gpu_delta_identity_and_shift(gpu):
     assert np.abs(out[:5] - a[5:0:-1]).max() < 5e-6       # mirror-single at the low z face
 
 
-def test_serpentine_sweep_order_is_bit_identical(gpu, monkeypatch):
-    """SPIM_SERPENTINE=1 only changes the order in which independent tiles are taken (L2 reuse between sweeps)."""
+def test_column_staging_modes_are_bit_identical(gpu, monkeypatch):
+    """SPIM_COLP (0 first stage from global memory, 2 one-shot cp.async staging, 3 persistent TMA pipeline) only changes how
+    a column tile reaches shared memory."""
     import numpy as np
     from spim_registration_b200 import synthetic
     shape = (40, 48, 56)
     _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 7, kind="beads")
     a, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    monkeypatch.setenv("SPIM_SERPENTINE", "1")
-    b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    assert np.array_equal(a, b)
+    for colp in ("0", "2", "3"):
+        monkeypatch.setenv("SPIM_COLP", colp)
+        b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
+        assert np.array_equal(a, b), colp
 
 
-def test_ascending_x_plan_and_lean_update_kernel(gpu, monkeypatch):
-    """SPIM_XPLAN_ASC=1 + SPIM_XINV_R0=1: x plan smallest radix first and the register-lean update kernel (80 registers, six
-    blocks per SM); same parity bar as the default."""
-    monkeypatch.setenv("SPIM_XPLAN_ASC", "1")
-    monkeypatch.setenv("SPIM_XINV_R0", "1")
-    P.decon_case(gpu, (40, 48, 56), 3, 7, O.EFFICIENT_BAYESIAN, 2, 3)
-    P.decon_case(gpu, (33, 41, 50), 2, 5, O.OPTIMIZATION_I, 1, 2)
-    P.decon_case(gpu, (16, 20, 524), 2, 31, O.EFFICIENT_BAYESIAN, 2, 2)      # x FFT length 560: N2 = 280 = 5 * 7 * 8, the bench plan
+def test_bench_plan_x_lines(gpu):
+    """x FFT length 560 (N2 = 280 = 8 * 7 * 5, the bench plan) and 1080 (N2 = 540 = 10 * 9 * 6, the 1024-wide volume on one
+    GPU) through the TMA-fed x-forward kernel and both x-inverse block sizes."""
+    P.decon_case(gpu, (16, 20, 524), 2, 31, O.EFFICIENT_BAYESIAN, 2, 2)
+    P.decon_case(gpu, (12, 18, 1040), 2, 31, O.OPTIMIZATION_II, 2, 2)
     for ext in range(5):
         P.conv_case(gpu, (40, 50, 70), (7, 9, 5), ext)
 
 
-def test_lean_column_pass_is_bit_identical(gpu, monkeypatch):
-    """SPIM_COL_LEAN=1: plans without radices 9 / 10 (the 288-point z axis of the bench volume) from the instantiation compiled
-    for radices <= 8 -- 80 registers, six resident blocks; the butterflies are the same code, so is every bit of the result."""
-    import numpy as np
-    from spim_registration_b200 import synthetic
-    shape = (40, 48, 56)
-    _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 7, kind="beads")
-    a, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    monkeypatch.setenv("SPIM_COL_LEAN", "1")
-    b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, 2, 3)
-    assert np.array_equal(a, b)
+def test_lean_column_pass(gpu):
+    """Small tiles of plans without radices 9 / 10 (the 288-point z axis of the bench volume) run from the instantiation
+    compiled for radices <= 8 -- 80 registers, six resident blocks."""
     for n in (48, 64, 96, 128, 288):
         for shp in ((n, 4, 8), (4, n, 8)):
             P.legacy_case(gpu, shp, (3, 3, 3), seed=n)
