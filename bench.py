@@ -292,10 +292,10 @@ def fusion_prestep_leg(shape, views, peak, lib=None, timed=None, stack_planes=No
 # CUDA events).  The first entry is the control: the default configuration in the very same harness.
 VARIANTS = [
     ("default", {}),
-    ("x_kernels_without_tma", {"SPIM_XFWD_TMA": "0", "SPIM_XINV_TMA": "0"}),   # the round-1 x kernels (plain loads, one tile per block)
+    ("x_forward_without_tma", {"SPIM_XFWD_TMA": "0"}),             # plain-load x-forward kernel instead of the TMA-fed pipeline
     ("ieee_epilogue", {"SPIM_FAST_EPI": "0"}),                     # IEEE division / sqrt instead of the branch-free refinement
-    ("y_passes_cp_async", {"SPIM_COLP_Y": "2"}),                   # y passes with one-shot cp.async staging instead of the TMA pipeline
-    ("no_pdl", {"SPIM_PDL": "0"}),                                 # without programmatic dependent launch
+    ("column_passes_cp_async", {"SPIM_COLP": "2"}),                # y passes with one-shot cp.async staging instead of the TMA pipeline
+    ("literal_constant_extension", {"SPIM_CONST_SHIFT": "0"}),     # gen-2 conv2 transforms its constant halo instead of shifting it away
 ]
 
 

@@ -139,7 +139,7 @@ struct FftPlanHost {
 //                     TMA / mbarrier pipeline; unset = 3 for large tiles (y passes of the bench volume), 2 for small ones
 //   SPIM_COL_NARROW=0|1  force 16- / 8-column tiles (unset: narrow where a 16-column tile leaves one block per SM)
 //   SPIM_FAST_EPI=0|1    override mvd_params.fast_epilogue
-//   SPIM_PDL=0           plain launches instead of programmatic dependent launch (runtime.h)
+//   SPIM_CONST_SHIFT=0   gen-2 conv2 with the literal constant extension instead of zero extension of (ratio - 1) (spim_b200.cu)
 inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -178,6 +178,8 @@ struct EpiDesc {            // what XInv does with the result
     double lambda = 0.0;
     float min_value = 1e-4f;
     int gen2_quotient = 1;
+    float ratio_offset = 0.f;     // EPI_RATIO: added to the stored quotient
+    float blur_offset = 0.f;      // EPI_UPDATE: added to the convolution result
     int exact_tikhonov = 0;
     int fast_epilogue = 1;
     double* stat_sum = nullptr;
@@ -282,7 +284,7 @@ public:
 
     // fix-up list of the TMA-fed x-forward kernel (XFwdT): every padded position whose value is not already where the bulk
     // copy of the array row puts it (staging index ox + u): {ox + u, source index | -1 zero gap | -2 constant}
-    struct XFix { int2* d = nullptr; int n = 0; };
+    struct XFix { int2* d = nullptr; int n = 0; int ndyn = 0; };
     std::map<XKey, XFix> xfixes;
     XFix x_fix_table(int nx, int hp, int hm, int sx, int ox, int ext, int vlo, int vhi, rt::Stream st) {
         const XKey key{nx, hp, hm, sx, ox, ext, vlo, vhi};
@@ -302,7 +304,11 @@ public:
             }
             if (i != ox + u) { int2 e; e.x = ox + u; e.y = i; f.push_back(e); }
         }
+        // entries that copy data first; constants written to cells beyond the row copy (index >= sx) last: those survive from
+        // tile to tile in the staging slot and are applied once
+        std::stable_partition(f.begin(), f.end(), [sx](const int2& e) { return !(e.y < 0 && e.x >= sx); });
         XFix r;
+        r.ndyn = (int)std::count_if(f.begin(), f.end(), [sx](const int2& e) { return !(e.y < 0 && e.x >= sx); });
         r.n = (int)f.size();
         r.d = (int2*)rt::dmalloc(sizeof(int2) * std::max<size_t>(1, f.size()));
         if (!f.empty()) rt::h2d(r.d, f.data(), sizeof(int2) * f.size(), st);
@@ -370,6 +376,8 @@ public:
                 const int bps = (int)std::min<size_t>(3, lim / (sm + 1024));
                 q.fix = fx_.d; q.nfix = fx_.n;
                 q.magic_nfix = magic_for(std::max(1, fx_.n));
+                q.nfix_dyn = fx_.ndyn;
+                q.magic_nfix_dyn = magic_for(std::max(1, fx_.ndyn));
                 q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
                 q.const_row = const_row(p.sx, q.cval, st);
                 q.nslot = 1;
@@ -491,6 +499,7 @@ public:
         p.doz = e.dst_origin[0]; p.doy = e.dst_origin[1]; p.dox = e.dst_origin[2];
         p.epi = e.epi; p.img = e.img; p.weight = e.weight; p.const_weight = e.const_weight;
         p.lambda = e.lambda; p.min_value = e.min_value; p.gen2_quotient = e.gen2_quotient;
+        p.ratio_offset = e.ratio_offset; p.blur_offset = e.blur_offset;
         p.two_lambda = (float)(2.0 * e.lambda);
         p.exact_tikhonov = e.exact_tikhonov;
         static int fast_env = env_int("SPIM_FAST_EPI", -1);      // A/B switch for the benchmarks: 0 / 1 override the parameter
@@ -504,15 +513,17 @@ public:
         if (timer) timer->begin(xinv_id, st);
         // Block size: small tiles (<= 36 KB: five / six blocks per SM) run 128 threads, larger ones (three or fewer blocks per
         // SM) 256 -- measured on the 540-point lines of the 1024^2 x 512 volume: 2.16 ms with 256 threads, 2.41 with 128.
-        // The register-capped instantiations keep six (ratio, 80 registers) / five (update, 96 registers) 128-thread blocks
-        // resident on the small tiles (update: 0.300 vs 0.336 ms uncapped).  A TMA-fed persistent variant of this kernel was
+        // The register-capped instantiations keep four 192-thread (ratio, 80 registers) / five 128-thread (update, 96 registers)
+        // blocks resident on the small tiles (update: 0.300 vs 0.336 ms uncapped).  A TMA-fed persistent variant of this kernel was
         // built and measured in round 2 (0.325 vs 0.300 ms average) and removed again: its staging slot halves the resident blocks.
         const bool small = smem <= 37 * 1024;
         const int T = small ? 128 : 256;
         if (e.epi == EPI_STORE) rt::launch<XInvStore>(p, grid, T, smem, st);
         else if (e.epi == EPI_RATIO) {
             if (p.fast_epilogue) {
-                if (small) rt::launch<XInvRatioFast, 128, 6>(p, grid, T, smem, st);
+                // four 192-thread blocks per SM: 8192 tiles of the bench volume are 13.8 waves of 592 blocks (0.213 ms) where six
+                // 128-thread blocks are 9.2 waves of 888 with a nearly empty tenth (0.236 ms)
+                if (small) rt::launch<XInvRatioFast, 192, 4>(p, grid, 192, smem, st);
                 else rt::launch<XInvRatioFast>(p, grid, T, smem, st);
             } else {
                 if (small) rt::launch<XInvRatioIeee, 128, 6>(p, grid, T, smem, st);
@@ -561,9 +572,20 @@ public:
     void convolve(const SrcDesc& src, const float2* khat, const EpiDesc& e, rt::Stream st) {
         Geom g;
         for (int d = 0; d < 3; ++d) { g.n[d] = n[d]; g.hp[d] = hp[d]; g.hm[d] = hm[d]; }
+        if (src.ext == EXT_ZERO) {
+            // zero extension: a halo that the source array does not provide as data is all zeros -- it joins the gap, and the
+            // forward sweeps neither transform its lines and planes nor load its rows
+            for (int d = 0; d < 3; ++d) {
+                const int bit = 1 << d;
+                const bool lo = (src.halo_lo & bit) && src.origin[d] >= hm[d];
+                const bool hi = (src.halo_hi & bit) && src.dims[d] - src.origin[d] - n[d] >= hp[d];
+                if (!lo) g.hm[d] = 0;
+                if (!hi) g.hp[d] = 0;
+            }
+        }
         x_forward(src, g, spec, st);
-        const int LZ = n[0] + hp[0] + hm[0];
-        col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + hp[0], LZ, P[0], st);
+        const int LZ = n[0] + g.hp[0] + g.hm[0];
+        col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + g.hp[0], LZ, P[0], st);
         col_pass(K_ZMID, spec, khat, 0, COL_MID, g, n[0], P[1], P[1], P[1], st);
         col_pass(K_YINV, spec, nullptr, 1, COL_INV, g, n[1], n[0], n[0], P[0], st);
         x_inverse(spec, e, st);

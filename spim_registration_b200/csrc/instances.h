@@ -22,7 +22,7 @@ typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
 #define SPIM_INSTANCES_COL_C(X) X(ColPassNarrow, 256, 1) X(ColPassNarrow, 128, 5)
 #define SPIM_INSTANCES_COL_D(X) X(ColPassT, 512, 1)
 #define SPIM_INSTANCES_X_A(X) X(XFwd, 192, 4) X(XInvStore, 256, 1)
-#define SPIM_INSTANCES_X_B(X) X(XInvRatioFast, 256, 1) X(XInvRatioFast, 128, 6)
+#define SPIM_INSTANCES_X_B(X) X(XInvRatioFast, 256, 1) X(XInvRatioFast, 192, 4)
 #define SPIM_INSTANCES_X_C(X) X(XInvRatioIeee, 256, 1) X(XInvRatioIeee, 128, 6)
 #define SPIM_INSTANCES_X_D(X) X(XInvUpdateFast, 256, 1) X(XInvUpdateFast, 128, 5)
 #define SPIM_INSTANCES_X_E(X) X(XInvUpdateIeee, 256, 1) X(XInvUpdateExact64, 256, 1)

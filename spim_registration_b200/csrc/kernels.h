@@ -845,6 +845,8 @@ struct XFwdTParams {
     const int2* fix;           // fix-up list: staging[fix.x] = fix.y >= 0 ? staging[fix.y] : (fix.y == -1 ? 0 : cval)
     int nfix;
     uint32_t magic_nfix;       // for item / nfix
+    int nfix_dyn;              // the first nfix_dyn entries copy data (mirrored / halo values): applied to every tile.  The rest
+    uint32_t magic_nfix_dyn;   // write constants (zero gap, out-of-bounds constant) to cells no row copy ever touches: once per slot
 };
 
 // source row of padded line l (nullptr beyond the last line) and its destination offset in the spectrum
@@ -958,14 +960,17 @@ struct XFwdT {
 #if !defined(SPIM_HOST_EMU)
             mbar_wait(full + slot, (unsigned)((i / q.nslot) & 1));
 #endif
-            // fix-ups: halo before the image, out-of-bounds values, zero gap
-            SPIM_FOR_ITEMS(it, TC * q.nfix) {
-                const int b = q.nfix > 1 ? fastdiv(it, q.magic_nfix) : it;
-                const int j = it - b * q.nfix;
-                if (dsto[slot * TC + b] < 0) continue;
-                const int2 f = fixs[j];
-                float* ln = sl + b * q.LS;
-                ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
+            // fix-ups: halo before the image, out-of-bounds values, zero gap (the constant ones only on a slot's first use)
+            {
+                const int nf = i < q.nslot ? q.nfix : q.nfix_dyn;
+                const uint32_t mg = i < q.nslot ? q.magic_nfix : q.magic_nfix_dyn;
+                SPIM_FOR_ITEMS(it, TC * nf) {
+                    const int b = nf > 1 ? fastdiv(it, mg) : it;
+                    const int j = it - b * nf;
+                    const int2 f = fixs[j];
+                    float* ln = sl + b * q.LS;
+                    ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
+                }
             }
             SPIM_FOR_ITEMS(b, TC) dcur[b] = dsto[slot * TC + b];
             SPIM_BARRIER();
@@ -1053,6 +1058,8 @@ struct XInvParams {
     float two_lambda;          // (float)(2*lambda)
     float min_value;
     int gen2_quotient;         // 1: q = img > 0 ? img / blur : 1 ; 0: q = img / blur
+    float ratio_offset;        // EPI_RATIO stores q + ratio_offset (-c when the next convolution extends by the constant c, see engine.h)
+    float blur_offset;         // EPI_UPDATE: added to the convolution result before the update (c * sum of the kernel)
     int exact_tikhonov;        // 1: evaluate (sqrt(1+2 lambda v)-1)/lambda in fp64 exactly like the Java code
     int fast_epilogue;         // 1: MATH_FAST division / square root in the ratio and update epilogues
     double* stat_sum;          // EPI_UPDATE statistics (may be nullptr)
@@ -1108,14 +1115,57 @@ template <int EPI, int MATH>
 SPIM_DEV float epi_one(const XInvParams& p, const EpiFlags& f, float v, float x1, float x2, float& csum, float& cmax) {
     if (EPI == EPI_RATIO) {            // x1 = observed image value; gen-2: q = img > 0 ? img / blur : 1
         const float q = epi_div<MATH>(x1, v);
-        return (f.gen2q && !(x1 > 0.f)) ? 1.f : q;
+        return ((f.gen2q && !(x1 > 0.f)) ? 1.f : q) + p.ratio_offset;
     }
     if (EPI == EPI_UPDATE) {           // x1 = psi (last), x2 = weight
-        const float next = next_value<MATH>(p, f.lam_pos, x1, v);
+        const float next = next_value<MATH>(p, f.lam_pos, x1, v + p.blur_offset);
         const float nw = spim_fadd_rn(x1, spim_fmul_rn(spim_fsub_rn(next, x1), x2));
         const float ch = fabsf(spim_fsub_rn(nw, x1));
         csum += ch;
         cmax = fmaxf(cmax, ch);
+        return nw;
+    }
+    return v;
+}
+
+// The fast epilogue on the two adjacent voxels of a row pair at once: the refinement sequences of fast_math.h on packed
+// pairs (FMUL2 / FFMA2 / FADD2) -- the same operations per component, so the results are bit-identical to epi_one<., MATH_FAST>.
+SPIM_DEV float2 p2_div_from_seed(float2 a, float2 b, float2 r0) {
+    const float2 nb = p2neg(b);
+    const float2 r = p2fma(p2fma(nb, r0, p2bc(1.f)), r0, r0);
+    const float2 q0 = p2mul(a, r);
+    const float2 q1 = p2fma(p2fma(nb, q0, a), r, q0);
+    return p2fma(p2fma(nb, q1, a), r, q1);
+}
+SPIM_DEV float2 p2_sqrt_from_seed(float2 x, float2 y0) {
+    float2 g = p2mul(x, y0), h = p2mul(p2bc(0.5f), y0);
+    const float2 r = p2fma(p2neg(h), g, p2bc(0.5f));
+    g = p2fma(g, r, g);
+    h = p2fma(h, r, h);
+    const float2 d = p2fma(p2neg(g), g, x);
+    return p2fma(d, h, g);
+}
+// v = blurred values, x1 = image (ratio) / psi (update), x2 = weights; s0, s1 = |change| of the two voxels, mx = their maximum
+template <int EPI>
+SPIM_DEV float2 epi_pair_fast(const XInvParams& p, const EpiFlags& f, float2 v, float2 x1, float2 x2, float& s0, float& s1, float& mx) {
+    if (EPI == EPI_RATIO) {
+        const float2 q = p2_div_from_seed(x1, v, make_float2(spim_rcp_seed(v.x), spim_rcp_seed(v.y)));
+        return p2add(make_float2((f.gen2q && !(x1.x > 0.f)) ? 1.f : q.x, (f.gen2q && !(x1.y > 0.f)) ? 1.f : q.y), p2bc(p.ratio_offset));
+    }
+    if (EPI == EPI_UPDATE) {
+        const float2 value = p2mul(x1, p2add(v, p2bc(p.blur_offset)));
+        const float2 t = p2fma(p2bc(p.two_lambda), value, p2bc(1.f));
+        const float2 sq = p2_sqrt_from_seed(t, make_float2(spim_rsqrt_seed(t.x), spim_rsqrt_seed(t.y)));
+        const float2 den = p2add(p2bc(1.f), sq);
+        const float2 tik = p2_div_from_seed(p2add(value, value), den, make_float2(spim_rcp_seed(den.x), spim_rcp_seed(den.y)));
+        float ax = f.lam_pos ? tik.x : value.x, ay = f.lam_pos ? tik.y : value.y;
+        ax = (value.x > 0.f) ? ax : p.min_value;
+        ay = (value.y > 0.f) ? ay : p.min_value;
+        const float2 next = make_float2(fmaxf(p.min_value, ax), fmaxf(p.min_value, ay));
+        const float2 nw = p2add(x1, p2mul(p2sub(next, x1), x2));
+        const float2 ch = p2sub(nw, x1);
+        s0 = fabsf(ch.x); s1 = fabsf(ch.y);
+        mx = fmaxf(s0, s1);
         return nw;
     }
     return v;
@@ -1199,10 +1249,13 @@ SPIM_DEV void xinv_stage0(const XInvParams& p, float2* tile2, const long long* a
                 const int n = m + q * M;
                 // rows beyond the image take part in the arithmetic with benign inputs and are simply not stored / counted
                 float s0 = 0.f, s1 = 0.f, mx = 0.f;
-                const float r0 = epi_one<EPI, MATH>(p, f, a[q].x, x1[q].x, x2[q].x, s0, mx);
-                const float r1 = epi_one<EPI, MATH>(p, f, a[q].y, x1[q].y, x2[q].y, s1, mx);
+                float2 v2;
+                if (MATH == MATH_FAST && EPI != EPI_STORE) v2 = epi_pair_fast<EPI>(p, f, a[q], x1[q], x2[q], s0, s1, mx);
+                else {
+                    v2.x = epi_one<EPI, MATH>(p, f, a[q].x, x1[q].x, x2[q].x, s0, mx);
+                    v2.y = epi_one<EPI, MATH>(p, f, a[q].y, x1[q].y, x2[q].y, s1, mx);
+                }
                 if (n < nh) {
-                    const float2 v2 = make_float2(r0, r1);
                     out[n] = v2;
                     csum += s0; csum += s1;
                     cmax = fmaxf(cmax, mx);

@@ -133,44 +133,24 @@ inline int sm_count() {
     return v;
 }
 
-// Programmatic dependent launch (the default; SPIM_PDL=0 launches plainly): every block first lets the NEXT kernel of the stream start launching
-// and then waits for the PREVIOUS kernel to complete and flush.  The next kernel's blocks become resident in the slots the
-// last wave of this one frees, parked at their own wait, so the tail of one sweep and the ramp-up of the next overlap instead
-// of adding up.  Both instructions are no-ops for a kernel launched without the attribute.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
+// (Programmatic dependent launch was measured in round 2 in two forms -- every block releasing the successor at its start,
+// and only the blocks of the last wave doing so -- and removed: per-kernel times were unchanged and whole iterations 2-7 %
+// slower than with plain launches, because the successor's parked blocks take slots from the predecessor's own tail.)
 template <class Body, int MAXT>
 __global__ void __launch_bounds__(MAXT) kernel_entry(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
-    pdl_prologue();
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
-// experiment hook: MINB blocks of MAXT threads per SM must fit (caps the registers per thread)
+// MINB blocks of MAXT threads per SM must fit (caps the registers per thread)
 template <class Body, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) kernel_entry_capped(const __grid_constant__ typename Body::Params p) {
     extern __shared__ __align__(1024) unsigned char spim_smem[];
-    pdl_prologue();
     Body::run(p, (int)blockIdx.x, reinterpret_cast<float2*>(spim_smem));
 }
 
-inline bool use_pdl() {
-    static int v = [] { const char* e = getenv("SPIM_PDL"); return (e && *e == '0') ? 0 : 1; }();
-    return v != 0;
-}
 template <class K, class P>
 inline void launch_kernel(K kernel, const P& p, unsigned grid, int block, size_t smem, Stream s) {
-    if (!use_pdl()) { kernel<<<grid, block, smem, s>>>(p); return; }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    SPIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+    kernel<<<grid, block, smem, s>>>(p);
 }
 
 // not `inline`: in the split build (instances.h) the engine kernels' launches are declared `extern template`, which only

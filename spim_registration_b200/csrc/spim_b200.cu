@@ -486,6 +486,7 @@ struct mvd_session {
     int kmax[3] = {0, 0, 0};
     long long N = 0;
     std::vector<HostVol> psf, k1, k2;
+    std::vector<double> k2sum;          // sum of each compound kernel (the response of conv2 to the constant 1)
     std::vector<float*> d_img, d_w;
     std::vector<float2*> d_kh1, d_kh2;
     float* d_psi = nullptr;    // dims pdims, origin porigin
@@ -586,6 +587,8 @@ struct mvd_session {
         }
         for (auto& w : small) w->release();
         small.clear();
+        k2sum.assign(V, 0.0);
+        for (int v = 0; v < V; ++v) { double t = 0.0; for (float x : k2[v].v) t += (double)x; k2sum[v] = t; }
     }
 
     ViewPtrs view_ptrs() const {
@@ -670,12 +673,22 @@ struct mvd_session {
         EpiDesc e;
         for (int d = 0; d < 3; ++d) { e.dst_dims[d] = pdims[d]; e.dst_origin[d] = porigin[d]; }
         e.min_value = prm.min_value;
+        // Constant extension of the quotient (gen-2 conv2, value c = 1) without transforming a single halo line: by linearity
+        // conv(ext_c(r), K) = conv(ext_0(r - c), K) + c * sum(K), so conv1's epilogue stores r - c, conv2 runs with ZERO
+        // extension -- the halo outside the volume joins the zero gap of the padded transform -- and the update epilogue adds
+        // c * sum(K2) back.  Neighbour-provided halos (brick mode) carry r - c like the interior.  SPIM_CONST_SHIFT=0 keeps
+        // the literal constant extension (A/B and parity runs).
+        static const bool shift_on = [] { const char* t = getenv("SPIM_CONST_SHIFT"); return !(t && *t == '0'); }();
+        const bool shift = shift_on && conv2_ext() == EXT_CONSTANT;
+        const float cext = 1.f;
         if (ph == 0) {
             src.p = d_psi; src.ext = conv1_ext(); src.ext_value = 0.f;
             e.epi = EPI_RATIO; e.dst = d_tmp; e.img = d_img[v]; e.gen2_quotient = (prm.generation == 2); e.fast_epilogue = prm.fast_epilogue;
+            if (shift) e.ratio_offset = -cext;
             plan.convolve(src, d_kh1[v], e, stream);
         } else {
-            src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = 1.f;
+            src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = cext;
+            if (shift) { src.ext = EXT_ZERO; src.ext_value = 0.f; e.blur_offset = (float)((double)cext * k2sum[v]); }
             e.epi = EPI_UPDATE; e.dst = d_psi; e.weight = d_w[v]; e.const_weight = 1.f;
             e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max; e.exact_tikhonov = prm.exact_tikhonov; e.fast_epilogue = prm.fast_epilogue;
             plan.convolve(src, d_kh2[v], e, stream);
