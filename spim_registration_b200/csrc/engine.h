@@ -14,7 +14,8 @@
 
 namespace spim {
 
-// host-side launch counters (mvd_debug_counter): [0] column passes launched with narrow tiles
+// host-side launch counters (mvd_debug_counter): [0] column passes launched with narrow tiles, [1] convolutions whose
+// forward sweeps ran de-duplicated, [2] convolutions with a dropped (zero) halo
 inline std::atomic<long long>& debug_counter(int i) { static std::atomic<long long> c[4]; return c[i & 3]; }
 
 // x-inverse launches are timed per epilogue: K_XINV = ratio (conv1), K_XINV_UPDATE = update (conv2), K_XINV_STORE = plain store
@@ -140,6 +141,7 @@ struct FftPlanHost {
 //   SPIM_COL_NARROW=0|1  force 16- / 8-column tiles (unset: narrow where a 16-column tile leaves one block per SM)
 //   SPIM_FAST_EPI=0|1    override mvd_params.fast_epilogue
 //   SPIM_CONST_SHIFT=0   gen-2 conv2 with the literal constant extension instead of zero extension of (ratio - 1) (spim_b200.cu)
+//   SPIM_DEDUP=0         forward sweeps transform every padded line / plane instead of only those that exist as data
 inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -248,6 +250,8 @@ public:
         xfixes.clear();
         for (auto& kv : const_rows) rt::dfree(kv.second);
         const_rows.clear();
+        for (auto& kv : dedups) rt::dfree(const_cast<int*>(kv.second.d_dup));
+        dedups.clear();
         d_pos = nullptr; d_wx = nullptr; spec = nullptr; d_kernel = nullptr; kernel_cap = 0;
     }
     size_t spec_bytes() const { return spec_elems * sizeof(float2); }
@@ -316,6 +320,44 @@ public:
         xfixes[key] = r;
         return r;
     }
+    // De-duplicated forward sweeps (mirror / periodic extension): along y and z the halo lines / planes that the source array
+    // does not provide as data are copies of image lines / planes, so the x-forward pass transforms only the lines that exist
+    // and stores each spectrum to its own row and to the halo row that mirrors it, and the forward y pass does the same with
+    // whole planes.  Per axis: U unique coordinates, enumerated [0, split) then the neighbour-provided halo before the image;
+    // dup[u] = padded position of the halo coordinate that maps to u, or -1.
+    struct AxisDedup { bool ok = false; int U = 0, split = 0; const int* d_dup = nullptr; bool any = false; };
+    struct DKey { int n, hp, hm, P, ext, lo, hi; bool operator<(const DKey& o) const {
+        return std::tie(n, hp, hm, P, ext, lo, hi) < std::tie(o.n, o.hp, o.hm, o.P, o.ext, o.lo, o.hi); } };
+    std::map<DKey, AxisDedup> dedups;
+    AxisDedup axis_dedup(int n_, int hp_, int hm_, int P_, int ext, bool data_lo, bool data_hi, rt::Stream st) {
+        const DKey key{n_, hp_, hm_, P_, ext, data_lo ? 1 : 0, data_hi ? 1 : 0};
+        auto it = dedups.find(key);
+        if (it != dedups.end()) return it->second;
+        AxisDedup r;
+        r.split = n_ + (data_hi ? hp_ : 0);
+        r.U = r.split + (data_lo ? hm_ : 0);
+        std::vector<int> dup((size_t)r.U, -1);
+        bool ok = (ext == EXT_MIRROR_SINGLE || ext == EXT_MIRROR_DOUBLE || ext == EXT_PERIODIC);
+        auto add = [&](int b) {           // halo coordinate b is not data: which image coordinate is it a copy of?
+            const int a = ext_map(b, n_, ext);
+            if (a < 0 || a >= n_ || dup[(size_t)a] >= 0) { ok = false; return; }
+            dup[(size_t)a] = b >= 0 ? b : P_ + b;
+            r.any = true;
+        };
+        if (!data_lo) for (int b = -hm_; b < 0 && ok; ++b) add(b);
+        if (!data_hi) for (int b = n_; b < n_ + hp_ && ok; ++b) add(b);
+        r.ok = ok;
+        if (ok) {
+            int* d = (int*)rt::dmalloc(sizeof(int) * (size_t)std::max(1, r.U));
+            rt::h2d(d, dup.data(), sizeof(int) * (size_t)r.U, st);
+            rt::stream_sync(st);
+            r.d_dup = d;
+        }
+        dedups[key] = r;
+        return r;
+    }
+    struct Dedup { bool on = false; AxisDedup y, z; };
+
     // a row of the out-of-bounds constant in global memory: lines that are constant along y / z are bulk-copied from it
     std::map<std::pair<int, unsigned>, float*> const_rows;
     const float* const_row(int sx, float value, rt::Stream st) {
@@ -335,7 +377,8 @@ public:
     // ---- sweeps -------------------------------------------------------------------------
     struct Geom { int n[3], hp[3], hm[3]; };   // logical size + halos of whatever is being transformed
 
-    void x_forward(const SrcDesc& src, const Geom& g, float2* out, rt::Stream st) {
+    // dd (optional): in = de-duplication wanted, out = whether this launch used it (only the TMA-fed kernel does)
+    void x_forward(const SrcDesc& src, const Geom& g, float2* out, rt::Stream st, Dedup* dd = nullptr) {
         XFwdParams p;
         memset(&p, 0, sizeof(p));
         p.src = src.p;
@@ -368,8 +411,8 @@ public:
             q.row_bytes = (unsigned)p.sx * 4u;
             const size_t slot_bytes = (size_t)TC * q.LS * sizeof(float);
             const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
-            const size_t sm = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
-                              (size_t)std::max(1, fx_.n) * sizeof(int2) + slot_bytes;
+            const size_t sm = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * 2 * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
+                              (XFwdT::MAXSLOT + 1) * sizeof(int) + (size_t)std::max(1, fx_.n) * sizeof(int2) + slot_bytes;
             const size_t lim = rt::max_smem();
             if (sm + 1024 <= lim) {
                 // one staging slot per block; three blocks per SM where that fits (tiles up to ~36 KB), else two, else one
@@ -381,8 +424,16 @@ public:
                 q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
                 q.const_row = const_row(p.sx, q.cval, st);
                 q.nslot = 1;
-                q.ntiles = (int)grid;
-                q.nctas = (int)std::min<long long>(grid, (long long)rt::sm_count() * bps);
+                long long tiles = grid;
+                if (dd && dd->on) {
+                    q.dedup = 1;
+                    q.UY = dd->y.U; q.UZ = dd->z.U; q.splity = dd->y.split; q.splitz = dd->z.split;
+                    q.dupy = dd->y.d_dup;
+                    q.x.nlines = (long long)q.UY * q.UZ;
+                    tiles = (q.x.nlines + TC - 1) / TC;
+                }
+                q.ntiles = (int)tiles;
+                q.nctas = (int)std::min<long long>(tiles, (long long)rt::sm_count() * bps);
                 if (timer) timer->begin(K_XFWD, st);
                 // three blocks per SM: 160 threads each -- the phases of a tile hold (N2 / R) * 8 items (280 / 320 / 448 for the
                 // 280-point plan 8 * 7 * 5, 282 for the split step), which 160 threads cover in 2 + 2 + 3 + 2 rounds at 92 % lane
@@ -394,15 +445,17 @@ public:
                 return;
             }
         }
+        if (dd) dd->on = false;        // the plain-load kernel transforms every padded line
         if (timer) timer->begin(K_XFWD, st);
         rt::launch<XFwd, 192, 4>(p, grid, 192, smem, st);       // four 192-thread blocks per SM (<= 85 registers)
         if (timer) timer->end(K_XFWD, st);
     }
 
     void col_pass(int id, float2* data, const float2* khat, int axis /*1=y,0=z*/, int mode, const Geom& g,
-                  int out_rows, int outer_valid_lo, int outer_count, int outer_P, rt::Stream st) {
+                  int out_rows, int outer_valid_lo, int outer_count, int outer_P, rt::Stream st, const int* dup_outer = nullptr) {
         ColPassParams p;
         memset(&p, 0, sizeof(p));
+        p.dup_outer = dup_outer;
         p.data = data; p.khat = khat;
         p.plan = (axis == 1) ? fy.dev : fz.dev;
         const int Pa = P[axis];
@@ -582,10 +635,26 @@ public:
                 if (!lo) g.hm[d] = 0;
                 if (!hi) g.hp[d] = 0;
             }
+            debug_counter(2) += 1;
         }
-        x_forward(src, g, spec, st);
+        // mirror / periodic extension: transform every line and plane once (SPIM_DEDUP=0: every padded line, as in round 1)
+        Dedup dd;
+        const bool dedup_on = env_int("SPIM_DEDUP", 1) != 0;
+        if (dedup_on && (src.ext == EXT_MIRROR_SINGLE || src.ext == EXT_MIRROR_DOUBLE || src.ext == EXT_PERIODIC)) {
+            auto data_side = [&](int d, bool hi) {
+                const int bit = 1 << d;
+                return hi ? ((src.halo_hi & bit) && g.hp[d] > 0 && src.dims[d] - src.origin[d] - n[d] >= g.hp[d])
+                          : ((src.halo_lo & bit) && g.hm[d] > 0 && src.origin[d] >= g.hm[d]);
+            };
+            dd.y = axis_dedup(n[1], g.hp[1], g.hm[1], P[1], src.ext, data_side(1, false), data_side(1, true), st);
+            dd.z = axis_dedup(n[0], g.hp[0], g.hm[0], P[0], src.ext, data_side(0, false), data_side(0, true), st);
+            dd.on = dd.y.ok && dd.z.ok && (dd.y.any || dd.z.any);
+        }
+        x_forward(src, g, spec, st, &dd);
+        if (dd.on) debug_counter(1) += 1;
         const int LZ = n[0] + g.hp[0] + g.hm[0];
-        col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + g.hp[0], LZ, P[0], st);
+        if (dd.on) col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], dd.z.split, dd.z.U, P[0], st, dd.z.any ? dd.z.d_dup : nullptr);
+        else col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + g.hp[0], LZ, P[0], st);
         col_pass(K_ZMID, spec, khat, 0, COL_MID, g, n[0], P[1], P[1], P[1], st);
         col_pass(K_YINV, spec, nullptr, 1, COL_INV, g, n[1], n[0], n[0], P[0], st);
         x_inverse(spec, e, st);

@@ -97,6 +97,7 @@ struct GRows {          // the global-memory side of a column tile
     long long stride;   // float2 units between consecutive rows (even)
     int va, vb;         // rows that hold data on load: [0, va) U [vb, n); others read as zero
     int sa;             // rows written on store: [0, sa)
+    long long dup4;     // != 0: every stored row also goes to the same tile dup4 float4 further (the mirrored plane, see ColPassParams::dup_outer)
 };
 
 SPIM_HD float2 lo2(float4 v) { return make_float2(v.x, v.y); }
@@ -230,10 +231,21 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
         if (dst_g) {
             // predicated streaming stores, the row pointer advanced by one 64-bit add per row
             float4* gp = reinterpret_cast<float4*>(g.p) + (long long)base * gs4 + c2;
+            if (g.dup4 == 0) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                stg_stream_if(gp, c2_to_il(x[q]), base + q * M < g.sa);
-                gp += gstep;
+                for (int q = 0; q < R; ++q) {
+                    stg_stream_if(gp, c2_to_il(x[q]), base + q * M < g.sa);
+                    gp += gstep;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const float4 v = c2_to_il(x[q]);
+                    const bool ok = base + q * M < g.sa;
+                    stg_stream_if(gp, v, ok);
+                    stg_stream_if(gp + g.dup4, v, ok);
+                    gp += gstep;
+                }
             }
         } else {
             float4 v[R];
@@ -378,12 +390,23 @@ struct ColPassParams {
     int outer_split, outer_shift;  // outer = o < split ? o : o + shift  (skips the zero gap)
     int va, vb, sa;
     int mode;
+    const int* dup_outer;      // forward y pass over de-duplicated planes: dup_outer[o] = plane that is a mirror image of plane o
+                               // (stored too) or -1; nullptr = none
     int ntiles, nctas;         // ColPassT (persistent): tiles in total / CTAs launched; ntiles < 0 selects the async mode of ColPass
     // ColPassT with tensor maps (use_tmap): y pass = 2-D map {2*pitch floats, Py*Pz rows}, box {32, box_rows};
     // z pass = 3-D map {2*pitch, Py, Pz}, box {32, 1, box_rows}; box_rows divides the FFT length
     int use_tmap, box_rows, tmap_rank;
     SpimTensorMap tmap;
 };
+
+// float4 distance from the tile of outer index o to its duplicate destination (0 = none)
+SPIM_DEV long long col_dup4(const ColPassParams& p, int o) {
+    if (p.dup_outer == nullptr) return 0;
+    const int d = spim_ldg(p.dup_outer + o);
+    if (d < 0) return 0;
+    const int outer = o < p.outer_split ? o : o + p.outer_shift;
+    return ((long long)(d - outer) * p.outer_stride) >> 1;
+}
 
 // asynchronous copy of tile rows [row_lo, row_hi) (W float4 = W x 16 B each) from global to shared memory.
 // Each thread keeps its column pair and walks rows with a constant stride: ~4 instructions per 16-byte chunk.
@@ -430,6 +453,7 @@ struct ColPassN {
         g.p = p.data + base;
         g.stride = p.row_stride;
         g.va = p.va; g.vb = p.vb; g.sa = p.sa;
+        g.dup4 = col_dup4(p, o);
         const FftPlanDev& pl = p.plan;
         const int S = pl.nstages;
         int sg = 1;                       // first stage reads global memory directly ...
@@ -499,6 +523,7 @@ struct ColPassT {
         g.p = p.data + base;
         g.stride = p.row_stride;
         g.va = P; g.vb = P; g.sa = p.sa;
+        g.dup4 = col_dup4(p, t / p.ntx);
         if (p.mode == COL_FWD) {
             for (int s = 0; s < S; ++s) stage_dispatch<false>(tg, pl, s, tile, 0, 0, s == S - 1, g, s > 0, 1);
         } else if (p.mode == COL_INV) {
@@ -728,7 +753,10 @@ SPIM_DEV void split_inv(C2 A, C2 B, float2 w, C2& zk, C2& zm) {
 
 // forward split step of one tile: half spectrum of 16 real lines from the 8 complex transforms of their pairs (factor
 // 1/2 folded into the kernel scale).  One item = one frequency pair (k, N2 - k) of FOUR line pairs, see xinv_presplit.
-SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2) {
+// dstoff[line * DS]: destination row of a line; DS = 2 (XFwdT): dstoff[line * 2 + 1] = a second row that receives the same
+// spectrum (the mirrored halo row) or -1 -- visited only when `anydup` says the tile has one
+template <int DS>
+SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2, int anydup = 0) {
     const int nk = p.nk;
     SPIM_FOR_ITEMS(i, nk * (TP / 4)) {
         const int h = fastdiv(i, p.magic_nk);
@@ -748,7 +776,7 @@ SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long lon
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int bp = h * 4 + g;
-            const long long d0 = dstoff[2 * bp], d1 = dstoff[2 * bp + 1];
+            const long long d0 = dstoff[(2 * bp) * DS], d1 = dstoff[(2 * bp + 1) * DS];
             C2 xk, xm;
             split_fwd(c2_from_pk(zk[g]), c2_from_pk(zm[g]), w, xk, xm);      // the tile is packed (stage_tile)
             if (d0 >= 0) {
@@ -758,6 +786,17 @@ SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long lon
             if (d1 >= 0) {
                 p.spec[d1 + k] = c2_b(xk);
                 if (two) p.spec[d1 + km] = c2_b(xm);
+            }
+            if (DS > 1 && anydup) {
+                const long long e0 = dstoff[(2 * bp) * DS + 1], e1 = dstoff[(2 * bp + 1) * DS + 1];
+                if (e0 >= 0) {
+                    p.spec[e0 + k] = c2_a(xk);
+                    if (two) p.spec[e0 + km] = c2_a(xm);
+                }
+                if (e1 >= 0) {
+                    p.spec[e1 + k] = c2_b(xk);
+                    if (two) p.spec[e1 + km] = c2_b(xm);
+                }
             }
         }
     }
@@ -804,9 +843,9 @@ struct XFwd {
         if (p.src_vec_ok) { SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR, true>(p, tile, srcoff))) }
         else { SPIM_RADIX_SWITCH(pl.radix[0], (xfwd_stage0<RR, false>(p, tile, srcoff))) }
         GRows g;
-        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0; g.dup4 = 0;
         for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
-        xfwd_split(p, tile, dstoff, N2);
+        xfwd_split<1>(p, tile, dstoff, N2);
         // zero the pad columns [N2+1, pitch)
         const int npad = p.pitch - (N2 + 1);
         SPIM_FOR_ITEMS(i, npad * TC) {
@@ -845,15 +884,33 @@ struct XFwdTParams {
     const int2* fix;           // fix-up list: staging[fix.x] = fix.y >= 0 ? staging[fix.y] : (fix.y == -1 ? 0 : cval)
     int nfix;
     uint32_t magic_nfix;       // for item / nfix
+    // De-duplicated lines (mirror / periodic extension): the halo lines along y and z are copies of image lines, so only the
+    // UY x UZ lines that exist as data are transformed; line index u along an axis has coordinate u < split ? u : u - U
+    // (neighbour-provided halo before the image last), and its spectrum is also stored to padded row dupy[u] when a halo row
+    // mirrors it.  Mirrored PLANES are left to the forward y pass (ColPassParams::dup_outer).  dedup = 0: every padded line.
+    int dedup, UY, UZ, splity, splitz;
+    const int* dupy;
     int nfix_dyn;              // the first nfix_dyn entries copy data (mirrored / halo values): applied to every tile.  The rest
     uint32_t magic_nfix_dyn;   // write constants (zero gap, out-of-bounds constant) to cells no row copy ever touches: once per slot
 };
 
 // source row of padded line l (nullptr beyond the last line) and its destination offset in the spectrum
-SPIM_DEV const float* xfwd_line(const XFwdTParams& q, long long l, long long& d_o) {
+SPIM_DEV const float* xfwd_line(const XFwdTParams& q, long long l, long long& d_o, long long& d_dup) {
     const XFwdParams& p = q.x;
-    d_o = -1;
+    d_o = -1; d_dup = -1;
     if (l >= p.nlines) return nullptr;
+    if (q.dedup) {
+        const int uz = (int)(l / q.UY);
+        const int uy = (int)(l - (long long)uz * q.UY);
+        const int ay = uy < q.splity ? uy : uy - q.UY;
+        const int az = uz < q.splitz ? uz : uz - q.UZ;
+        const int yp = ay >= 0 ? ay : p.Py + ay;
+        const int zp = az >= 0 ? az : p.Pz + az;
+        d_o = ((long long)zp * p.Py + yp) * (long long)p.pitch;
+        const int yd = spim_ldg(q.dupy + uy);
+        if (yd >= 0) d_dup = ((long long)zp * p.Py + yd) * (long long)p.pitch;
+        return p.src + ((long long)(az + p.oz) * p.sy + (ay + p.oy)) * (long long)p.sx;
+    }
     const int iz = (int)(l / p.LY);
     const int iy = (int)(l - (long long)iz * p.LY);
     const int yp = iy < p.ny + p.hpy ? iy : iy + (p.Py - p.LY);
@@ -905,26 +962,30 @@ struct XFwdT {
     static constexpr bool kEmuThreads = true;
     static constexpr int MAXSLOT = 3;
     // descriptors of tile t into slot `slot`, and its 16 row copies.  GPU: the first warp; emulator: every thread its lines.
-    SPIM_DEV static void issue(const Params& q, int t, int slot, float* stg, long long* dsto, uint64_t* full) {
+    SPIM_DEV static void issue(const Params& q, int t, int slot, float* stg, long long* dsto, int* anyd, uint64_t* full) {
 #if defined(SPIM_HOST_EMU)
         (void)full;
         SPIM_FOR_ITEMS(b, TC) {
-            long long d_o;
-            const float* sp = xfwd_line(q, (long long)t * TC + b, d_o);
-            dsto[slot * TC + b] = d_o;
+            long long d_o, d_dup;
+            const float* sp = xfwd_line(q, (long long)t * TC + b, d_o, d_dup);
+            dsto[(slot * TC + b) * 2] = d_o;
+            dsto[(slot * TC + b) * 2 + 1] = d_dup;
             if (sp) memcpy(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes);
         }
+        anyd[slot] = q.dedup;       // (threads of the emulated block write the same value)
 #else
         if (threadIdx.x < 32) {
             const int b = (int)threadIdx.x;
-            long long d_o = -1;
+            long long d_o = -1, d_dup = -1;
             const float* sp = nullptr;
             if (b < TC) {
-                sp = xfwd_line(q, (long long)t * TC + b, d_o);
-                dsto[slot * TC + b] = d_o;
+                sp = xfwd_line(q, (long long)t * TC + b, d_o, d_dup);
+                dsto[(slot * TC + b) * 2] = d_o;
+                dsto[(slot * TC + b) * 2 + 1] = d_dup;
             }
             const unsigned live = __ballot_sync(0xffffffffu, sp != nullptr);
-            if (b == 0) mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes);
+            const unsigned dups = __ballot_sync(0xffffffffu, d_dup >= 0);
+            if (b == 0) { anyd[slot] = dups != 0u; mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes); }
             __syncwarp();
             if (sp) bulk_g2s(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes, full + slot);
         }
@@ -937,10 +998,11 @@ struct XFwdT {
         const int N2 = pl.n;
         float4* tile = reinterpret_cast<float4*>(smem2);
         float* stg = reinterpret_cast<float*>(smem2 + (size_t)N2 * TC);
-        long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * q.LS);     // [nslot][TC]
-        long long* dcur = dsto + MAXSLOT * TC;                                                 // [TC], the tile in work
-        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC);                               // [MAXSLOT]
-        int2* fixs = reinterpret_cast<int2*>(full + MAXSLOT);                                  // [nfix], the fix-up list
+        long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * q.LS);     // [nslot][TC][2]
+        long long* dcur = dsto + MAXSLOT * TC * 2;                                             // [TC][2], the tile in work
+        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC * 2);                           // [MAXSLOT]
+        int* anyd = reinterpret_cast<int*>(full + MAXSLOT);                                    // [MAXSLOT + 1]: tile has duplicate rows
+        int2* fixs = reinterpret_cast<int2*>(anyd + MAXSLOT + 1);                              // [nfix], the fix-up list
         const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
 #if !defined(SPIM_HOST_EMU)
         if (threadIdx.x == 0) {
@@ -949,11 +1011,11 @@ struct XFwdT {
         }
         __syncthreads();
 #endif
-        for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, bid + j * q.nctas, j, stg, dsto, full);
+        for (int j = 0; j < q.nslot && j < ntl; ++j) issue(q, bid + j * q.nctas, j, stg, dsto, anyd, full);
         SPIM_FOR_ITEMS(j, q.nfix) fixs[j] = spim_ldg(q.fix + j);
         SPIM_BARRIER();
         GRows g;
-        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0; g.dup4 = 0;
         for (int i = 0; i < ntl; ++i) {
             const int slot = i % q.nslot;
             float* sl = stg + (size_t)slot * TC * q.LS;
@@ -972,22 +1034,25 @@ struct XFwdT {
                     ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
                 }
             }
-            SPIM_FOR_ITEMS(b, TC) dcur[b] = dsto[slot * TC + b];
+            SPIM_FOR_ITEMS(b, TC * 2) dcur[b] = dsto[slot * TC * 2 + b];
+            if (SPIM_TID == 0) anyd[MAXSLOT] = anyd[slot];
             SPIM_BARRIER();
             SPIM_RADIX_SWITCH(pl.radix[0], (xfwdt_stage0<RR>(p, tile, sl, q.LS)))
 #if !defined(SPIM_HOST_EMU)
             fence_proxy_async();       // this slot's generic-proxy accesses are ordered before the async-proxy refill below
 #endif
             SPIM_BARRIER();
-            if (i + q.nslot < ntl) issue(q, bid + (i + q.nslot) * q.nctas, slot, stg, dsto, full);
+            if (i + q.nslot < ntl) issue(q, bid + (i + q.nslot) * q.nctas, slot, stg, dsto, anyd, full);
             for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
-            xfwd_split(p, tile, dcur, N2);
+            const int anydup = anyd[MAXSLOT];
+            xfwd_split<2>(p, tile, dcur, N2, anydup);
             const int npad = p.pitch - (N2 + 1);
             SPIM_FOR_ITEMS(k, npad * TC) {
                 const int b = k / (npad > 0 ? npad : 1);
                 const int j = k - b * npad;
-                const long long d_o = dcur[b];
+                const long long d_o = dcur[b * 2], d_d = dcur[b * 2 + 1];
                 if (d_o >= 0) p.spec[d_o + N2 + 1 + j] = make_float2(0.f, 0.f);
+                if (d_d >= 0) p.spec[d_d + N2 + 1 + j] = make_float2(0.f, 0.f);
             }
             SPIM_BARRIER();            // the tile and dcur are free for the next round
         }
@@ -1389,7 +1454,7 @@ struct XInvT {
         xinv_presplit(p, tile, srcoff, N2, pl.nstages > 1);
         SPIM_BARRIER();
         GRows g;
-        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0;
+        g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0; g.dup4 = 0;
         for (int s = pl.nstages - 1; s >= 1; --s) stage_dispatch<true>(tg, pl, s, tile, 1, 0, 0, g, 1, s > 1);   // stage 0 reads single lines: interleaved
         EpiAcc acc;
         acc.sum = 0.0; acc.mx = 0.f;

@@ -678,7 +678,7 @@ struct mvd_session {
         // extension -- the halo outside the volume joins the zero gap of the padded transform -- and the update epilogue adds
         // c * sum(K2) back.  Neighbour-provided halos (brick mode) carry r - c like the interior.  SPIM_CONST_SHIFT=0 keeps
         // the literal constant extension (A/B and parity runs).
-        static const bool shift_on = [] { const char* t = getenv("SPIM_CONST_SHIFT"); return !(t && *t == '0'); }();
+        const bool shift_on = env_int("SPIM_CONST_SHIFT", 1) != 0;
         const bool shift = shift_on && conv2_ext() == EXT_CONSTANT;
         const float cext = 1.f;
         if (ph == 0) {

@@ -352,3 +352,44 @@ def test_lean_column_pass_for_small_radix_plans(emu_lib):
               18, 20, 30, 50, 90, 100, 560):                                   # plans with 9 / 10: general kernel
         for shp in ((n, 4, 8), (4, n, 8)):
             P.legacy_case(emu_lib, shp, (3, 3, 3), seed=n)
+
+
+def test_deduplicated_forward_sweeps_are_bit_identical(emu_lib, monkeypatch):
+    """Mirror / periodic extension: the halo lines and planes are copies of image lines, so the forward x and y sweeps
+    transform each only once and store it twice (SPIM_DEDUP=0: every padded line).  Same data through the same
+    arithmetic: not a bit may differ -- single convolutions with every rule, gen-1 (mirror in both convolutions) and gen-2."""
+    syn = __import__("spim_registration_b200").synthetic
+    for shape, k in (((14, 18, 24), 5), ((33, 20, 40), 7), ((12, 40, 16), 9)):
+        _, imgs, ws, psfs = syn.make_dataset(shape, 2, k, kind="beads")
+        for gen in (1, 2):
+            monkeypatch.setenv("SPIM_DEDUP", "1")
+            c1 = emu_lib.mvd_debug_counter(1)
+            a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            assert emu_lib.mvd_debug_counter(1) >= c1 + (8 if gen == 1 else 4)      # mirror: both convolutions (gen-1) / conv1 (gen-2)
+            monkeypatch.setenv("SPIM_DEDUP", "0")
+            b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            assert np.array_equal(a, b), (shape, gen)
+    monkeypatch.setenv("SPIM_DEDUP", "1")
+    for ext in range(5):
+        P.conv_case(emu_lib, (10, 12, 16), (5, 5, 5), ext)
+        P.conv_case(emu_lib, (6, 9, 8), (5, 7, 3), ext)         # halo wider than half the image: several rows per source row -> falls back
+
+
+def test_constant_extension_by_shift(emu_lib, monkeypatch):
+    """gen-2 conv2 extends the quotient by the constant 1.  conv(ext_1(r), K) = conv(ext_0(r - 1), K) + sum(K): the session
+    stores r - 1, convolves zero-extended and adds sum(K2) in the update (SPIM_CONST_SHIFT=0: the literal extension).
+    Identical in exact arithmetic; in fp32 the two agree to round-off and both meet the parity bar."""
+    syn = __import__("spim_registration_b200").synthetic
+    shape = (14, 18, 24)
+    _, imgs, ws, psfs = syn.make_dataset(shape, 3, 5, kind="beads")
+    for typ in (O.EFFICIENT_BAYESIAN, O.INDEPENDENT, O.OPTIMIZATION_I, O.OPTIMIZATION_II):
+        monkeypatch.setenv("SPIM_CONST_SHIFT", "1")
+        c2 = emu_lib.mvd_debug_counter(2)
+        a, *_ = P.run_session(emu_lib, imgs, ws, psfs, typ, 2, 3)
+        assert emu_lib.mvd_debug_counter(2) >= c2 + 9
+        monkeypatch.setenv("SPIM_CONST_SHIFT", "0")
+        b, *_ = P.run_session(emu_lib, imgs, ws, psfs, typ, 2, 3)
+        per, l2 = O.parity_errors(a, b)
+        assert per <= 2e-5 and l2 <= 2e-6, (typ, per, l2)
+    monkeypatch.setenv("SPIM_CONST_SHIFT", "1")
+    P.decon_case(emu_lib, shape, 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)

@@ -97,3 +97,35 @@ def test_lean_column_pass(gpu):
     for n in (48, 64, 96, 128, 288):
         for shp in ((n, 4, 8), (4, n, 8)):
             P.legacy_case(gpu, shp, (3, 3, 3), seed=n)
+
+
+def test_deduplicated_forward_sweeps_are_bit_identical(gpu, monkeypatch):
+    """Mirror extension: halo lines / planes are transformed once and stored twice (SPIM_DEDUP=0: every padded line)."""
+    import numpy as np
+    from spim_registration_b200 import synthetic
+    for shape, k in (((40, 48, 56), 7), ((36, 70, 524), 31)):
+        _, imgs, ws, psfs = synthetic.make_dataset(shape, 2, k, kind="beads")
+        for gen in (1, 2):
+            monkeypatch.setenv("SPIM_DEDUP", "1")
+            c1 = gpu.mvd_debug_counter(1)
+            a, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            assert gpu.mvd_debug_counter(1) > c1
+            monkeypatch.setenv("SPIM_DEDUP", "0")
+            b, *_ = P.run_session(gpu, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            assert np.array_equal(a, b), (shape, gen)
+
+
+def test_constant_extension_by_shift(gpu, monkeypatch):
+    """gen-2 conv2: zero extension of (quotient - 1) plus sum(K2) instead of the literal extension by 1 (SPIM_CONST_SHIFT=0)."""
+    from spim_registration_b200 import synthetic
+    shape = (40, 48, 56)
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, 3, 7, kind="beads")
+    for typ in (O.EFFICIENT_BAYESIAN, O.INDEPENDENT, O.OPTIMIZATION_I, O.OPTIMIZATION_II):
+        monkeypatch.setenv("SPIM_CONST_SHIFT", "1")
+        a, *_ = P.run_session(gpu, imgs, ws, psfs, typ, 2, 3)
+        monkeypatch.setenv("SPIM_CONST_SHIFT", "0")
+        b, *_ = P.run_session(gpu, imgs, ws, psfs, typ, 2, 3)
+        per, l2 = O.parity_errors(a, b)
+        assert per <= 2e-5 and l2 <= 2e-6, (typ, per, l2)
+    monkeypatch.setenv("SPIM_CONST_SHIFT", "0")
+    P.decon_case(gpu, shape, 3, 7, O.EFFICIENT_BAYESIAN, 2, 3)
