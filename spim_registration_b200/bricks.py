@@ -200,6 +200,12 @@ class BrickRunner:
         send, recv = [], []
         for d in range(3):
             o, wlo, whi = origin[d], self.halo_lo[d], self.halo_hi[d]
+            if d == 2 and off[d] != 0 and wlo > 0 and whi > 0 and os.environ.get("SPIM_BRICK_XPAD", "1") != "0":
+                # x pieces widened to whole 16-byte groups where the buffer has the cells (a 15-voxel halo moves as 16 columns):
+                # the push kernel then moves them as float4 like the y / z faces; the extra column lands in a cell nobody reads
+                w4lo, w4hi = (wlo + 3) & ~3, (whi + 3) & ~3
+                if o % 4 == 0 and n[d] % 4 == 0 and o >= w4lo and o + n[d] + w4hi <= dims[d] and n[d] >= max(w4lo, w4hi):
+                    wlo, whi = w4lo, w4hi
             if off[d] == 0:
                 send.append(slice(o, o + n[d])); recv.append(slice(o, o + n[d]))
             elif off[d] < 0:       # neighbour below: it needs my first `whi` interior cells; I get its last `wlo`

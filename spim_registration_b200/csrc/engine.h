@@ -440,7 +440,9 @@ public:
                 // use where 256 threads need 2 + 2 + 2 + 2 at 65 % (measured 0.197 vs 0.208 ms, profiles/r2)
                 if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, 160, sm, st);
                 else if (bps == 2) rt::launch<XFwdT, 384, 2>(q, q.nctas, 384, sm, st);
-                else rt::launch<XFwdT, 512, 1>(q, q.nctas, 512, sm, st);
+                // one block per SM (lines of 1080 voxels and longer): 768 threads at <= 85 registers -- the 432 / 480 / 720 / 542 items
+                // of a 540-point tile then take one round per phase (SPIM_XFWD_T1 overrides for A/B runs)
+                else rt::launch<XFwdT, 768, 1>(q, q.nctas, env_int("SPIM_XFWD_T1", 768), sm, st);
                 if (timer) timer->end(K_XFWD, st);
                 return;
             }

@@ -26,7 +26,7 @@ typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
 #define SPIM_INSTANCES_X_C(X) X(XInvRatioIeee, 256, 1) X(XInvRatioIeee, 128, 6)
 #define SPIM_INSTANCES_X_D(X) X(XInvUpdateFast, 256, 1) X(XInvUpdateFast, 128, 5)
 #define SPIM_INSTANCES_X_E(X) X(XInvUpdateIeee, 256, 1) X(XInvUpdateExact64, 256, 1)
-#define SPIM_INSTANCES_X_F(X) X(XFwdT, 256, 3) X(XFwdT, 384, 2) X(XFwdT, 512, 1)
+#define SPIM_INSTANCES_X_F(X) X(XFwdT, 256, 3) X(XFwdT, 384, 2) X(XFwdT, 768, 1)
 #define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "X_A", "X_B", "X_C", "X_D", "X_E", "X_F"
 #define SPIM_INSTANCES_ALL(X)                                                                                      \
     SPIM_INSTANCES_COL_A(X) SPIM_INSTANCES_COL_B(X) SPIM_INSTANCES_COL_C(X) SPIM_INSTANCES_COL_D(X)                \

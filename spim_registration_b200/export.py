@@ -262,3 +262,317 @@ class Save3dTIFF:
 
     def finish(self) -> bool:
         return False
+
+
+# =================================================================================================================
+# SpimData2 XML projects around the exported stacks (spim/process/fusion/export/ExportSpimData2TIFF.java,
+# AppendSpimData2.java, XMLTIFFImgTitler.java; loader tags from spim/fiji/spimdata/imgloaders/XmlIoStackImgLoader.java:44-66).
+# The XML writer of the reference is the un-vendored spimdata library (mpicbg.spim.data.XmlIoSpimData): the element
+# layout below is its published "SpimData version 0.2" schema -- readable by BigDataViewer / Multiview-Reconstruction,
+# not a byte copy of what JDOM would emit.  The HDF5 variants (ExportSpimData2HDF5 / AppendSpimData2HDF5) need an HDF5
+# library, which this image does not have: they raise NotImplementedError with that message.
+# =================================================================================================================
+import xml.etree.ElementTree as _ET
+from dataclasses import dataclass, field
+
+
+@dataclass(frozen=True)
+class Entity:
+    """Angle / Channel / Illumination of the spimdata model: an id and a display name (equality by id, like
+    mpicbg.spim.data.generic.base.Entity)."""
+    id: int
+    name: str = field(default="", compare=False)
+
+    def getName(self) -> str:
+        return self.name if self.name else str(self.id)
+
+
+@dataclass(frozen=True)
+class TimePoint:
+    id: int
+
+    def getId(self) -> int:
+        return self.id
+
+    def getName(self) -> str:
+        return str(self.id)
+
+
+@dataclass(frozen=True)
+class ViewSetup:
+    id: int
+    angle: Entity = Entity(0)
+    channel: Entity = Entity(0)
+    illumination: Entity = Entity(0)
+    name: str = ""
+    size_xyz: Optional[Tuple[int, int, int]] = None
+    voxel_size_xyz: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    voxel_unit: str = "um"
+
+    def getId(self) -> int:
+        return self.id
+
+    def getAngle(self) -> Entity:
+        return self.angle
+
+    def getChannel(self) -> Entity:
+        return self.channel
+
+    def getIllumination(self) -> Entity:
+        return self.illumination
+
+
+class XMLTIFFImgTitler:
+    """XMLTIFFImgTitler.java:46-63: "img" + _TL<t> / _Ch<c> / _Ill<i> / _Angle<a>, each only when more than one exists."""
+
+    def __init__(self, newTimepoints: Sequence[TimePoint], newViewSetups: Sequence[ViewSetup]):
+        self.timepoints, self.viewSetups = list(newTimepoints), list(newViewSetups)
+
+    def getImageTitle(self, tp: TimePoint, vs: ViewSetup) -> str:
+        fn = "img"
+        if len(self.timepoints) > 1:
+            fn += "_TL" + str(tp.getId())
+        if len({v.getChannel() for v in self.viewSetups}) > 1:
+            fn += "_Ch" + vs.getChannel().getName()
+        if len({v.getIllumination() for v in self.viewSetups}) > 1:
+            fn += "_Ill" + vs.getIllumination().getName()
+        if len({v.getAngle() for v in self.viewSetups}) > 1:
+            fn += "_Angle" + vs.getAngle().getName()
+        return fn
+
+
+@dataclass
+class FileNamePattern:
+    layoutTP: int = 0
+    layoutChannels: int = 0
+    layoutIllum: int = 0
+    layoutAngles: int = 0
+    fileNamePattern: str = "img"
+
+
+def getFileNamePattern(timepoints: Sequence[TimePoint], viewSetups: Sequence[ViewSetup], compress: bool = False) -> FileNamePattern:
+    """ExportSpimData2TIFF.java:186-224."""
+    f = FileNamePattern()
+    if len(timepoints) > 1:
+        f.fileNamePattern += "_TL{t}"; f.layoutTP = 1
+    if len({v.getChannel() for v in viewSetups}) > 1:
+        f.fileNamePattern += "_Ch{c}"; f.layoutChannels = 1
+    if len({v.getIllumination() for v in viewSetups}) > 1:
+        f.fileNamePattern += "_Ill{i}"; f.layoutIllum = 1
+    if len({v.getAngle() for v in viewSetups}) > 1:
+        f.fileNamePattern += "_Angle{a}"; f.layoutAngles = 1
+    f.fileNamePattern += ".tif"
+    if compress:
+        f.fileNamePattern += ".zip"
+    return f
+
+
+def integer_pattern(ids: Sequence[int]) -> str:
+    """Resave_TIFF.listAllTimePoints: the ids as a comma separated list (ranges are not collapsed by the reference either)."""
+    return ",".join(str(int(i)) for i in ids)
+
+
+@dataclass
+class SpimData2:
+    """The part of spim.fiji.spimdata.SpimData2 the exporters touch: sequence description (time points, view setups, stack
+    loader), one transform list per (timepoint, setup), empty interest points / bounding boxes."""
+    basePath: str
+    timepoints: List[TimePoint]
+    viewSetups: List[ViewSetup]
+    loader: Optional[FileNamePattern] = None
+    registrations: Dict[Tuple[int, int], List[Tuple[str, Tuple[float, ...]]]] = field(default_factory=dict)
+
+    def to_xml(self) -> "_ET.Element":
+        root = _ET.Element("SpimData", {"version": "0.2"})
+        _ET.SubElement(root, "BasePath", {"type": "relative"}).text = "."
+        seq = _ET.SubElement(root, "SequenceDescription")
+        if self.loader is not None:
+            il = _ET.SubElement(seq, "ImageLoader", {"format": "spimreconstruction.stack.ij"})
+            _ET.SubElement(il, "imagedirectory", {"type": "relative"}).text = "."
+            _ET.SubElement(il, "filePattern").text = self.loader.fileNamePattern
+            _ET.SubElement(il, "layoutTimepoints").text = str(self.loader.layoutTP)
+            _ET.SubElement(il, "layoutChannels").text = str(self.loader.layoutChannels)
+            _ET.SubElement(il, "layoutIlluminations").text = str(self.loader.layoutIllum)
+            _ET.SubElement(il, "layoutAngles").text = str(self.loader.layoutAngles)
+            _ET.SubElement(il, "imglib2container").text = "ArrayImgFactory"
+        vss = _ET.SubElement(seq, "ViewSetups")
+        for vs in self.viewSetups:
+            e = _ET.SubElement(vss, "ViewSetup")
+            _ET.SubElement(e, "id").text = str(vs.id)
+            if vs.name:
+                _ET.SubElement(e, "name").text = vs.name
+            if vs.size_xyz is not None:
+                _ET.SubElement(e, "size").text = " ".join(str(int(x)) for x in vs.size_xyz)
+            vx = _ET.SubElement(e, "voxelSize")
+            _ET.SubElement(vx, "unit").text = vs.voxel_unit
+            _ET.SubElement(vx, "size").text = " ".join(repr(float(x)) for x in vs.voxel_size_xyz)
+            at = _ET.SubElement(e, "attributes")
+            _ET.SubElement(at, "illumination").text = str(vs.illumination.id)
+            _ET.SubElement(at, "channel").text = str(vs.channel.id)
+            _ET.SubElement(at, "angle").text = str(vs.angle.id)
+        for tag, cls, get in (("illumination", "Illumination", ViewSetup.getIllumination), ("channel", "Channel", ViewSetup.getChannel),
+                              ("angle", "Angle", ViewSetup.getAngle)):
+            a = _ET.SubElement(vss, "Attributes", {"name": tag})
+            for ent in sorted({get(v) for v in self.viewSetups}, key=lambda q: q.id):
+                e = _ET.SubElement(a, cls)
+                _ET.SubElement(e, "id").text = str(ent.id)
+                _ET.SubElement(e, "name").text = ent.getName()
+        tps = _ET.SubElement(seq, "Timepoints", {"type": "pattern"})
+        _ET.SubElement(tps, "integerpattern").text = integer_pattern([t.id for t in self.timepoints])
+        _ET.SubElement(seq, "MissingViews")
+        regs = _ET.SubElement(root, "ViewRegistrations")
+        for tp in self.timepoints:
+            for vs in self.viewSetups:
+                r = _ET.SubElement(regs, "ViewRegistration", {"timepoint": str(tp.id), "setup": str(vs.id)})
+                for name, m in self.registrations.get((tp.id, vs.id), [("identity", (1., 0., 0., 0., 0., 1., 0., 0., 0., 0., 1., 0.))]):
+                    t = _ET.SubElement(r, "ViewTransform", {"type": "affine"})
+                    _ET.SubElement(t, "Name").text = name
+                    _ET.SubElement(t, "affine").text = " ".join(repr(float(x)) for x in m)
+        _ET.SubElement(root, "ViewInterestPoints")
+        _ET.SubElement(root, "BoundingBoxes")
+        return root
+
+    def save(self, xml_path: str) -> None:
+        root = self.to_xml()
+        _ET.indent(root, space="  ")
+        _ET.ElementTree(root).write(xml_path, encoding="UTF-8", xml_declaration=True)
+
+
+def load_spimdata_xml(xml_path: str) -> SpimData2:
+    """Reader for what SpimData2.save wrote (and for hand-written projects of the same schema)."""
+    root = _ET.parse(xml_path).getroot()
+    seq = root.find("SequenceDescription")
+    ents = {}
+    for a in seq.find("ViewSetups").findall("Attributes"):
+        ents[a.get("name")] = {int(e.find("id").text): Entity(int(e.find("id").text), (e.find("name").text or "")) for e in a}
+    setups = []
+    for e in seq.find("ViewSetups").findall("ViewSetup"):
+        at = e.find("attributes")
+        size = e.find("size")
+        vx = e.find("voxelSize")
+        setups.append(ViewSetup(int(e.find("id").text),
+                                angle=ents["angle"][int(at.find("angle").text)],
+                                channel=ents["channel"][int(at.find("channel").text)],
+                                illumination=ents["illumination"][int(at.find("illumination").text)],
+                                name=(e.find("name").text if e.find("name") is not None else ""),
+                                size_xyz=tuple(int(x) for x in size.text.split()) if size is not None else None,
+                                voxel_size_xyz=tuple(float(x) for x in vx.find("size").text.split()),
+                                voxel_unit=vx.find("unit").text))
+    tps = [TimePoint(int(x)) for x in seq.find("Timepoints").find("integerpattern").text.split(",") if x.strip()]
+    il = seq.find("ImageLoader")
+    loader = None
+    if il is not None:
+        loader = FileNamePattern(int(il.find("layoutTimepoints").text), int(il.find("layoutChannels").text),
+                                 int(il.find("layoutIlluminations").text), int(il.find("layoutAngles").text), il.find("filePattern").text)
+    regs = {}
+    for r in root.find("ViewRegistrations").findall("ViewRegistration"):
+        regs[(int(r.get("timepoint")), int(r.get("setup")))] = [
+            (t.find("Name").text, tuple(float(x) for x in t.find("affine").text.split())) for t in r.findall("ViewTransform")]
+    return SpimData2(os.path.dirname(os.path.abspath(xml_path)), tps, setups, loader, regs)
+
+
+def fusion_bounding_box_transform(bb_min: Sequence[int], downsampling: float = 1.0) -> Tuple[str, Tuple[float, ...]]:
+    """ExportSpimData2TIFF.java:91-99 / AppendSpimData2.java:93-101: the registration of an exported volume is its bounding
+    box -- scale = downsampling, translation = bb.min -- replacing whatever transforms the view had."""
+    s = float(downsampling)
+    return ("fusion bounding box", (s, 0.0, 0.0, float(bb_min[0]), 0.0, s, 0.0, float(bb_min[1]), 0.0, 0.0, s, float(bb_min[2])))
+
+
+class ExportSpimData2TIFF:
+    """"Save as new XML Project (TIFF)", ExportSpimData2TIFF.java: stacks named by XMLTIFFImgTitler next to a new XML whose
+    loader pattern finds them again; finish() writes the XML and returns False (the caller's project was not modified)."""
+
+    def __init__(self, xml_path: str, compress: bool = False):
+        self.xml_path, self.compress = xml_path, compress
+        self.newTimepoints = self.newViewSetups = None
+        self.saver = self.spimData = None
+
+    def setXMLData(self, newTimepoints: Sequence[TimePoint], newViewSetups: Sequence[ViewSetup]) -> None:
+        self.newTimepoints, self.newViewSetups = list(newTimepoints), list(newViewSetups)
+
+    def queryParameters(self) -> bool:
+        if self.newTimepoints is None or self.newViewSetups is None:
+            return False      # "new timepoints and new viewsetup list not set yet ... cannot continue"
+        base = os.path.dirname(os.path.abspath(self.xml_path))
+        self.saver = Save3dTIFF(base, self.compress)
+        self.saver.setImgTitler(XMLTIFFImgTitler(self.newTimepoints, self.newViewSetups))
+        self.spimData = SpimData2(base, self.newTimepoints, self.newViewSetups,
+                                  getFileNamePattern(self.newTimepoints, self.newViewSetups, self.compress))
+        return True
+
+    def exportImage(self, img, bb_min: Sequence[int], tp: TimePoint, vs: ViewSetup, downsampling: int = 1,
+                    min: float = float("nan"), max: float = float("nan")) -> bool:
+        if not self.saver.exportImage(img, bb_min, downsampling, tp, vs, min, max):
+            return False
+        self.spimData.registrations[(tp.getId(), vs.getId())] = [fusion_bounding_box_transform(bb_min, downsampling)]
+        return True
+
+    def finish(self) -> bool:
+        self.spimData.save(self.xml_path)
+        return False
+
+    def getDescription(self) -> str:
+        return "Save as new XML Project (TIFF)"
+
+
+class AppendSpimData2(ExportSpimData2TIFF):
+    """"Append to current XML Project", AppendSpimData2.java (stack-loader branch): the new view setups / time points join an
+    EXISTING project -- its loader pattern must be able to name them (:219-262 checks exactly that) -- the stacks are written
+    next to it, and finish() returns True: the project object was modified and the caller saves it."""
+
+    def __init__(self, spimData: SpimData2, xml_path: str):
+        super().__init__(xml_path, False)
+        self.existing = spimData
+
+    def queryParameters(self) -> bool:
+        if self.newTimepoints is None or self.newViewSetups is None:
+            return False
+        if self.existing.loader is None:
+            raise NotImplementedError("AppendSpimData2: only projects with a stack image loader (TIFF) can be appended to; the HDF5 "
+                                      "branch (AppendSpimData2HDF5) needs an HDF5 library that this image does not provide")
+        ids = {v.id for v in self.existing.viewSetups}
+        if any(v.id in ids for v in self.newViewSetups):
+            raise ValueError("AppendSpimData2: new view setup ids collide with existing ones")
+        all_tps = sorted({t.id for t in self.existing.timepoints} | {t.id for t in self.newTimepoints})
+        all_vs = list(self.existing.viewSetups) + list(self.newViewSetups)
+        need = getFileNamePattern([TimePoint(t) for t in all_tps], all_vs)
+        have = self.existing.loader
+        for a, b, what in ((need.layoutTP, have.layoutTP, "timepoints"), (need.layoutChannels, have.layoutChannels, "channels"),
+                           (need.layoutIllum, have.layoutIllum, "illuminations"), (need.layoutAngles, have.layoutAngles, "angles")):
+            if a and not b:
+                raise ValueError(f"AppendSpimData2: the project's file pattern '{have.fileNamePattern}' cannot distinguish several {what}")
+        self.saver = Save3dTIFF(self.existing.basePath, False)
+        titler = _PatternTitler(have)
+        self.saver.setImgTitler(titler)
+        self.existing.viewSetups = all_vs
+        self.existing.timepoints = [TimePoint(t) for t in all_tps]
+        self.spimData = self.existing
+        return True
+
+    def finish(self) -> bool:
+        return True
+
+    def getDescription(self) -> str:
+        return "Append to current XML Project"
+
+
+class _PatternTitler:
+    """file name of (timepoint, setup) under a stack loader's pattern: {t} {c} {i} {a} replaced (StackImgLoader.getFileName)"""
+
+    def __init__(self, pattern: FileNamePattern):
+        self.p = pattern
+
+    def getImageTitle(self, tp: TimePoint, vs: ViewSetup) -> str:
+        return (self.p.fileNamePattern.replace("{t}", str(tp.getId())).replace("{c}", vs.getChannel().getName())
+                .replace("{i}", vs.getIllumination().getName()).replace("{a}", vs.getAngle().getName()))
+
+
+class ExportSpimData2HDF5:
+    """ExportSpimData2HDF5.java writes BigDataViewer HDF5 (multi-resolution chunked int16) through the un-vendored
+    bdv / jhdf5 libraries.  No HDF5 library exists in this image (h5py absent), so this exporter is declared, not built."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("HDF5 export needs an HDF5 library (h5py / jhdf5); use ExportSpimData2TIFF")
+
+
+AppendSpimData2HDF5 = ExportSpimData2HDF5

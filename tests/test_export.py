@@ -90,3 +90,56 @@ def test_load_and_transform_psfs_from_tiff(tmp_path, emu_lib):
     np.testing.assert_array_equal(e2.getTransformedPSF("v"), psf)
     with pytest.raises(RuntimeError):
         fusion.ExtractPSF.loadAndTransformPSFs({}, ["v"], None, lib=emu_lib)
+
+
+def test_xml_project_export_and_append(tmp_path):
+    """ExportSpimData2TIFF / AppendSpimData2 (ExportSpimData2TIFF.java:79-224, AppendSpimData2.java:75-262): file names by
+    XMLTIFFImgTitler, loader pattern with the layout flags, 'fusion bounding box' registrations, XML round trip."""
+    E = export
+    tps = [E.TimePoint(0), E.TimePoint(3)]
+    vss = [E.ViewSetup(0, channel=E.Entity(0, "488"), size_xyz=(9, 7, 5)), E.ViewSetup(1, channel=E.Entity(1, "561"), size_xyz=(9, 7, 5))]
+    pat = E.getFileNamePattern(tps, vss)
+    assert pat.fileNamePattern == "img_TL{t}_Ch{c}.tif" and (pat.layoutTP, pat.layoutChannels, pat.layoutIllum, pat.layoutAngles) == (1, 1, 0, 0)
+    assert E.getFileNamePattern(tps[:1], vss[:1]).fileNamePattern == "img.tif"
+    assert E.XMLTIFFImgTitler(tps, vss).getImageTitle(tps[1], vss[1]) == "img_TL3_Ch561"
+    xml = str(tmp_path / "dataset.xml")
+    ex = E.ExportSpimData2TIFF(xml)
+    assert ex.queryParameters() is False           # setXMLData first, like the reference
+    ex.setXMLData(tps, vss)
+    assert ex.queryParameters()
+    vols = {}
+    for tp in tps:
+        for vs in vss:
+            vols[(tp.id, vs.id)] = _vol((5, 7, 9), seed=10 * tp.id + vs.id)
+            assert ex.exportImage(vols[(tp.id, vs.id)], (10, -20, 30), tp, vs, downsampling=2)
+    assert ex.finish() is False
+    for (t, v), a in vols.items():
+        np.testing.assert_array_equal(E.read_tiff_stack(str(tmp_path / f"img_TL{t}_Ch{vss[v].channel.name}.tif")), a)
+    sd = E.load_spimdata_xml(xml)
+    assert [t.id for t in sd.timepoints] == [0, 3] and [v.id for v in sd.viewSetups] == [0, 1]
+    assert sd.viewSetups[1].channel == E.Entity(1, "561") and sd.viewSetups[0].size_xyz == (9, 7, 5)
+    assert sd.loader.fileNamePattern == "img_TL{t}_Ch{c}.tif" and sd.loader.layoutChannels == 1
+    name, m = sd.registrations[(3, 1)][0]
+    assert name == "fusion bounding box" and m == (2.0, 0, 0, 10.0, 0, 2.0, 0, -20.0, 0, 0, 2.0, 30.0)
+    txt = open(xml).read()
+    assert '<SpimData version="0.2">' in txt and 'format="spimreconstruction.stack.ij"' in txt and "<integerpattern>0,3</integerpattern>" in txt
+    # append a deconvolved channel to the project just written
+    new_vs = [E.ViewSetup(2, channel=E.Entity(2, "dc"), size_xyz=(9, 7, 5))]
+    ap = E.AppendSpimData2(sd, xml)
+    ap.setXMLData(tps, new_vs)
+    assert ap.queryParameters()
+    d = _vol((5, 7, 9), seed=99)
+    assert ap.exportImage(d, (0, 0, 0), tps[0], new_vs[0])
+    assert ap.finish() is True                     # the project object was modified: the caller saves it
+    sd.save(xml)
+    sd2 = E.load_spimdata_xml(xml)
+    assert [v.id for v in sd2.viewSetups] == [0, 1, 2] and sd2.registrations[(0, 2)][0][0] == "fusion bounding box"
+    np.testing.assert_array_equal(E.read_tiff_stack(str(tmp_path / "img_TL0_Chdc.tif")), d)
+    # a project whose pattern has no {c} cannot take a second channel
+    one = E.SpimData2(str(tmp_path), tps[:1], vss[:1], E.getFileNamePattern(tps[:1], vss[:1]))
+    ap2 = E.AppendSpimData2(one, xml)
+    ap2.setXMLData(tps[:1], new_vs)
+    with pytest.raises(ValueError):
+        ap2.queryParameters()
+    with pytest.raises(NotImplementedError):
+        E.ExportSpimData2HDF5()
