@@ -465,12 +465,13 @@ public:
         // (FFT lengths above ~880, e.g. the 1080-long axes of a 1024^2 x 512 volume on one GPU); SPIM_COL_NARROW=0/1 forces
         const size_t lim = rt::max_smem();
         const int narrow_env = env_int("SPIM_COL_NARROW", -1);
-        // staging: the persistent TMA / mbarrier pipeline where three tiles fit (FFT lengths up to ~590: the 72 KB y tiles of
-        // the bench volume run 0.136 / 0.126 ms instead of 0.161 / 0.148), but not for small tiles (<= 40 KB: five or six
-        // blocks per SM with one-shot cp.async staging are faster, 0.247 vs 0.300 ms on the z pass)
+        // staging: the persistent TMA / mbarrier pipeline for the plain forward / inverse passes where three tiles fit (FFT
+        // lengths up to ~590: the 72 KB y tiles of the bench volume run 0.136 / 0.126 ms instead of 0.161 / 0.148), but not for
+        // small tiles (<= 40 KB: five or six blocks per SM with one-shot cp.async staging are faster, 0.247 vs 0.300 ms on the
+        // z pass) and not for the fused forward-multiply-inverse pass (72 KB z tiles of the 1024^2 x 512 volume: 1.84 vs 1.94 ms)
         const size_t tile16 = (size_t)Pa * TC * sizeof(float2);
         int colp = env_int("SPIM_COLP", -1);
-        if (colp < 0) colp = tile16 > 40 * 1024 ? 3 : 2;
+        if (colp < 0) colp = (tile16 > 40 * 1024 && mode != COL_MID) ? 3 : 2;
         if (colp == 3 && 3 * tile16 + 64 > lim) colp = 2;
         const bool narrow = colp == 2 && (narrow_env >= 0 ? narrow_env != 0 : 2 * (tile16 + 1024) > lim);
         const int tcols = narrow ? TC / 2 : TC;
