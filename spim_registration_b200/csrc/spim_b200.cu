@@ -531,6 +531,7 @@ struct mvd_session {
 
     int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
     int conv2_ext() const { return prm.conv2_ext >= 0 ? prm.conv2_ext : (prm.generation == 2 ? EXT_CONSTANT : EXT_MIRROR_SINGLE); }
+    bool shift_active() const { return env_int("SPIM_CONST_SHIFT", 1) != 0 && conv2_ext() == EXT_CONSTANT; }
 
     size_t psi_bytes = 0, kh_bytes = 0;       // sizes the psi / ratio buffers and the kernel spectra were allocated with
 
@@ -678,8 +679,7 @@ struct mvd_session {
         // extension -- the halo outside the volume joins the zero gap of the padded transform -- and the update epilogue adds
         // c * sum(K2) back.  Neighbour-provided halos (brick mode) carry r - c like the interior.  SPIM_CONST_SHIFT=0 keeps
         // the literal constant extension (A/B and parity runs).
-        const bool shift_on = env_int("SPIM_CONST_SHIFT", 1) != 0;
-        const bool shift = shift_on && conv2_ext() == EXT_CONSTANT;
+        const bool shift = shift_active();
         const float cext = 1.f;
         if (ph == 0) {
             src.p = d_psi; src.ext = conv1_ext(); src.ext_value = 0.f;
@@ -1207,7 +1207,8 @@ int mvd_fill_halo(mvd_session* s, int which, int lo_mask, int hi_mask) {
     if (!s->prm.haloed || !s->d_psi) return fail("mvd_fill_halo: not a brick-mode session / not initialised");
     rt::set_device(s->prm.device);
     const int ext = which == 0 ? s->conv1_ext() : s->conv2_ext();
-    const float value = which == 0 ? 0.f : 1.f;
+    // the ratio buffer holds r - 1 when the constant extension is realised by shift (mvd_session::phase): its constant is 0
+    const float value = which == 0 ? 0.f : (s->shift_active() ? 0.f : 1.f);
     for (int axis = 2; axis >= 0; --axis) {
         for (int side = 0; side < 2; ++side) {
             const int mask = side == 0 ? lo_mask : hi_mask;

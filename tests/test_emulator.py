@@ -393,3 +393,31 @@ def test_constant_extension_by_shift(emu_lib, monkeypatch):
         assert per <= 2e-5 and l2 <= 2e-6, (typ, per, l2)
     monkeypatch.setenv("SPIM_CONST_SHIFT", "1")
     P.decon_case(emu_lib, shape, 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
+
+
+def test_single_brick_with_rule_filled_halos_equals_plain_session(emu_lib, monkeypatch):
+    """Brick mode on one rank with EVERY halo declared neighbour data and filled by the out-of-bounds rule
+    (mvd_fill_halo) must reproduce the plain session -- also with conv2's constant realised by shift, where the ratio
+    buffer holds r - 1 and its rule constant therefore is 0."""
+    from spim_registration_b200 import synthetic
+    from spim_registration_b200.deconvolution import Session
+    shape, V = (12, 16, 20), 2
+    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, 5)
+    for shift in ("1", "0"):
+        monkeypatch.setenv("SPIM_CONST_SHIFT", shift)
+        with Session(shape, V, 2, generation=2, haloed=True, lib=emu_lib) as s:
+            for v in range(V):
+                s.set_view(v, imgs[v], ws[v], psfs[v])
+            s.init()
+            part = s.init_partials()
+            s.set_avg(part[0] / part[1], 1.0)
+            s.set_halo_mask(7, 7)
+            for v in range(V):
+                s.fill_halo(0, 7, 7)
+                s.view_phase(v, 0)
+                s.fill_halo(1, 7, 7)
+                s.view_phase(v, 1)
+            s.finish()
+            brick = s.get_psi()
+        plain, *_ = P.run_session(emu_lib, imgs, ws, psfs, 2, 2, 1)
+        assert np.abs(brick - plain).max() <= 1e-5 * np.abs(plain).max(), shift
