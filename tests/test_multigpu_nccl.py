@@ -99,3 +99,43 @@ def test_bricks_in_one_process_one_thread_per_device(gpu, monkeypatch):
     ref = O.deconvolve(imgs, ws, psfs, O.DeconParams(iteration_type=typ, num_iterations=iters, lam=0.006, gen=gen))
     per, l2 = O.parity_errors(psi, ref.psi)
     assert per <= 1e-3 and l2 <= 1e-4, (per, l2)
+
+
+def _fullsize(args, world, timeout):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29561", os.path.join(ROOT, "tests", "run_bricks_fullsize.py")] + args
+    if world == 1:
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "run_bricks_fullsize.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    print(r.stdout[-1500:])
+    assert "FULLSIZE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_fullsize_configs1_one_full_iteration_against_the_oracle(gpu):
+    """BASELINE configs[1] at full size on one GPU (7 views, 512x512x256, 31^3 PSFs, Efficient-Bayesian): one full iteration,
+    then sub-bricks at the volume centre and at the volume corner are recomputed by the oracle from crops of the inputs
+    (dependency cone of 7 view-steps included)."""
+    _fullsize(["--config", "custom", "--brick", "256", "512", "512", "--views", "7", "--iter-type", "2"], 1, 500)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_fullsize_configs2_bricks_on_all_gpus(gpu):
+    """BASELINE configs[2] geometry: bricks of 512x512x256 on every GPU of the box (8 -> the 1024x1024x512 volume), one full
+    iteration, sub-bricks straddling brick faces / the corner of all bricks / the volume corner against the oracle."""
+    n = gpu.getNumDevicesCUDA()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _fullsize(["--config", "c3"], 8 if n >= 8 else (4 if n >= 4 else 2), 800)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(1200)
+def test_configs4_on_8_gpus(gpu):
+    """BASELINE configs[4]: 8 views, 2048x2048x1024 in bricks of 1024x1024x512 on 8 GPUs (89 GB of HBM each), views handed over
+    cell by cell with mvd_upload_region; the first view-steps checked against the oracle, then 10 iterations."""
+    if gpu.getNumDevicesCUDA() < 8:
+        pytest.skip("needs 8 GPUs")
+    _fullsize(["--config", "c5"], 8, 1100)
