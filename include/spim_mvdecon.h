@@ -82,14 +82,6 @@ void mvd_session_destroy(mvd_session* s);
 int mvd_set_view(mvd_session* s, int view, const float* img, const float* weight,
                  const float* psf, const int psf_dims[3]);
 
-/* The same without waiting for the copy: the transfers are queued on the session's copy stream and mvd_set_view_async returns
- * at once (pinned host memory; pageable memory is staged by the driver and simply copies synchronously).  img / weight
- * must stay valid until mvd_init returns: mvd_init builds the kernels and their spectra -- which need only the PSFs --
- * while the views are still arriving, and waits for the copies before it first reads them.  Any other entry that
- * touches the views waits as well. */
-int mvd_set_view_async(mvd_session* s, int view, const float* img, const float* weight,
-                       const float* psf, const int psf_dims[3]);
-
 /* The same for volumes handed over in cells (imglib2 CellImg) or larger than Java's 2^31-element arrays:
  * upload the box [lo, lo + ext) (z, y, x) of the view's image (which = 0) or weight (which = 1) from a tightly
  * packed host buffer.  The first call for a buffer creates it zero-filled; the PSF is set with mvd_set_psf

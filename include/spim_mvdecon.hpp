@@ -175,10 +175,9 @@ public:
                 if (view.getImage().dims != first.dims) throw std::invalid_argument("all views must have the same dims");
                 const Image& k = view.getKernel1();
                 const int kd[3] = {k.dims[2], k.dims[1], k.dims[0]};
-                // queued, not awaited: the views (owned by `data`, alive until mvd_init returns) travel while mvd_init builds the kernels
-                check(mvd_set_view_async(s_, v, view.getImage().data.data(),
-                                         view.getWeight().empty() ? nullptr : view.getWeight().data.data(), k.data.data(), kd),
-                      "mvd_set_view_async");
+                check(mvd_set_view(s_, v, view.getImage().data.data(),
+                                   view.getWeight().empty() ? nullptr : view.getWeight().data.data(), k.data.data(), kd),
+                      "mvd_set_view");
             }
             check(mvd_init(s_), "mvd_init");              // views.init( iterationType ), psi = avg, OSEM clamp
             for (int v = 0; v < (int)data.size(); ++v) {   // expose the normalised kernel1 and kernel2 on the views

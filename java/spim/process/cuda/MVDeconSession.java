@@ -50,9 +50,6 @@ public interface MVDeconSession extends Library
 	int mvd_session_create( Params p, PointerByReference session );
 	void mvd_session_destroy( Pointer session );
 	int mvd_set_view( Pointer session, int view, float[] img, float[] weight, float[] psf, int[] psfDimsZYX );
-	/** the same with the copies queued, not awaited: img / weight must be native memory (com.sun.jna.Memory or a direct
-	 *  NIO buffer -- JNA copies Java arrays only for the duration of the call) that stays valid until mvd_init returns */
-	int mvd_set_view_async( Pointer session, int view, Pointer img, Pointer weight, float[] psf, int[] psfDimsZYX );
 	int mvd_init( Pointer session );
 	int mvd_run( Pointer session, int nIterations, double[] sumChange, double[] maxChange );
 	int mvd_finish( Pointer session );

@@ -60,7 +60,6 @@ int mvd_load_stack(mvd_session* s, const float* stack, const int dims[3], int no
     SPIM_API_BEGIN
     if (!s) return fail("mvd_load_stack: null session");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     if (!stack) {
         rt::stream_sync(s->stream);
         rt::dfree(s->d_stack);
@@ -112,7 +111,6 @@ int mvd_transform_view(mvd_session* s, int view, const mvd_transform* t) {
     if (t->want_image && !s->d_stack) return fail("mvd_transform_view: no stack loaded (mvd_load_stack)");
     if (s->stack_dims[0] < 1) return fail("mvd_transform_view: stack dimensions unknown (mvd_load_stack)");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     const size_t bytes = (size_t)s->N * sizeof(float);
     if (t->want_image && !s->d_img[view]) s->d_img[view] = (float*)s->dalloc(bytes);
     if (t->want_weight && !s->d_w[view]) s->d_w[view] = (float*)s->dalloc(bytes);
@@ -164,7 +162,6 @@ int mvd_normalize_weights(mvd_session* s, int mode, int num_portions, int* min_v
     const int V = s->prm.num_views;
     for (int v = 0; v < V; ++v) if (!s->d_w[v]) return fail("mvd_normalize_weights: view " + std::to_string(v) + " has no weight image");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     WeightNormParams p;
     memset(&p, 0, sizeof(p));
     p.v.nviews = V;
@@ -216,7 +213,6 @@ int mvd_get_view(mvd_session* s, int view, int which, float* out) {
     const float* src = which == 0 ? s->d_img[view] : s->d_w[view];
     if (!src) return fail("mvd_get_view: buffer not set (constant weight or missing image)");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     rt::d2h(out, src, (size_t)s->N * sizeof(float), s->stream);
     rt::stream_sync(s->stream);
     return 0;
@@ -230,7 +226,6 @@ int mvd_extract_psf(mvd_session* s, int n_beads, const double* locations_xyz, co
     if (!s->d_stack) return fail("mvd_extract_psf: no stack loaded (mvd_load_stack)");
     for (int d = 0; d < 3; ++d) if (size[d] < 1) return fail("mvd_extract_psf: bad size");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     const long long n = (long long)size[0] * size[1] * size[2];
     float* d_out = (float*)rt::dmalloc((size_t)n * sizeof(float));
     double* d_loc = (double*)rt::dmalloc((size_t)std::max(1, n_beads) * 3 * sizeof(double));

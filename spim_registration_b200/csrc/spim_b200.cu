@@ -497,9 +497,6 @@ struct mvd_session {
     ConvPlan plan;
     bool plan_ok = false, inited = false;
     rt::Stream stream = 0;
-    rt::Stream copy_stream = 0;        // mvd_set_view_async: host -> device copies that overlap mvd_init's kernel work
-    bool have_copy_stream = false, copies_pending = false;
-    void wait_copies() { if (copies_pending) { rt::stream_sync(copy_stream); copies_pending = false; } }
     rt::KernelTimer timer;
     double* d_stat_sum = nullptr;
     unsigned int* d_stat_max = nullptr;
@@ -777,7 +774,6 @@ void mvd_session_destroy(mvd_session* s) {
     if (!s) return;
     try {
         rt::set_device(s->prm.device);
-        s->wait_copies();
         rt::stream_sync(s->stream);
         for (auto p : s->d_img) rt::dfree(p);
         for (auto p : s->d_w) rt::dfree(p);
@@ -790,48 +786,31 @@ void mvd_session_destroy(mvd_session* s) {
         rt::dfree(s->p2p.d_ctl);
         if (s->plan_ok) s->plan.destroy();
         rt::stream_destroy(s->stream);
-        if (s->have_copy_stream) rt::stream_destroy(s->copy_stream);
     } catch (...) {}
     delete s;
 }
 
-static int set_view_common(mvd_session* s, int v, const float* img, const float* weight, const float* psf, const int psf_dims[3], bool async) {
+int mvd_set_view(mvd_session* s, int v, const float* img, const float* weight, const float* psf, const int psf_dims[3]) {
+    SPIM_API_BEGIN
     if (!s || !img || !psf || !psf_dims) return fail("mvd_set_view: null argument");
     if (v < 0 || v >= s->prm.num_views) return fail("mvd_set_view: view index out of range");
     for (int d = 0; d < 3; ++d) if (psf_dims[d] < 1) return fail("mvd_set_view: bad psf dims");
     rt::set_device(s->prm.device);
-    if (async && !s->have_copy_stream) { s->copy_stream = rt::stream_create(); s->have_copy_stream = true; }
-    if (async) rt::stream_sync(s->stream);         // nothing queued earlier may still read the buffers about to be overwritten
-    else s->wait_copies();
-    const rt::Stream st = async ? s->copy_stream : s->stream;
     const size_t bytes = (size_t)s->N * sizeof(float);
     if (!s->d_img[v]) s->d_img[v] = (float*)s->dalloc(bytes);
-    rt::h2d(s->d_img[v], img, bytes, st);
+    rt::h2d(s->d_img[v], img, bytes, s->stream);
     if (weight) {
         if (!s->d_w[v]) s->d_w[v] = (float*)s->dalloc(bytes);
-        rt::h2d(s->d_w[v], weight, bytes, st);
+        rt::h2d(s->d_w[v], weight, bytes, s->stream);
     } else if (s->d_w[v]) {
-        s->wait_copies();
         rt::dfree(s->d_w[v]); s->d_w[v] = nullptr;
     }
     HostVol& k = s->psf[v];
     for (int d = 0; d < 3; ++d) k.d[d] = psf_dims[d];
     k.v.assign(psf, psf + k.size());
-    if (async) s->copies_pending = true;
-    else rt::stream_sync(s->stream);
+    rt::stream_sync(s->stream);
     s->inited = false;
     return 0;
-}
-
-int mvd_set_view(mvd_session* s, int v, const float* img, const float* weight, const float* psf, const int psf_dims[3]) {
-    SPIM_API_BEGIN
-    return set_view_common(s, v, img, weight, psf, psf_dims, false);
-    SPIM_API_END
-}
-
-int mvd_set_view_async(mvd_session* s, int v, const float* img, const float* weight, const float* psf, const int psf_dims[3]) {
-    SPIM_API_BEGIN
-    return set_view_common(s, v, img, weight, psf, psf_dims, true);
     SPIM_API_END
 }
 
@@ -843,7 +822,6 @@ int mvd_upload_region(mvd_session* s, int view, int which, const float* data, co
     for (int d = 0; d < 3; ++d)
         if (lo[d] < 0 || ext[d] < 1 || (long long)lo[d] + ext[d] > s->n[d]) return fail("mvd_upload_region: region out of range");
     rt::set_device(s->prm.device);
-    s->wait_copies();
     float*& dst = which == 0 ? s->d_img[view] : s->d_w[view];
     if (!dst) {
         // a freshly created buffer starts as "no data" (image 0) / "no contribution" (weight 0)
@@ -922,8 +900,7 @@ int mvd_init(mvd_session* s) {
     SPIM_API_BEGIN
     if (!s) return fail("mvd_init: null session");
     rt::set_device(s->prm.device);
-    if (int rc = session_prepare(s)) { s->wait_copies(); return rc; }      // kernels + spectra: only the PSFs are needed
-    s->wait_copies();                                                       // ... the views from here on
+    if (int rc = session_prepare(s)) return rc;
     if (s->prm.haloed) return 0;   // brick mode: caller all-reduces mvd_init_partials and calls mvd_set_avg
     double part[6];
     s->partials(part);

@@ -65,7 +65,6 @@ class Session:
         self.dims = tuple(int(d) for d in dims)
         self.num_views = int(num_views)
         self.psf_dims: List[tuple] = [()] * self.num_views
-        self._pending: list = []                # host arrays of queued asynchronous uploads, released by init()
         self._h = C.c_void_p()
         native.check(self.lib, self.lib.mvd_session_create(C.byref(p), C.byref(self._h)), "mvd_session_create")
 
@@ -86,9 +85,7 @@ class Session:
     def __exit__(self, *a):
         self.close()
 
-    def set_view(self, v: int, img: np.ndarray, weight: Optional[np.ndarray], psf: np.ndarray, asynchronous: bool = False):
-        """Hand a view over.  ``asynchronous``: queue the host -> device copies (mvd_set_view_async) and return at once; init()
-        builds the kernel spectra while the views are still arriving and waits for them before it first reads them."""
+    def set_view(self, v: int, img: np.ndarray, weight: Optional[np.ndarray], psf: np.ndarray):
         img = np.ascontiguousarray(img, dtype=np.float32)
         if img.shape != self.dims:
             raise ValueError(f"view {v}: image shape {img.shape} != session dims {self.dims}")
@@ -97,11 +94,8 @@ class Session:
             raise ValueError(f"view {v}: weight shape {w.shape} != session dims {self.dims}")
         k = np.ascontiguousarray(psf, dtype=np.float32)
         self.psf_dims[v] = k.shape
-        fn = self.lib.mvd_set_view_async if asynchronous else self.lib.mvd_set_view
-        if asynchronous:
-            self._pending.append((img, w))       # the host buffers must outlive the queued copies (until init returns)
-        native.check(self.lib, fn(self._h, v, img.ctypes.data, None if w is None else w.ctypes.data,
-                                  k.ctypes.data, native.int3(k.shape)), "mvd_set_view")
+        native.check(self.lib, self.lib.mvd_set_view(self._h, v, img.ctypes.data, None if w is None else w.ctypes.data,
+                                                     k.ctypes.data, native.int3(k.shape)), "mvd_set_view")
 
     def set_view_ptr(self, v: int, img_ptr: int, weight_ptr: Optional[int], psf: np.ndarray):
         """Same with raw host pointers (e.g. pinned torch tensors' ``data_ptr()``)."""
@@ -124,10 +118,7 @@ class Session:
                                                           native.int3(ext)), "mvd_upload_region")
 
     def init(self):
-        try:
-            native.check(self.lib, self.lib.mvd_init(self._h), "mvd_init")
-        finally:
-            self._pending.clear()               # mvd_init has waited for every queued copy, also on failure
+        native.check(self.lib, self.lib.mvd_init(self._h), "mvd_init")
 
     def run(self, n_iterations: int, stats: bool = True):
         n = n_iterations * self.num_views
@@ -569,8 +560,7 @@ class _Deconvolution(Deconvolver):
                                 osem_index=int(osemspeedupindex), device=dev)
         for v, view in enumerate(self.data):
             view.init(PSFTYPE(iterationType), self.data)
-            # queued, not awaited: the views travel over PCIe while init() builds the kernels and their spectra from the PSFs
-            self._session.set_view(v, view.getImage(), view.getWeight(), view.getKernel1(), asynchronous=True)
+            self._session.set_view(v, view.getImage(), view.getWeight(), view.getKernel1())
         # views.init(iterationType) + psi initialisation happen on the device
         self._session.init()
         for v, view in enumerate(self.data):

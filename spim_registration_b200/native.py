@@ -69,7 +69,7 @@ LEGACY_SYMBOLS = (
     "convolution3DfftCUDA", "spim_fftconv_last_error",
 )
 SESSION_SYMBOLS = (
-    "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_set_view_async", "mvd_upload_region", "mvd_init", "mvd_run",
+    "mvd_params_default", "mvd_session_create", "mvd_session_destroy", "mvd_set_view", "mvd_upload_region", "mvd_init", "mvd_run",
     "mvd_finish", "mvd_get_psi", "mvd_set_psi", "mvd_get_kernel", "mvd_get_info", "mvd_sync", "mvd_get_stream", "mvd_set_timing",
     "mvd_get_timing", "mvd_get_device_buffer", "mvd_set_halo_mask", "mvd_halo_pack", "mvd_halo_unpack", "mvd_fill_halo", "mvd_view_phase", "mvd_init_partials",
     "mvd_set_avg", "mvd_p2p_export", "mvd_p2p_connect", "mvd_p2p_push", "mvd_p2p_wait", "mvd_p2p_status", "mvd_p2p_disconnect", "mvd_convolve", "mvd_fft_size", "mvd_debug_counter", "mvd_last_error", "mvd_version",
@@ -133,8 +133,6 @@ def _declare(lib: C.CDLL) -> None:
     lib.mvd_session_destroy.restype = None
     lib.mvd_set_view.argtypes = [S, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]
     lib.mvd_set_view.restype = C.c_int
-    lib.mvd_set_view_async.argtypes = [S, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]
-    lib.mvd_set_view_async.restype = C.c_int
     lib.mvd_upload_region.argtypes = [S, C.c_int, C.c_int, C.c_void_p, c_int_p, c_int_p]
     lib.mvd_upload_region.restype = C.c_int
     lib.mvd_init.argtypes = [S]

@@ -421,24 +421,3 @@ def test_single_brick_with_rule_filled_halos_equals_plain_session(emu_lib, monke
             brick = s.get_psi()
         plain, *_ = P.run_session(emu_lib, imgs, ws, psfs, 2, 2, 1)
         assert np.abs(brick - plain).max() <= 1e-5 * np.abs(plain).max(), shift
-
-
-def test_asynchronous_view_hand_over(emu_lib):
-    """mvd_set_view_async queues the uploads and mvd_init waits for them after building the kernels: the result is the
-    synchronous one bit for bit, and re-setting a view asynchronously after a run is safe."""
-    from spim_registration_b200 import synthetic
-    from spim_registration_b200.deconvolution import Session
-    shape, V = (12, 16, 20), 3
-    _, imgs, ws, psfs = synthetic.make_dataset(shape, V, 5)
-    res = []
-    for asyn in (False, True):
-        with Session(shape, V, 2, generation=2, lib=emu_lib) as s:
-            for v in range(V):
-                s.set_view(v, imgs[v], ws[v], psfs[v], asynchronous=asyn)
-            s.init()
-            s.run(2)
-            s.set_view(0, imgs[1], ws[1], psfs[0], asynchronous=asyn)      # replace a view, initialise again
-            s.init()
-            s.run(1)
-            res.append(s.get_psi())
-    assert np.array_equal(res[0], res[1])
