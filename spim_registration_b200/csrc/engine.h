@@ -138,7 +138,8 @@ struct FftPlanHost {
 //   SPIM_XFWD_TMA=0   x-forward from the plain-load kernel (XFwd) instead of the TMA-fed pipeline (XFwdT)
 //   SPIM_COLP=0|2|3   column passes: 0 first stage straight from global memory, 2 one-shot cp.async staging, 3 persistent
 //                     TMA / mbarrier pipeline; unset = 3 for large tiles (y passes of the bench volume), 2 for small ones
-//   SPIM_COL_NARROW=0|1  force 16- / 8-column tiles (unset: narrow where a 16-column tile leaves one block per SM)
+//   SPIM_COL_NARROW=0|1  force 16- / 8-column tiles (unset: narrow where a 16-column tile leaves one block per SM);
+//                        SPIM_XFWD_LINES=16|8 the same for the lines per x-forward tile
 //   SPIM_FAST_EPI=0|1    override mvd_params.fast_epilogue
 //   SPIM_CONST_SHIFT=0   gen-2 conv2 with the literal constant extension instead of zero extension of (ratio - 1) (spim_b200.cu)
 //   SPIM_DEDUP=0         forward sweeps transform every padded line / plane instead of only those that exist as data
@@ -409,13 +410,20 @@ public:
             q.x = p;
             q.LS = (std::max(p.sx, p.ox + P[2]) + 3) & ~3;
             q.row_bytes = (unsigned)p.sx * 4u;
-            const size_t slot_bytes = (size_t)TC * q.LS * sizeof(float);
             const XFix fx_ = x_fix_table(p.nx, p.hpx, p.hmx, p.sx, p.ox, p.ext, (src.halo_lo >> 2) & 1, (src.halo_hi >> 2) & 1, st);
-            const size_t sm = (size_t)N2 * TC * sizeof(float2) + (XFwdT::MAXSLOT + 1) * TC * 2 * sizeof(long long) + XFwdT::MAXSLOT * sizeof(uint64_t) +
-                              (XFwdT::MAXSLOT + 1) * sizeof(int) + (size_t)std::max(1, fx_.n) * sizeof(int2) + slot_bytes;
             const size_t lim = rt::max_smem();
+            // shared memory of a block with L lines per tile: packed tile + one staging slot + descriptors + fix-up list
+            auto smem_for = [&](int L) {
+                return (size_t)N2 * L * sizeof(float2) + (size_t)L * q.LS * sizeof(float) + (XFwdT::MAXSLOT + 1) * L * 2 * sizeof(long long) +
+                       XFwdT::MAXSLOT * sizeof(uint64_t) + (XFwdT::MAXSLOT + 1) * sizeof(int) + (size_t)std::max(1, fx_.n) * sizeof(int2);
+            };
+            // 16 lines per tile; lines so long that this leaves one block per SM (1080 voxels and more) run 8-line tiles, three
+            // blocks per SM again (SPIM_XFWD_LINES=16 / 8 forces either for A/B runs and tests)
+            int L = TC;
+            const int want = env_int("SPIM_XFWD_LINES", 0);
+            if (want == 8 || (want != 16 && 2 * (smem_for(TC) + 1024) > lim)) L = TC / 2;
+            const size_t sm = smem_for(L);
             if (sm + 1024 <= lim) {
-                // one staging slot per block; three blocks per SM where that fits (tiles up to ~36 KB), else two, else one
                 const int bps = (int)std::min<size_t>(3, lim / (sm + 1024));
                 q.fix = fx_.d; q.nfix = fx_.n;
                 q.magic_nfix = magic_for(std::max(1, fx_.n));
@@ -424,25 +432,28 @@ public:
                 q.cval = p.ext == EXT_CONSTANT ? p.ext_value : 0.f;
                 q.const_row = const_row(p.sx, q.cval, st);
                 q.nslot = 1;
-                long long tiles = grid;
                 if (dd && dd->on) {
                     q.dedup = 1;
                     q.UY = dd->y.U; q.UZ = dd->z.U; q.splity = dd->y.split; q.splitz = dd->z.split;
                     q.dupy = dd->y.d_dup;
                     q.x.nlines = (long long)q.UY * q.UZ;
-                    tiles = (q.x.nlines + TC - 1) / TC;
                 }
+                const long long tiles = (q.x.nlines + L - 1) / L;
                 q.ntiles = (int)tiles;
                 q.nctas = (int)std::min<long long>(tiles, (long long)rt::sm_count() * bps);
                 if (timer) timer->begin(K_XFWD, st);
                 // three blocks per SM: 160 threads each -- the phases of a tile hold (N2 / R) * 8 items (280 / 320 / 448 for the
                 // 280-point plan 8 * 7 * 5, 282 for the split step), which 160 threads cover in 2 + 2 + 3 + 2 rounds at 92 % lane
                 // use where 256 threads need 2 + 2 + 2 + 2 at 65 % (measured 0.197 vs 0.208 ms, profiles/r2)
-                if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, 160, sm, st);
+                if (L == TC / 2) {
+                    if (bps >= 3) rt::launch<XFwdTNarrow, 256, 3>(q, q.nctas, 160, sm, st);      // 216 / 240 / 360 / 271 items per phase: 1.35 ms with 160 threads, 1.39 with 256
+                    else rt::launch<XFwdTNarrow, 384, 2>(q, q.nctas, bps == 2 ? 384 : 512, sm, st);
+                }
+                else if (bps >= 3) rt::launch<XFwdT, 256, 3>(q, q.nctas, 160, sm, st);
                 else if (bps == 2) rt::launch<XFwdT, 384, 2>(q, q.nctas, 384, sm, st);
-                // one block per SM (lines of 1080 voxels and longer): 768 threads at <= 85 registers -- the 432 / 480 / 720 / 542 items
-                // of a 540-point tile then take one round per phase (SPIM_XFWD_T1 overrides for A/B runs)
-                else rt::launch<XFwdT, 768, 1>(q, q.nctas, env_int("SPIM_XFWD_T1", 768), sm, st);
+                // one block per SM: 768 threads at <= 85 registers -- the 432 / 480 / 720 / 542 items of a 540-point tile then take
+                // one round per phase
+                else rt::launch<XFwdT, 768, 1>(q, q.nctas, 768, sm, st);
                 if (timer) timer->end(K_XFWD, st);
                 return;
             }

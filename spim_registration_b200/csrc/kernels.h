@@ -146,6 +146,9 @@ SPIM_DEV void mul_twiddles1(float2 (&a)[R], const float2 (&w)[R]) {
 // physical float4 slot of column pair c2 in row `row` (x kernels rotate the pairs so that the
 // transposing first / last phases are conflict-free)
 SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
+// the same rotation for a tile row of W pairs: W = 8 (128-byte rows) rotates by the row, W = 4 (64-byte rows, two rows per
+// 128 bytes of banks) by every second row, so that 8 consecutive rows of one pair still cover all eight 16-byte bank groups
+template <int W> SPIM_HD int xslot(int c2, int row) { return W == 8 ? ((c2 + row) & 7) : ((c2 + (row >> 1)) & 3); }
 
 // twiddle multiply of a packed pair: x[p] *= w[p] (forward) or conj(w[p]) (inverse), w broadcast to both columns
 template <int R, bool INV>
@@ -202,7 +205,7 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
             }
         } else {
             float4 v[R];
-            if (W != TP || !swz) {
+            if (!swz) {
                 const float4* sp = tile + base * W + c2;
 #pragma unroll
                 for (int q = 0; q < R; ++q) v[q] = sp[q * M * W];
@@ -210,7 +213,7 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
                     const int row = base + q * M;
-                    v[q] = tile[row * TP + ((c2 + row) & (TP - 1))];
+                    v[q] = tile[row * W + xslot<W>(c2, row)];
                 }
             }
             if (src_p) {
@@ -256,7 +259,7 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
 #pragma unroll
                 for (int q = 0; q < R; ++q) v[q] = c2_to_il(x[q]);
             }
-            if (W != TP || !swz) {
+            if (!swz) {
                 float4* sp = tile + base * W + c2;
 #pragma unroll
                 for (int q = 0; q < R; ++q) sp[q * M * W] = v[q];
@@ -264,7 +267,7 @@ SPIM_DEV void stage_tile(const TG& tg, const FftPlanDev& pl, int s, float4* tile
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
                     const int row = base + q * M;
-                    tile[row * TP + ((c2 + row) & (TP - 1))] = v[q];
+                    tile[row * W + xslot<W>(c2, row)] = v[q];
                 }
             }
         }
@@ -755,10 +758,10 @@ SPIM_DEV void split_inv(C2 A, C2 B, float2 w, C2& zk, C2& zm) {
 // 1/2 folded into the kernel scale).  One item = one frequency pair (k, N2 - k) of FOUR line pairs, see xinv_presplit.
 // dstoff[line * DS]: destination row of a line; DS = 2 (XFwdT): dstoff[line * 2 + 1] = a second row that receives the same
 // spectrum (the mirrored halo row) or -1 -- visited only when `anydup` says the tile has one
-template <int DS>
+template <int DS, int W = TP>
 SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long long* dstoff, int N2, int anydup = 0) {
     const int nk = p.nk;
-    SPIM_FOR_ITEMS(i, nk * (TP / 4)) {
+    SPIM_FOR_ITEMS(i, nk * (W / 4)) {
         const int h = fastdiv(i, p.magic_nk);
         const int k = i - h * nk;
         const int km = N2 - k;
@@ -770,8 +773,8 @@ SPIM_DEV void xfwd_split(const XFwdParams& p, const float4* tile, const long lon
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int bp = h * 4 + g;
-            zk[g] = tile[rk * TP + ((bp + rk) & (TP - 1))];
-            zm[g] = tile[rm * TP + ((bp + rm) & (TP - 1))];
+            zk[g] = tile[rk * W + xslot<W>(bp, rk)];
+            zm[g] = tile[rm * W + xslot<W>(bp, rm)];
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -931,12 +934,12 @@ SPIM_DEV const float* xfwd_line(const XFwdTParams& q, long long l, long long& d_
     return cst ? q.const_row : p.src + ((long long)jz * p.sy + jy) * (long long)p.sx;
 }
 
-template <int R>
+template <int R, int W>
 SPIM_DEV void xfwdt_stage0(const XFwdParams& p, float4* tile, const float* stg, int LS) {
     const FftPlanDev& pl = p.plan;
     const int M = pl.M[0];
     const float2* twp = pl.tws + pl.tw_off[0];
-    SPIM_FOR_ITEMS(i, M * TP) {
+    SPIM_FOR_ITEMS(i, M * W) {
         const int bp = (M == 1) ? i : fastdiv(i, p.magic_m0);
         const int m = i - bp * M;
         const float2* l0 = reinterpret_cast<const float2*>(stg + (2 * bp) * LS + p.ox) + m;
@@ -952,12 +955,14 @@ SPIM_DEV void xfwdt_stage0(const XFwdParams& p, float4* tile, const float* stg, 
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int row = m + q * M;
-            tile[row * TP + ((bp + row) & (TP - 1))] = c2_to_pk(x[q]);      // packed tile (stage_tile)
+            tile[row * W + xslot<W>(bp, row)] = c2_to_pk(x[q]);      // packed tile (stage_tile)
         }
     }
 }
 
-struct XFwdT {
+template <int W>
+struct XFwdTW {
+    static constexpr int TCW = 2 * W;           // lines per tile
     typedef XFwdTParams Params;
     static constexpr bool kEmuThreads = true;
     static constexpr int MAXSLOT = 3;
@@ -965,12 +970,12 @@ struct XFwdT {
     SPIM_DEV static void issue(const Params& q, int t, int slot, float* stg, long long* dsto, int* anyd, uint64_t* full) {
 #if defined(SPIM_HOST_EMU)
         (void)full;
-        SPIM_FOR_ITEMS(b, TC) {
+        SPIM_FOR_ITEMS(b, TCW) {
             long long d_o, d_dup;
-            const float* sp = xfwd_line(q, (long long)t * TC + b, d_o, d_dup);
-            dsto[(slot * TC + b) * 2] = d_o;
-            dsto[(slot * TC + b) * 2 + 1] = d_dup;
-            if (sp) memcpy(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes);
+            const float* sp = xfwd_line(q, (long long)t * TCW + b, d_o, d_dup);
+            dsto[(slot * TCW + b) * 2] = d_o;
+            dsto[(slot * TCW + b) * 2 + 1] = d_dup;
+            if (sp) memcpy(stg + ((size_t)slot * TCW + b) * q.LS, sp, q.row_bytes);
         }
         anyd[slot] = q.dedup;       // (threads of the emulated block write the same value)
 #else
@@ -978,16 +983,16 @@ struct XFwdT {
             const int b = (int)threadIdx.x;
             long long d_o = -1, d_dup = -1;
             const float* sp = nullptr;
-            if (b < TC) {
-                sp = xfwd_line(q, (long long)t * TC + b, d_o, d_dup);
-                dsto[(slot * TC + b) * 2] = d_o;
-                dsto[(slot * TC + b) * 2 + 1] = d_dup;
+            if (b < TCW) {
+                sp = xfwd_line(q, (long long)t * TCW + b, d_o, d_dup);
+                dsto[(slot * TCW + b) * 2] = d_o;
+                dsto[(slot * TCW + b) * 2 + 1] = d_dup;
             }
             const unsigned live = __ballot_sync(0xffffffffu, sp != nullptr);
             const unsigned dups = __ballot_sync(0xffffffffu, d_dup >= 0);
             if (b == 0) { anyd[slot] = dups != 0u; mbar_expect_tx(full + slot, (unsigned)__popc(live) * q.row_bytes); }
             __syncwarp();
-            if (sp) bulk_g2s(stg + ((size_t)slot * TC + b) * q.LS, sp, q.row_bytes, full + slot);
+            if (sp) bulk_g2s(stg + ((size_t)slot * TCW + b) * q.LS, sp, q.row_bytes, full + slot);
         }
 #endif
     }
@@ -997,10 +1002,10 @@ struct XFwdT {
         const FftPlanDev& pl = p.plan;
         const int N2 = pl.n;
         float4* tile = reinterpret_cast<float4*>(smem2);
-        float* stg = reinterpret_cast<float*>(smem2 + (size_t)N2 * TC);
-        long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TC * q.LS);     // [nslot][TC][2]
-        long long* dcur = dsto + MAXSLOT * TC * 2;                                             // [TC][2], the tile in work
-        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TC * 2);                           // [MAXSLOT]
+        float* stg = reinterpret_cast<float*>(smem2 + (size_t)N2 * TCW);
+        long long* dsto = reinterpret_cast<long long*>(stg + (size_t)q.nslot * TCW * q.LS);     // [nslot][TCW][2]
+        long long* dcur = dsto + MAXSLOT * TCW * 2;                                             // [TCW][2], the tile in work
+        uint64_t* full = reinterpret_cast<uint64_t*>(dcur + TCW * 2);                           // [MAXSLOT]
         int* anyd = reinterpret_cast<int*>(full + MAXSLOT);                                    // [MAXSLOT + 1]: tile has duplicate rows
         int2* fixs = reinterpret_cast<int2*>(anyd + MAXSLOT + 1);                              // [nfix], the fix-up list
         const int ntl = (q.ntiles - bid + q.nctas - 1) / q.nctas;
@@ -1018,7 +1023,7 @@ struct XFwdT {
         g.p = nullptr; g.stride = 0; g.va = g.vb = g.sa = 0; g.dup4 = 0;
         for (int i = 0; i < ntl; ++i) {
             const int slot = i % q.nslot;
-            float* sl = stg + (size_t)slot * TC * q.LS;
+            float* sl = stg + (size_t)slot * TCW * q.LS;
 #if !defined(SPIM_HOST_EMU)
             mbar_wait(full + slot, (unsigned)((i / q.nslot) & 1));
 #endif
@@ -1026,7 +1031,7 @@ struct XFwdT {
             {
                 const int nf = i < q.nslot ? q.nfix : q.nfix_dyn;
                 const uint32_t mg = i < q.nslot ? q.magic_nfix : q.magic_nfix_dyn;
-                SPIM_FOR_ITEMS(it, TC * nf) {
+                SPIM_FOR_ITEMS(it, TCW * nf) {
                     const int b = nf > 1 ? fastdiv(it, mg) : it;
                     const int j = it - b * nf;
                     const int2 f = fixs[j];
@@ -1034,20 +1039,20 @@ struct XFwdT {
                     ln[f.x] = f.y >= 0 ? ln[f.y] : (f.y == -1 ? 0.f : q.cval);
                 }
             }
-            SPIM_FOR_ITEMS(b, TC * 2) dcur[b] = dsto[slot * TC * 2 + b];
+            SPIM_FOR_ITEMS(b, TCW * 2) dcur[b] = dsto[slot * TCW * 2 + b];
             if (SPIM_TID == 0) anyd[MAXSLOT] = anyd[slot];
             SPIM_BARRIER();
-            SPIM_RADIX_SWITCH(pl.radix[0], (xfwdt_stage0<RR>(p, tile, sl, q.LS)))
+            SPIM_RADIX_SWITCH(pl.radix[0], (xfwdt_stage0<RR, W>(p, tile, sl, q.LS)))
 #if !defined(SPIM_HOST_EMU)
             fence_proxy_async();       // this slot's generic-proxy accesses are ordered before the async-proxy refill below
 #endif
             SPIM_BARRIER();
             if (i + q.nslot < ntl) issue(q, bid + (i + q.nslot) * q.nctas, slot, stg, dsto, anyd, full);
-            for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
+            for (int s = 1; s < pl.nstages; ++s) stage_dispatch<false, W>(tg, pl, s, tile, 1, 0, 0, g, 1, 1);
             const int anydup = anyd[MAXSLOT];
-            xfwd_split<2>(p, tile, dcur, N2, anydup);
+            xfwd_split<2, W>(p, tile, dcur, N2, anydup);
             const int npad = p.pitch - (N2 + 1);
-            SPIM_FOR_ITEMS(k, npad * TC) {
+            SPIM_FOR_ITEMS(k, npad * TCW) {
                 const int b = k / (npad > 0 ? npad : 1);
                 const int j = k - b * npad;
                 const long long d_o = dcur[b * 2], d_d = dcur[b * 2 + 1];
@@ -1058,6 +1063,8 @@ struct XFwdT {
         }
     }
 };
+typedef XFwdTW<TP> XFwdT;
+typedef XFwdTW<TP / 2> XFwdTNarrow;      // 8-line tiles: lines so long (1080 voxels and more) that a 16-line tile leaves one block per SM
 
 // ---------------------------------------------------------------------------------------------
 // XInv: half spectrum -> real lines + fused epilogue (specialised at compile time per epilogue mode)

@@ -421,3 +421,24 @@ def test_single_brick_with_rule_filled_halos_equals_plain_session(emu_lib, monke
             brick = s.get_psi()
         plain, *_ = P.run_session(emu_lib, imgs, ws, psfs, 2, 2, 1)
         assert np.abs(brick - plain).max() <= 1e-5 * np.abs(plain).max(), shift
+
+
+def test_eight_line_x_forward_tiles(emu_lib, monkeypatch):
+    """Lines of 1080 voxels and more run 8-line x-forward tiles (three blocks per SM instead of one); forced here on small
+    volumes: same arithmetic per line pair, so not a bit may differ from the 16-line tiles -- every extension rule, odd line
+    counts (partial tiles), de-duplicated and full sweeps, brick-style haloed sources."""
+    syn = __import__("spim_registration_b200").synthetic
+    for shape, k in (((14, 18, 24), 5), ((7, 13, 40), 7), ((12, 40, 16), 9)):
+        _, imgs, ws, psfs = syn.make_dataset(shape, 2, k, kind="beads")
+        for gen in (1, 2):
+            monkeypatch.setenv("SPIM_XFWD_LINES", "16")
+            a, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            monkeypatch.setenv("SPIM_XFWD_LINES", "8")
+            b, *_ = P.run_session(emu_lib, imgs, ws, psfs, O.EFFICIENT_BAYESIAN, gen, 2)
+            assert np.array_equal(a, b), (shape, gen)
+    monkeypatch.setenv("SPIM_XFWD_LINES", "8")
+    for ext in range(5):
+        P.conv_case(emu_lib, (10, 12, 16), (5, 5, 5), ext)
+    for n in (20, 30, 42, 56, 60, 70, 84, 100, 120, 140):
+        P.legacy_case(emu_lib, (4, 4, n), (3, 3, 3), seed=n)
+    P.decon_case(emu_lib, (14, 18, 24), 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
