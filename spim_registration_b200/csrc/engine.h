@@ -15,7 +15,7 @@
 namespace spim {
 
 // host-side launch counters (mvd_debug_counter): [0] column passes launched with narrow tiles, [1] convolutions whose
-// forward sweeps ran de-duplicated, [2] convolutions with a dropped (zero) halo
+// forward sweeps ran de-duplicated, [2] convolutions with a dropped (zero) halo, [3] x-inverse launches with the fused halo push
 inline std::atomic<long long>& debug_counter(int i) { static std::atomic<long long> c[4]; return c[i & 3]; }
 
 // x-inverse launches are timed per epilogue: K_XINV = ratio (conv1), K_XINV_UPDATE = update (conv2), K_XINV_STORE = plain store
@@ -185,6 +185,7 @@ struct EpiDesc {            // what XInv does with the result
     int gen2_quotient = 1;
     float ratio_offset = 0.f;     // EPI_RATIO: added to the stored quotient
     float blur_offset = 0.f;      // EPI_UPDATE: added to the convolution result
+    const HaloFuse* fuse = nullptr;   // brick mode with mapped peers: the epilogue also stores the neighbours' halo voxels (device pointer)
     int exact_tikhonov = 0;
     int fast_epilogue = 1;
     double* stat_sum = nullptr;
@@ -553,7 +554,8 @@ public:
         if (timer) timer->end(id, st);
     }
 
-    void x_inverse(const float2* in, const EpiDesc& e, rt::Stream st) {
+    // returns true when the epilogue also pushed the neighbours' halos (e.fuse given and the fused instantiation applies)
+    bool x_inverse(const float2* in, const EpiDesc& e, rt::Stream st) {
         XInvParams p;
         memset(&p, 0, sizeof(p));
         p.spec = in; p.pitch = pitch; p.Px = P[2]; p.Py = P[1];
@@ -587,6 +589,20 @@ public:
         // built and measured in round 2 (0.325 vs 0.300 ms average) and removed again: its staging slot halves the resident blocks.
         const bool small = smem <= 37 * 1024;
         const int T = small ? 128 : 256;
+        if (e.fuse && p.vec_ok && p.fast_epilogue && !e.exact_tikhonov && (e.epi == EPI_RATIO || e.epi == EPI_UPDATE)) {
+            p.fuse = e.fuse;
+            const size_t sm = smem + kFuseSmemBytes;
+            if (e.epi == EPI_RATIO) {
+                if (small) rt::launch<XInvRatioFastFuse, 192, 4>(p, grid, 192, sm, st);
+                else rt::launch<XInvRatioFastFuse>(p, grid, T, sm, st);
+            } else {
+                if (small) rt::launch<XInvUpdateFastFuse, 128, 5>(p, grid, T, sm, st);
+                else rt::launch<XInvUpdateFastFuse>(p, grid, T, sm, st);
+            }
+            if (timer) timer->end(xinv_id, st);
+            debug_counter(3) += 1;
+            return true;
+        }
         if (e.epi == EPI_STORE) rt::launch<XInvStore>(p, grid, T, smem, st);
         else if (e.epi == EPI_RATIO) {
             if (p.fast_epilogue) {
@@ -606,6 +622,7 @@ public:
         }
         else rt::launch<XInvUpdateIeee>(p, grid, T, smem, st);
         if (timer) timer->end(xinv_id, st);
+        return false;
     }
 
     // spectrum of a (host) kernel, pre-scaled by 1/(4 Px Py Pz), in the layout the mid pass expects
@@ -638,7 +655,7 @@ public:
     }
 
     // out = ext(src) (*) kernel, cropped to the logical image, through the epilogue
-    void convolve(const SrcDesc& src, const float2* khat, const EpiDesc& e, rt::Stream st) {
+    bool convolve(const SrcDesc& src, const float2* khat, const EpiDesc& e, rt::Stream st) {
         Geom g;
         for (int d = 0; d < 3; ++d) { g.n[d] = n[d]; g.hp[d] = hp[d]; g.hm[d] = hm[d]; }
         if (src.ext == EXT_ZERO) {
@@ -673,7 +690,7 @@ public:
         else col_pass(K_YFWD, spec, nullptr, 1, COL_FWD, g, P[1], n[0] + g.hp[0], LZ, P[0], st);
         col_pass(K_ZMID, spec, khat, 0, COL_MID, g, n[0], P[1], P[1], P[1], st);
         col_pass(K_YINV, spec, nullptr, 1, COL_INV, g, n[1], n[0], n[0], P[0], st);
-        x_inverse(spec, e, st);
+        return x_inverse(spec, e, st);
     }
 };
 

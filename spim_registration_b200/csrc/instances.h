@@ -14,6 +14,8 @@ typedef XInvT<EPI_RATIO, MATH_FAST> XInvRatioFast;
 typedef XInvT<EPI_UPDATE, MATH_IEEE> XInvUpdateIeee;
 typedef XInvT<EPI_UPDATE, MATH_FAST> XInvUpdateFast;
 typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
+typedef XInvT<EPI_RATIO, MATH_FAST, true> XInvRatioFastFuse;       // brick mode with mapped peers: the epilogue also stores the neighbours' halo voxels
+typedef XInvT<EPI_UPDATE, MATH_FAST, true> XInvUpdateFastFuse;
 }
 
 // (body, __launch_bounds__ max threads, min blocks per SM): exactly the launches of engine.h
@@ -28,10 +30,12 @@ typedef XInvT<EPI_UPDATE, MATH_EXACT64> XInvUpdateExact64;
 #define SPIM_INSTANCES_X_E(X) X(XInvUpdateIeee, 256, 1) X(XInvUpdateExact64, 256, 1)
 #define SPIM_INSTANCES_X_F(X) X(XFwdT, 256, 3) X(XFwdT, 384, 2) X(XFwdT, 768, 1)
 #define SPIM_INSTANCES_X_G(X) X(XFwdTNarrow, 256, 3) X(XFwdTNarrow, 384, 2)
-#define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "X_A", "X_B", "X_C", "X_D", "X_E", "X_F", "X_G"
+#define SPIM_INSTANCES_X_H(X) X(XInvRatioFastFuse, 256, 1) X(XInvRatioFastFuse, 192, 4)
+#define SPIM_INSTANCES_X_I(X) X(XInvUpdateFastFuse, 256, 1) X(XInvUpdateFastFuse, 128, 5)
+#define SPIM_INSTANCE_GROUPS "COL_A", "COL_B", "COL_C", "COL_D", "X_A", "X_B", "X_C", "X_D", "X_E", "X_F", "X_G", "X_H", "X_I"
 #define SPIM_INSTANCES_ALL(X)                                                                                      \
     SPIM_INSTANCES_COL_A(X) SPIM_INSTANCES_COL_B(X) SPIM_INSTANCES_COL_C(X) SPIM_INSTANCES_COL_D(X)                \
-    SPIM_INSTANCES_X_A(X) SPIM_INSTANCES_X_B(X) SPIM_INSTANCES_X_C(X) SPIM_INSTANCES_X_D(X) SPIM_INSTANCES_X_E(X) SPIM_INSTANCES_X_F(X) SPIM_INSTANCES_X_G(X)
+    SPIM_INSTANCES_X_A(X) SPIM_INSTANCES_X_B(X) SPIM_INSTANCES_X_C(X) SPIM_INSTANCES_X_D(X) SPIM_INSTANCES_X_E(X) SPIM_INSTANCES_X_F(X) SPIM_INSTANCES_X_G(X) SPIM_INSTANCES_X_H(X) SPIM_INSTANCES_X_I(X)
 
 #if defined(SPIM_SPLIT_BUILD) && !defined(SPIM_HOST_EMU)
 namespace spim {

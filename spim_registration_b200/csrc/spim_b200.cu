@@ -527,6 +527,12 @@ struct mvd_session {
         int slot_there[MAX_PIECES], slot_here[MAX_PIECES];
         std::vector<void*> opened;         // cudaIpcOpenMemHandle mappings to close
         long long pushes[2] = {0, 0}, waits[2] = {0, 0};
+        // halo push fused into the x-inverse epilogue (HaloFuse, kernels.h): one descriptor per buffer on the device;
+        // fused_valid[b]: buffer b was last written by a fused epilogue, i.e. the neighbours' halos already hold its faces
+        // and the next push of b only has to raise the flags
+        HaloFuse* d_fuse[2] = {nullptr, nullptr};
+        bool fuse_ok = false;
+        bool fused_valid[2] = {false, false};
     } p2p;
 
     int conv1_ext() const { return prm.conv1_ext >= 0 ? prm.conv1_ext : EXT_MIRROR_SINGLE; }
@@ -663,6 +669,7 @@ struct mvd_session {
         }
         FillK::Params f; f.p = d_psi; f.n = pelems; f.v = (float)avg; f.nblocks = ew_blocks(pelems);
         rt::launch<FillK>(f, f.nblocks, kThreads, 0, stream);
+        p2p.fused_valid[0] = false;
         rt::stream_sync(stream);
         inited = true;
     }
@@ -685,13 +692,15 @@ struct mvd_session {
             src.p = d_psi; src.ext = conv1_ext(); src.ext_value = 0.f;
             e.epi = EPI_RATIO; e.dst = d_tmp; e.img = d_img[v]; e.gen2_quotient = (prm.generation == 2); e.fast_epilogue = prm.fast_epilogue;
             if (shift) e.ratio_offset = -cext;
-            plan.convolve(src, d_kh1[v], e, stream);
+            if (p2p.connected && p2p.fuse_ok) e.fuse = p2p.d_fuse[1];
+            p2p.fused_valid[1] = plan.convolve(src, d_kh1[v], e, stream);
         } else {
             src.p = d_tmp; src.ext = conv2_ext(); src.ext_value = cext;
             if (shift) { src.ext = EXT_ZERO; src.ext_value = 0.f; e.blur_offset = (float)((double)cext * k2sum[v]); }
             e.epi = EPI_UPDATE; e.dst = d_psi; e.weight = d_w[v]; e.const_weight = 1.f;
             e.lambda = prm.lambda; e.stat_sum = d_sum; e.stat_max = d_max; e.exact_tikhonov = prm.exact_tikhonov; e.fast_epilogue = prm.fast_epilogue;
-            plan.convolve(src, d_kh2[v], e, stream);
+            if (p2p.connected && p2p.fuse_ok) e.fuse = p2p.d_fuse[0];
+            p2p.fused_valid[0] = plan.convolve(src, d_kh2[v], e, stream);
         }
     }
 
@@ -711,6 +720,9 @@ static void p2p_disconnect(mvd_session* s) {
     s->p2p.opened.clear();
     s->p2p.connected = false;
     s->p2p.npieces = 0;
+    s->p2p.fuse_ok = false;
+    s->p2p.fused_valid[0] = s->p2p.fused_valid[1] = false;
+    for (int b = 0; b < 2; ++b) { rt::dfree(s->p2p.d_fuse[b]); s->p2p.d_fuse[b] = nullptr; }
 }
 
 // ================================================================================================
@@ -1016,6 +1028,7 @@ int mvd_finish(mvd_session* s) {
         for (int d = 0; d < 3; ++d) { p.pdims[d] = s->pdims[d]; p.porigin[d] = s->porigin[d]; p.n[d] = s->n[d]; }
         p.nblocks = ew_blocks(s->N);
         rt::launch<MaskK>(p, p.nblocks, kThreads, 0, s->stream);
+        s->p2p.fused_valid[0] = false;       // psi changed without the neighbours' halos following
     }
     rt::stream_sync(s->stream);
     return 0;
@@ -1056,6 +1069,7 @@ int mvd_set_psi(mvd_session* s, const float* in) {
     if (!s || !in) return fail("mvd_set_psi: null argument");
     if (!s->d_psi) return fail("mvd_set_psi: session not initialised");
     rt::set_device(s->prm.device);
+    s->p2p.fused_valid[0] = false;
     const size_t bytes = (size_t)s->N * sizeof(float);
     if (!s->prm.haloed) {
         rt::h2d(s->d_psi, in, bytes, s->stream);
@@ -1333,6 +1347,55 @@ int mvd_p2p_connect(mvd_session* s, int npieces, const unsigned char* records, c
     q.npieces = npieces;
     q.connected = true;
     q.pushes[0] = q.pushes[1] = q.waits[0] = q.waits[1] = 0;
+    // Descriptors of the fused push: the x-inverse epilogue stores halo voxels straight into the neighbours' buffers and the
+    // push only raises the flags.  Opt-in (SPIM_BRICK_FUSE=1): correct on hardware (2 B200: oracle parity and the full-size
+    // check pass), but measured SLOWER there -- 13.78 vs 13.30 ms per iteration, the fused epilogue costs the x-inverse
+    // kernels 6 % while one z-face exchange is only 30 us; it can pay only where the exchange is larger (8 bricks: 86 us).  The direction of piece i follows from where its box lands in the
+    // neighbour's buffer: beyond the brick = the neighbour is below me on that axis, before it = above.
+    q.fuse_ok = false;
+    if (env_int("SPIM_BRICK_FUSE", 0) != 0) {
+        HaloFuse h[2];
+        memset(h, 0, sizeof(h));
+        bool ok = (s->porigin[2] % 2 == 0) && (s->pdims[2] % 2 == 0) && (s->n[2] % 2 == 0);
+        int seen_lo = 0, seen_hi = 0;
+        for (int b = 0; b < 2; ++b)
+            for (int d = 0; d < 3; ++d) { h[b].n[d] = s->n[d]; h[b].wlo[d] = s->plan.hm[d]; h[b].whi[d] = s->plan.hp[d]; }
+        for (int i = 0; i < npieces && ok; ++i) {
+            int off[3];
+            for (int d = 0; d < 3; ++d)
+                off[d] = q.dlo[i][d] >= s->porigin[d] + s->n[d] ? -1 : (q.dlo[i][d] < s->porigin[d] ? 1 : 0);
+            const int dir = (off[0] + 1) * 9 + (off[1] + 1) * 3 + (off[2] + 1);
+            if (dir == 13) { ok = false; break; }
+            const long long shift = ((long long)off[0] * s->n[0] * s->pdims[1] + (long long)off[1] * s->n[1]) * s->pdims[2] + (long long)off[2] * s->n[2];
+            for (int b = 0; b < 2; ++b) { h[b].peer[dir] = q.peer_buf[b][i]; h[b].shift[dir] = shift; }
+            for (int d = 0; d < 3; ++d) { if (off[d] < 0) seen_lo |= 1 << d; if (off[d] > 0) seen_hi |= 1 << d; }
+        }
+        // every combination of the axes that have a neighbour must be mapped (a regular grid of bricks provides them)
+        for (int dz = -1; dz <= 1 && ok; ++dz)
+            for (int dy = -1; dy <= 1 && ok; ++dy)
+                for (int dx = -1; dx <= 1 && ok; ++dx) {
+                    if (!dz && !dy && !dx) continue;
+                    const int o[3] = {dz, dy, dx};
+                    bool need = true;
+                    for (int d = 0; d < 3; ++d) if ((o[d] < 0 && !(seen_lo & (1 << d))) || (o[d] > 0 && !(seen_hi & (1 << d)))) need = false;
+                    if (need && !h[0].peer[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)]) ok = false;
+                }
+        // the x pieces travel as pairs (2n, 2n+1): the widened ranges must exist in the neighbours' rows
+        const int lo2 = 2 * ((s->plan.hp[2] + 1) >> 1), hi2 = s->n[2] - 2 * ((s->n[2] - s->plan.hm[2]) >> 1);
+        if ((seen_lo & 4) && s->porigin[2] + s->n[2] + lo2 > s->pdims[2]) ok = false;
+        if ((seen_hi & 4) && s->porigin[2] < hi2) ok = false;
+        for (int d = 0; d < 3; ++d) if (s->n[d] < s->plan.hm[d] + s->plan.hp[d]) ok = false;     // a line is in at most one face region per axis
+        if (ok && (seen_lo | seen_hi)) {
+            for (int b = 0; b < 2; ++b) {
+                h[b].has_lo = seen_lo; h[b].has_hi = seen_hi;
+                q.d_fuse[b] = (HaloFuse*)rt::dmalloc(sizeof(HaloFuse));
+                rt::h2d(q.d_fuse[b], &h[b], sizeof(HaloFuse), s->stream);
+            }
+            rt::stream_sync(s->stream);
+            q.fuse_ok = true;
+        }
+    }
+    q.fused_valid[0] = q.fused_valid[1] = false;
     return 0;
     SPIM_API_END
 }
@@ -1361,8 +1424,14 @@ int mvd_p2p_push(mvd_session* s, int which) {
         p.vsh[i] = vec ? 2 : 0;
         off += vec ? n / 4 : n;
     }
+    if (q.fused_valid[which]) {
+        // the x-inverse epilogue that produced this buffer has already stored every piece at the neighbours: only the flags
+        for (int i = 0; i <= q.npieces; ++i) p.off[i] = 0;
+        off = 0;
+        s->p2p.fused_valid[which] = false;
+    }
     p.off[q.npieces] = off;
-    p.nblocks = ew_blocks(off);
+    p.nblocks = off > 0 ? ew_blocks(off) : 1;
     p.done = s->p2p.d_ctl + 64;
     p.epoch = s->p2p.d_ctl + 65 + which;
     rt::launch<HaloPushK>(p, p.nblocks, kThreads, 0, s->stream);

@@ -41,14 +41,19 @@ def _rank_thread(rank, world, shared, brick, V, ks, typ, gen, iters, lib, data, 
                                                       (8, 2, 2, 7, (8, 9, 10)), (4, 1, 3, 3, (8, 9, 10)),
                                                       # x origin 4, row length 20, x extent 12: the float4 path of the y / z faces
                                                       (8, 2, 2, 7, (8, 8, 12)), (4, 2, 3, 7, (7, 9, 12))])
-def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, typ, ks, brick):
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, typ, ks, brick, fuse):
+    """fuse = 1: the x-inverse epilogue stores the neighbours' halo voxels itself and the push only raises the flags
+    (HaloFuse); fuse = 0: the separate copy + signal kernel."""
     import torch
     import __graft_entry__ as g
     from oracle import mvdecon_oracle as O
     from spim_registration_b200 import bricks, native, synthetic
     monkeypatch.setenv("SPIM_BRICK_P2P", "1")
+    monkeypatch.setenv("SPIM_BRICK_FUSE", fuse)
     torch.set_num_threads(1)
     lib = native.load_library(g.build_emulator())
+    fused_before = lib.mvd_debug_counter(3)
     V, iters = 2, 2
     grid = bricks.grid_for(world)
     gshape = tuple(brick[d] * grid[d] for d in range(3))
@@ -65,6 +70,11 @@ def test_direct_push_bricks_match_whole_volume_oracle(monkeypatch, world, gen, t
     assert not errors, errors
     assert len(out) == world
     assert all(o["used"] for o in out.values()), "a rank fell back from the direct-push path"
+    fused = lib.mvd_debug_counter(3) - fused_before
+    if fuse == "1" and brick[2] % 2 == 0:
+        assert fused >= world * V * 2 * (iters + 1), "the fused halo push was not used"
+    if fuse == "0":
+        assert fused == 0
     assert not any(o["timed_out"] for o in out.values())
     ref = O.deconvolve(imgs, ws, psfs, O.DeconParams(iteration_type=typ, num_iterations=iters + 1, lam=0.006, gen=gen))
     psi = np.zeros(gshape, np.float32)
