@@ -10,7 +10,7 @@
 //                     and therefore sits in the same order).
 //
 // One FFT-convolution = five sweeps, each one read + one write of the volume:
-//   XFwd   real -> half spectrum along x; out-of-bounds extension (mirror / constant / periodic /
+//   XFwdT  real -> half spectrum along x; out-of-bounds extension (mirror / constant / periodic /
 //          zero) is applied on load, the padded volume never exists in memory
 //   ColPass(fwd, y)   in-place column FFT over tiles of 16 x-frequencies
 //   ColPass(mid, z)   forward z-FFT, multiply with the kernel spectrum, inverse z-FFT in one kernel
@@ -19,11 +19,11 @@
 //          (computeQuotient) or the weighted Tikhonov update of psi + change statistics
 //          (computeFinalValues)
 //
-// Every block works on a shared-memory tile [rows][16] of float2.  A stage is a set of independent
-// radix-R butterflies executed in place; the first stage reads its operands straight from global
-// memory and the last one writes straight back, so a tile makes 2(S-1) shared-memory round trips
-// for S stages.  Bodies are written as "phases" of independent items separated by barriers so the
-// same source runs under the CPU emulator used by the unit tests (see hd.h).
+// Every block works on a shared-memory tile [rows][16] of float2 (8-column / 8-line tiles for long axes).  A stage is a set
+// of independent radix-R butterflies on TWO adjacent columns executed in place on packed pairs (fft_math.h: FADD2 / FMUL2 /
+// FFMA2 -- both columns share every butterfly instruction); tiles are staged by TMA (x-forward lines, y tiles) or cp.async
+// (z tiles) and the last stage writes straight back from registers.  Bodies are written as "phases" of independent items
+// separated by barriers so the same source runs under the CPU emulator used by the unit tests (see hd.h).
 #pragma once
 #include "fft_math.h"
 #include "fast_math.h"
@@ -102,25 +102,6 @@ struct GRows {          // the global-memory side of a column tile
 
 SPIM_HD float2 lo2(float4 v) { return make_float2(v.x, v.y); }
 SPIM_HD float2 hi2(float4 v) { return make_float2(v.z, v.w); }
-SPIM_HD float4 pack4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
-
-template <int R, bool INV>
-SPIM_DEV void apply_twiddles2(float2 (&a)[R], float2 (&b)[R], const float2* tw) {
-#pragma unroll
-    for (int p = 1; p < R; ++p) {
-        const float2 w = spim_ldg(tw + (p - 1));
-        a[p] = INV ? cmulc(a[p], w) : cmul(a[p], w);
-        b[p] = INV ? cmulc(b[p], w) : cmul(b[p], w);
-    }
-}
-template <int R, bool INV>
-SPIM_DEV void apply_twiddles1(float2 (&a)[R], const float2* tw) {
-#pragma unroll
-    for (int p = 1; p < R; ++p) {
-        const float2 w = spim_ldg(tw + (p - 1));
-        a[p] = INV ? cmulc(a[p], w) : cmul(a[p], w);
-    }
-}
 
 // twiddles of one butterfly, fetched into registers at the very start of the item so that their L1 / L2
 // latency overlaps the shared-memory loads and the butterfly instead of being exposed right before use
@@ -130,24 +111,14 @@ SPIM_DEV void load_twiddles(float2 (&w)[R], const float2* tw) {
     for (int p = 1; p < R; ++p) w[p] = spim_ldg(tw + (p - 1));
 }
 template <int R, bool INV>
-SPIM_DEV void mul_twiddles2(float2 (&a)[R], float2 (&b)[R], const float2 (&w)[R]) {
-#pragma unroll
-    for (int p = 1; p < R; ++p) {
-        a[p] = INV ? cmulc(a[p], w[p]) : cmul(a[p], w[p]);
-        b[p] = INV ? cmulc(b[p], w[p]) : cmul(b[p], w[p]);
-    }
-}
-template <int R, bool INV>
 SPIM_DEV void mul_twiddles1(float2 (&a)[R], const float2 (&w)[R]) {
 #pragma unroll
     for (int p = 1; p < R; ++p) a[p] = INV ? cmulc(a[p], w[p]) : cmul(a[p], w[p]);
 }
 
-// physical float4 slot of column pair c2 in row `row` (x kernels rotate the pairs so that the
-// transposing first / last phases are conflict-free)
-SPIM_HD int slot_of(int c2, int row, int swz) { return swz ? ((c2 + row) & (TP - 1)) : c2; }
-// the same rotation for a tile row of W pairs: W = 8 (128-byte rows) rotates by the row, W = 4 (64-byte rows, two rows per
-// 128 bytes of banks) by every second row, so that 8 consecutive rows of one pair still cover all eight 16-byte bank groups
+// physical float4 slot of column pair c2 in row `row`: the x kernels rotate the pairs so that their transposing first / last
+// phases are conflict-free.  W = 8 pairs (128-byte rows) rotate by the row, W = 4 (64-byte rows, two rows per 128 bytes of
+// banks) by every second row, so that 8 consecutive rows of one pair still cover all eight 16-byte bank groups
 template <int W> SPIM_HD int xslot(int c2, int row) { return W == 8 ? ((c2 + row) & 7) : ((c2 + (row >> 1)) & 3); }
 
 // twiddle multiply of a packed pair: x[p] *= w[p] (forward) or conj(w[p]) (inverse), w broadcast to both columns
