@@ -948,7 +948,7 @@ struct XFwdTW {
             dsto[(slot * TCW + b) * 2 + 1] = d_dup;
             if (sp) memcpy(stg + ((size_t)slot * TCW + b) * q.LS, sp, q.row_bytes);
         }
-        anyd[slot] = q.dedup;       // (threads of the emulated block write the same value)
+        if (SPIM_TID == 0) anyd[slot] = q.dedup;
 #else
         if (threadIdx.x < 32) {
             const int b = (int)threadIdx.x;

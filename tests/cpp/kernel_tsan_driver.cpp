@@ -22,15 +22,16 @@ static int conv(const int n[3], const int k[3], int ext, std::vector<float>& out
     return mvd_convolve(img.data(), n, ker.data(), k, ext, 1.0f, out.data(), 0);
 }
 
-// mode 0: defaults; 1: narrow column tiles; 2: register-lean instantiations (column pass for radices <= 8, ascending x plan,
-// update kernel for a small stage-0 radix); 3: serpentine sweep order
+// mode 0: defaults (rows of 16 voxels: the TMA-fed x-forward kernel with its fix-up phases, de-duplicated mirror halos,
+// conv2's constant halo by shift); 1: narrow column tiles; 2: 8-line x-forward tiles; 3: full forward sweeps and the
+// literal constant extension; 4: rows that are not 16-byte aligned (the plain-load x-forward kernel)
+static const char* kSwitches[] = {"SPIM_COL_NARROW", "SPIM_XFWD_LINES", "SPIM_DEDUP", "SPIM_CONST_SHIFT"};
 static int decon(int mode, std::vector<float>& psi) {
-    const int n[3] = {10, 12, 14}, kd[3] = {5, 5, 5}, V = 2;
-    const char* all[] = {"SPIM_COL_NARROW", "SPIM_COL_LEAN", "SPIM_XPLAN_ASC", "SPIM_XINV_R0", "SPIM_SERPENTINE"};
-    for (const char* e : all) unsetenv(e);
+    const int n[3] = {10, 12, mode == 4 ? 14 : 16}, kd[3] = {5, 5, 5}, V = 2;
+    for (const char* e : kSwitches) unsetenv(e);
     if (mode == 1) setenv("SPIM_COL_NARROW", "1", 1);
-    if (mode == 2) { setenv("SPIM_COL_LEAN", "1", 1); setenv("SPIM_XPLAN_ASC", "1", 1); setenv("SPIM_XINV_R0", "1", 1); }
-    if (mode == 3) setenv("SPIM_SERPENTINE", "1", 1);
+    if (mode == 2) setenv("SPIM_XFWD_LINES", "8", 1);
+    if (mode == 3) { setenv("SPIM_DEDUP", "0", 1); setenv("SPIM_CONST_SHIFT", "0", 1); }
     mvd_params p;
     mvd_params_default(&p);
     for (int d = 0; d < 3; ++d) p.dims[d] = n[d];
@@ -56,7 +57,8 @@ static int decon(int mode, std::vector<float>& psi) {
 }
 
 int main() {
-    const int shapes[][6] = {{9, 7, 11, 3, 5, 3}, {5, 30, 33, 1, 7, 9}, {6, 6, 6, 4, 2, 6}, {12, 20, 18, 3, 7, 5}, {3, 40, 6, 3, 9, 3}};
+    const int shapes[][6] = {{9, 7, 11, 3, 5, 3}, {5, 30, 33, 1, 7, 9}, {6, 6, 6, 4, 2, 6}, {12, 20, 18, 3, 7, 5}, {3, 40, 6, 3, 9, 3},
+                             {10, 12, 16, 5, 5, 5}, {7, 9, 24, 3, 5, 7}};     // the last two: 16-byte aligned rows (TMA-fed x-forward)
     int fail = 0;
     for (int pass = 0; pass < 2; ++pass) {
         static std::vector<std::vector<float>> ref;
@@ -70,14 +72,14 @@ int main() {
                 else if (memcmp(ref[idx].data(), out.data(), out.size() * 4)) { fprintf(stderr, "threaded result differs (conv %zu)\n", idx); fail = 1; }
                 ++idx;
             }
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 5; ++mode) {
             std::vector<float> psi;
             if (decon(mode, psi)) { fprintf(stderr, "deconvolution failed: %s\n", mvd_last_error()); fail = 1; }
             if (pass == 0) ref.push_back(psi);
             else if (memcmp(ref[idx].data(), psi.data(), psi.size() * 4)) { fprintf(stderr, "threaded result differs (decon mode %d)\n", mode); fail = 1; }
             ++idx;
         }
-        for (const char* e : {"SPIM_COL_NARROW", "SPIM_COL_LEAN", "SPIM_XPLAN_ASC", "SPIM_XINV_R0", "SPIM_SERPENTINE"}) unsetenv(e);
+        for (const char* e : kSwitches) unsetenv(e);
     }
     printf(fail ? "KERNEL_DRIVER_FAILED\n" : "KERNEL_DRIVER_OK\n");
     return fail;

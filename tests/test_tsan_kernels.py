@@ -1,8 +1,9 @@
 """Barrier placement of the FFT-convolution kernels under ThreadSanitizer, without a GPU.  With SPIM_EMU_THREADS=T the kernel
 emulator runs every block of every kernel as T real threads that split the work items like the
 threads of a CUDA block and meet at real barriers (csrc/hd.h, csrc/runtime.h); tests/cpp/kernel_tsan_driver.cpp drives all
-extension rules, narrow tiles, the register-lean instantiations, the serpentine order and a deconvolution with the fused
-update epilogue through the C ABI.  No data race may be reported and the threaded results must equal the single-thread ones
+extension rules (also on 16-byte aligned rows: the TMA-fed x-forward kernel with its fix-up, de-duplication and split phases),
+narrow column tiles, 8-line x-forward tiles, the full / literal forward sweeps and a deconvolution with the fused update
+epilogue through the C ABI.  No data race may be reported and the threaded results must equal the single-thread ones
 bit for bit; the negative control -- the same program with the barrier after a radix stage removed -- must be caught."""
 import os
 import subprocess
