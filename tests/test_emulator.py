@@ -442,3 +442,26 @@ def test_eight_line_x_forward_tiles(emu_lib, monkeypatch):
     for n in (20, 30, 42, 56, 60, 70, 84, 100, 120, 140):
         P.legacy_case(emu_lib, (4, 4, n), (3, 3, 3), seed=n)
     P.decon_case(emu_lib, (14, 18, 24), 3, 5, O.EFFICIENT_BAYESIAN, 2, 3)
+
+
+def test_randomized_work_saving_switches(emu_lib, monkeypatch):
+    """Random shapes (rows of 4 k voxels, so the TMA-fed x-forward kernel runs), kernels up to and beyond the image size, every
+    extension rule: the de-duplicated sweeps and the 8-line tiles must reproduce the full 16-line sweeps bit for bit, and all
+    must agree with the oracle."""
+    from spim_registration_b200 import native
+    rng = np.random.default_rng(20241018)
+    for _ in range(60):
+        shape = (int(rng.integers(1, 20)), int(rng.integers(1, 20)), 4 * int(rng.integers(1, 7)))
+        ks = tuple(int(rng.integers(1, 12)) for _ in range(3))
+        ext = int(rng.integers(0, 5))
+        img = rng.random(shape, dtype=np.float32)
+        k = rng.random(ks, dtype=np.float32)
+        outs = []
+        for dedup, lines in (("1", "16"), ("0", "16"), ("1", "8"), ("0", "8")):
+            monkeypatch.setenv("SPIM_DEDUP", dedup)
+            monkeypatch.setenv("SPIM_XFWD_LINES", lines)
+            outs.append(native.convolve(img, k, ext, 1.0, lib=emu_lib))
+        for o in outs[1:]:
+            assert np.array_equal(outs[0], o), (shape, ks, ext)
+        ref = O.convolve(img, k, ext, value=1.0, dtype=np.float64)
+        assert np.abs(outs[0] - ref).max() <= P.TOL_CONV * np.abs(ref).max(), (shape, ks, ext)
